@@ -1,0 +1,32 @@
+"""CPU oracle for the sparse-GP posterior-gradient EDR path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs (``cpu_baseline`` and
+``--impl reference``) may import this package.  Nothing under ``edrgp_b200/`` imports it; the
+product path raises if its CUDA library is missing instead of falling back to this code.
+
+What it restates
+----------------
+edr-gp's hot path keeps its arithmetic in a third-party dependency, **GPy** (requirement
+``gpy>=1.8.4``, ``/root/reference/requirements.txt:3``; unpinned, no lock file; plus its optimiser
+package ``paramz``).  GPy is not vendored in ``/root/reference`` and is not installable in this
+environment (no wheel, no network).  ``oracle/gpy_restatement.py`` therefore restates GPy's
+*published* algorithm (``GPy.kern.RBF``/``Stationary``, ``GPy.inference.latent_function_inference.
+VarDTC``, ``GPy.core.GP.predictive_gradients``, ``GPy.util.normalizer.Standardize``,
+``paramz`` L-BFGS-B with Logexp transforms) in NumPy FP64 in GPy's operation order, anchored on the
+reference's call sites:
+
+* model construction  ``edrgp/gp_model/regression.py:153-157``
+* fit / optimise      ``edrgp/gp_model/base.py:46-70``
+* posterior gradient  ``edrgp/gp_model/base.py:208-222``
+* SVD of gradients    ``edrgp/utils.py:123-157``; variance ratio ``edrgp/utils.py:27-55``
+
+PARITY UNPINNED at the 1e-8 level: the reference's tests hold no golden vector, known-answer value
+or fixture for this path (``edrgp/tests/test_edr.py`` asserts only |LL_dense - LL_sparse| < 0.5,
+MI > 1 and two rtol=1e-3 invariances).  The restatement is pinned instead by (i) those reference
+tests re-run through the UNMODIFIED reference orchestration layer (``edrgp.edr``/``edrgp.base``/
+``edrgp.utils``, which import fine without GPy) with the oracle estimator plugged in, and (ii)
+mathematical known-answer checks that need no GPy (finite differences, Z = X sparse == dense GP,
+Cholesky chain == direct solve, VFE chain == direct formula, eigh(G^T G) == SVD(G)); see
+``tests/test_oracle.py``.  ``tests/golden/`` holds fixtures generated from this oracle together
+with the unmodified reference L3 by ``tests/golden/make_golden.py``.
+"""
