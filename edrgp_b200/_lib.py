@@ -1,0 +1,58 @@
+"""ctypes binding of libedrgp_b200.so (C ABI declared in include/edrgp_b200.h).
+
+There is NO CPU fallback: if the library is missing, or a call fails, this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libedrgp_b200.so')
+
+_c_dp = ctypes.c_void_p      # device pointers travel as integers
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/edrgp_b200.h one to one
+SIGNATURES = {
+    'edrgp_version': (_int, []),
+    'edrgp_last_error': (ctypes.c_char_p, []),
+    'edrgp_sm_count': (_int, []),
+    'edrgp_pack_bytes': (_sz, [_int, _int]),
+    'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
+    'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp]),
+    'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
+    'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+}
+
+
+class EdrgpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EdrgpError(
+            "libedrgp_b200.so not found at %s: build it with `python -m edrgp_b200.build` "
+            "(there is no CPU fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().edrgp_last_error()
+        raise EdrgpError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ''))

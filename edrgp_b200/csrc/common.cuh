@@ -1,0 +1,76 @@
+// Shared device helpers for the edrgp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edrgp {
+
+constexpr int MT = 32;               // inducing points per streamed tile
+constexpr int WARPS = 8;             // compute warps per CTA
+constexpr int ROWS_PER_WARP = 16;    // two m8 blocks
+constexpr int BM = WARPS * ROWS_PER_WARP;   // 128 data rows per CTA tile
+
+__host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// padded feature count: the k-permutation of the distance GEMM works on groups of 16 features
+__host__ __device__ constexpr int padded_dim(int d) { return round_up(d, 16); }
+// shared-memory row stride (doubles): == 2 (mod 16) makes both DMMA fragment patterns
+// (rows g, cols {0,1,8,9}+2s  and  rows 2t+s, cols g) bank-conflict free for 64-bit loads
+__host__ __device__ constexpr int row_stride(int dp) { return dp + 2; }
+// doubles per packed inducing tile: MT rows + MT x hz + MT x coef
+__host__ __device__ constexpr int pack_tile_doubles(int dp) { return MT * (row_stride(dp) + 2); }
+
+// ---- FP64 tensor core: D(8x8) += A(8x4) * B(4x8); SASS DMMA.8x8x4 ------------------------------
+// lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c0 = C[g][2t], c1 = C[g][2t+1]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS UBLKCP) -----------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// order generic-proxy shared-memory accesses before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace edrgp

@@ -1,0 +1,113 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): kernel entries, gradients and EDR matrices within 1e-8
+relative error in FP64.  The checks below use a max-norm relative error and assert 1e-10 or
+better, i.e. two orders inside the stated tolerance."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import pipeline as op          # noqa: E402  (the checker, never the product)
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda')
+
+
+def _relerr(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+SHAPES = [
+    (500, 10, 20),      # BASELINE config 1
+    (1000, 2, 5),       # tiny d, m < one tile
+    (777, 7, 33),       # odd d, ragged n and m
+    (4096, 32, 256),    # config 2 shape, reduced n
+    (3000, 64, 512),    # config 3 shape, reduced n
+    (1500, 48, 100),
+    (129, 16, 32),
+    (1, 4, 3),          # single row
+]
+
+
+@pytest.mark.parametrize("n,d,m", SHAPES)
+def test_kuf_matches_oracle(n, d, m):
+    from edrgp_b200 import ops
+    w = op.make_workload(max(n, m), d, m, seed=n + d)
+    X, y = w['X'][:n], w['y'][:n]
+    pack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']))
+    K, b = ops.kuf(_dev(X), pack, 1.7, y=_dev(y))
+    Kref = op.kuf_faithful(X, w['Z'], w['ell'], 1.7)
+    assert K.shape == (n, m)
+    assert _relerr(K.cpu().numpy(), Kref) < 1e-12
+    assert _relerr(b.cpu().numpy(), Kref.T.dot(y)) < 1e-11
+
+
+@pytest.mark.parametrize("n,d,m", SHAPES)
+def test_gradients_and_gram_match_oracle(n, d, m):
+    from edrgp_b200 import ops
+    w = op.make_workload(max(n, m), d, m, seed=n + d + 1)
+    X = w['X'][:n]
+    rng = np.random.RandomState(7)
+    alpha = rng.standard_normal(m)
+    sf2, scale = 1.3, 0.7
+    pack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']), _dev(alpha), sf2 * scale)
+    G, C = ops.grad_gram(_dev(X), pack)
+    Gref = op.gradients_faithful(X, w['Z'], w['ell'], sf2, alpha, scale)
+    assert G.shape == (n, d) and C.shape == (d, d)
+    assert _relerr(G.cpu().numpy(), Gref) < 1e-11
+    Cref = Gref.T.dot(Gref)
+    assert _relerr(C.cpu().numpy(), Cref) < 1e-11
+    # gradients never leaving the chip give the same Gram matrix
+    _, C2 = ops.grad_gram(_dev(X), pack, want_G=False)
+    assert torch.equal(C, C2)
+
+
+def test_coincident_points_are_zeroed_like_gpy():
+    """x_i == z_j exactly: GPy's _inv_dist drops the pair; so must the kernel (no NaN, same G)."""
+    from edrgp_b200 import ops
+    w = op.make_workload(600, 8, 40, seed=11)
+    X = w['X'].copy()
+    X[:40] = w['Z']                       # first rows coincide with the inducing points
+    alpha = np.random.RandomState(1).standard_normal(40)
+    pack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']), _dev(alpha), 1.0)
+    G, _ = ops.grad_gram(_dev(X), pack, want_C=False)
+    Gref = op.gradients_faithful(X, w['Z'], w['ell'], 1.0, alpha)
+    assert torch.isfinite(G).all()
+    assert _relerr(G.cpu().numpy(), Gref) < 1e-11
+
+
+def test_far_points_underflow_cleanly():
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((300, 6)) * 50.0
+    Z = rng.standard_normal((16, 6))
+    ell = np.full(6, 0.5)
+    pack = ops.InducingPack(_dev(Z), _dev(ell))
+    K, _ = ops.kuf(_dev(X), pack, 1.0)
+    Kref = op.kuf_faithful(X, Z, ell, 1.0)
+    assert torch.isfinite(K).all()
+    assert np.max(np.abs(K.cpu().numpy() - Kref)) < 1e-300 + 1e-12 * np.max(Kref)
+
+
+def test_full_size_linearity_property():
+    """At a BASELINE-sized row count the oracle is too slow; use linearity in alpha instead:
+    G(a1 + a2) == G(a1) + G(a2) and C is the Gram matrix of the G the kernel wrote."""
+    from edrgp_b200 import ops
+    n, d, m = 200_000, 64, 512
+    g = torch.Generator(device='cuda').manual_seed(5)
+    X = torch.randn(n, d, dtype=torch.float64, device='cuda', generator=g)
+    Z = X[torch.randperm(n, device='cuda', generator=g)[:m]].contiguous()
+    ell = torch.full((d,), 8.0, dtype=torch.float64, device='cuda') * (1 + 0.5 * torch.rand(d, dtype=torch.float64, device='cuda', generator=g))
+    a1 = torch.randn(m, dtype=torch.float64, device='cuda', generator=g)
+    a2 = torch.randn(m, dtype=torch.float64, device='cuda', generator=g)
+    pack = ops.InducingPack(Z, ell, a1, 1.0)
+    G1, _ = ops.grad_gram(X, pack, want_C=False)
+    G2, _ = ops.grad_gram(X, pack.set_coef(a2, 1.0), want_C=False)
+    G12, C12 = ops.grad_gram(X, pack.set_coef(a1 + a2, 1.0))
+    err = (G12 - (G1 + G2)).abs().max() / G12.abs().max()
+    assert float(err) < 1e-12
+    Cref = G12.T @ G12
+    assert float((C12 - Cref).abs().max() / Cref.abs().max()) < 1e-12
