@@ -89,4 +89,56 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_gram");
 }
 
+size_t edrgp_syrk_workspace_bytes(int64_t n, int k) {
+  int sms = sm_count_cached();
+  if (sms <= 0) sms = 160;
+  return edrgp::syrk_workspace_bytes(n, k, sms);
+}
+
+int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, void* workspace,
+               void* stream) {
+  if (!A || !C || !workspace || n <= 0 || k <= 0 || lda < k || ldc < k) return fail(EDRGP_ERR_ARG, "syrk: bad argument");
+  if ((lda & 1) || !aligned16(A)) return fail(EDRGP_ERR_ARG, "syrk: lda must be even and A 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "syrk: no CUDA device");
+  cudaError_t e = edrgp::launch_syrk(A, n, k, lda, C, ldc, (double*)workspace, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "syrk");
+}
+
+int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, double jitter, double* Kmm,
+              int64_t ldk, void* stream) {
+  int rc = check_x("kmm", Zp, m, d, pack, m);
+  if (rc) return rc;
+  if (!Kmm || ldk < m || (ldk & 1) || !aligned16(Kmm))
+    return fail(EDRGP_ERR_ARG, "kmm: Kmm must be 16-byte aligned with an even leading dimension >= m");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kmm: no CUDA device");
+  cudaError_t e = edrgp::launch_kuf(Zp, m, d, pack, m, sf2, Kmm, ldk, nullptr, nullptr, sms, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = edrgp::launch_kmm_fix(Kmm, m, ldk, sf2, jitter, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kmm");
+}
+
+size_t edrgp_solve_workspace_bytes(int m) { return (size_t)2 * m * m * sizeof(double); }
+
+int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* LB, double* alpha,
+                double* c, double* scalars, int* info, void* workspace, void* stream) {
+  if (!Kmm || !P || !b || !LB || !alpha || !c || !scalars || !info || !workspace || m <= 0)
+    return fail(EDRGP_ERR_ARG, "solve: bad argument");
+  cudaError_t e = edrgp::launch_solve(Kmm, P, b, m, beta, LB, alpha, c, scalars, info, (double*)workspace,
+                                      (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "solve");
+}
+
+int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream) {
+  if (!L || !B || m <= 0 || nrhs <= 0) return fail(EDRGP_ERR_ARG, "trsm: bad argument");
+  cudaError_t e = edrgp::launch_trsm(L, m, m, B, nrhs, nrhs, trans, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "trsm");
+}
+
+int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace, void* stream) {
+  if (!C || !evals || !comps || !workspace || d <= 0) return fail(EDRGP_ERR_ARG, "eigh: bad argument");
+  cudaError_t e = edrgp::launch_eigh(C, d, (double*)workspace, evals, comps, sweeps, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "eigh");
+}
+
 }  // extern "C"

@@ -13,4 +13,16 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
 cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
                        int64_t ldk, const double* y, double* b, int sms, cudaStream_t st);
 
+size_t syrk_workspace_bytes(int64_t n, int k, int sms);
+cudaError_t launch_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, double* workspace,
+                        int sms, cudaStream_t st);
+cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t st);
+cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
+                        cudaStream_t st);
+cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitter, cudaStream_t st);
+cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* Bmat,
+                         double* alpha, double* cvec, double* scalars, int* info, double* workspace,
+                         cudaStream_t st);
+cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st);
+
 }  // namespace edrgp

@@ -96,3 +96,75 @@ def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
         if C is not None:
             C = C[:d_user, :d_user].contiguous()
     return G, C
+
+
+def syrk(A, k=None):
+    """C = A[:, :k]^T A[:, :k] for a tall (n, lda) tensor (lda even)."""
+    lib = _lib.load()
+    _need_cuda(A)
+    n, lda = A.shape
+    k = lda if k is None else k
+    if lda % 2:
+        raise ValueError("syrk needs an even leading dimension")
+    C = torch.empty(k, k, dtype=F64, device=A.device)
+    ws = torch.empty(max(1, lib.edrgp_syrk_workspace_bytes(n, k) // 8), dtype=F64, device=A.device)
+    _lib.check(lib.edrgp_syrk(_ptr(A), n, k, lda, _ptr(C), k, _ptr(ws), _stream()), 'edrgp_syrk')
+    return C
+
+
+def kmm(pack, sf2, jitter=1e-8):
+    """Kuu = K(Z, Z) + jitter I with GPy's exact-sf2 diagonal."""
+    lib = _lib.load()
+    m = pack.m
+    ldk = m + (m & 1)
+    K = torch.empty(m, ldk, dtype=F64, device=pack.buf.device)
+    _lib.check(lib.edrgp_kmm(_ptr(pack.Z), _ptr(pack.buf), m, pack.d, float(sf2), float(jitter), _ptr(K), ldk,
+                             _stream()), 'edrgp_kmm')
+    return K if ldk == m else K[:, :m].contiguous()
+
+
+class SolveResult(object):
+    __slots__ = ('alpha', 'c', 'Lm', 'LB', 'scalars', 'info')
+
+
+def solve(Kmm, P, b, beta):
+    """VarDTC solve chain on the device.  Kmm is consumed (overwritten by its Cholesky factor)."""
+    lib = _lib.load()
+    _need_cuda(Kmm, P, b)
+    m = Kmm.shape[0]
+    dev = Kmm.device
+    out = SolveResult()
+    out.Lm = Kmm
+    out.LB = torch.empty(m, m, dtype=F64, device=dev)
+    out.alpha = torch.empty(m, dtype=F64, device=dev)
+    out.c = torch.empty(m, dtype=F64, device=dev)
+    out.scalars = torch.empty(4, dtype=F64, device=dev)
+    out.info = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.edrgp_solve_workspace_bytes(m) // 8, dtype=F64, device=dev)
+    _lib.check(lib.edrgp_solve(_ptr(Kmm), _ptr(P), _ptr(b), m, float(beta), _ptr(out.LB), _ptr(out.alpha),
+                               _ptr(out.c), _ptr(out.scalars), _ptr(out.info), _ptr(ws), _stream()), 'edrgp_solve')
+    return out
+
+
+def trsm(L, B, trans=False):
+    """In-place triangular solve with a lower factor: L X = B (trans=False) or L^T X = B."""
+    lib = _lib.load()
+    _need_cuda(L, B)
+    m = L.shape[0]
+    nrhs = 1 if B.dim() == 1 else B.shape[1]
+    _lib.check(lib.edrgp_trsm(_ptr(L), m, _ptr(B), nrhs, int(bool(trans)), _stream()), 'edrgp_trsm')
+    return B
+
+
+def eigh(C):
+    """Descending eigen-decomposition of a symmetric (d, d) matrix: (evals, comps) with comps rows
+    = eigenvectors.  C is not modified."""
+    lib = _lib.load()
+    _need_cuda(C)
+    d = C.shape[0]
+    A = C.clone()
+    evals = torch.empty(d, dtype=F64, device=C.device)
+    comps = torch.empty(d, d, dtype=F64, device=C.device)
+    ws = torch.empty(d * d, dtype=F64, device=C.device)
+    _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
+    return evals, comps

@@ -78,6 +78,53 @@ size_t edrgp_grad_gram_workspace_bytes(int d);
 int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m,
                     double* G, double* C, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K2 / K5  C = A^T A for a tall row-major A (n, lda), k columns (k <= lda, lda even, A 16-byte
+ * aligned).  Replaces GPy tdot (dsyrk) inside VarDTC.inference for P = Kuf Kfu
+ * (edrgp/gp_model/base.py:69) and the Gram matrix of the gradients when d > 64
+ * (edrgp/utils.py:140).  C (k, ldc) is overwritten, full symmetric.
+ * ------------------------------------------------------------------------------------------- */
+size_t edrgp_syrk_workspace_bytes(int64_t n, int k);
+int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc,
+               void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kuu = K(Z, Z) with the diagonal forced to sf2 + jitter (GPy Stationary._unscaled_dist zeroes the
+ * diagonal distance; VarDTC adds const_jitter = 1e-8).  Zp is the (m, d) inducing matrix with d
+ * even (as stored by the host pack), `pack` built with coef = NULL.  Kmm is (m, ldk) row-major
+ * with ldk even and >= m (rows are written with 16-byte stores).
+ * ------------------------------------------------------------------------------------------- */
+int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, double jitter,
+              double* Kmm, int64_t ldk, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  the m x m solve chain of GPy VarDTC.inference, driven by the n-reduced statistics
+ * (edrgp/gp_model/base.py:69):
+ *     Lm = chol(Kmm);  A = beta Lm^-1 P Lm^-T;  LB = chol(I + A);
+ *     c = LB^-1 Lm^-1 (beta b);  alpha = Lm^-T LB^-T c            (GPy woodbury_vector)
+ * In:  Kmm (m, m) -- OVERWRITTEN by Lm (lower triangle);  P (m, m);  b (m);  beta = 1 / noise.
+ * Out: LB (m, m) lower triangle;  alpha (m);  c (m);
+ *      scalars[0] = tr(A), scalars[1] = sum log diag(LB), scalars[2] = c^T c;
+ *      info[0], info[1]: 0 or 1 + index of the first non-positive pivot of chol(Kmm) / chol(I + A).
+ * workspace: edrgp_solve_workspace_bytes(m).
+ * ------------------------------------------------------------------------------------------- */
+size_t edrgp_solve_workspace_bytes(int m);
+int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* LB,
+                double* alpha, double* c, double* scalars, int* info, void* workspace, void* stream);
+
+/* lower-triangular solves with a factor from edrgp_solve: trans = 0: L X = B, 1: L^T X = B;
+ * B (m, nrhs) row-major, overwritten.  (GPy dtrtrs.) */
+int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  symmetric eigendecomposition of the d x d EDR matrix C = G^T G (cyclic Jacobi).
+ * Replaces np.linalg.svd(G) in SVDTransformer.fit (edrgp/utils.py:140): comps rows are the right
+ * singular vectors of G, evals = S^2, descending.  C is destroyed.  workspace: d*d doubles.
+ * sweeps (device int, may be NULL) receives the number of Jacobi sweeps used.
+ * ------------------------------------------------------------------------------------------- */
+int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

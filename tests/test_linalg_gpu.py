@@ -1,0 +1,105 @@
+"""Parity of the m x m solve chain, SYRK and the Jacobi eigensolver against the CPU oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import pipeline as op          # noqa: E402
+from oracle import gpy_restatement as gpy  # noqa: E402
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda')
+
+
+def _relerr(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("n,k", [(1000, 20), (5000, 256), (20000, 512), (777, 34), (333, 130), (50000, 128)])
+def test_syrk_matches_numpy(n, k):
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(n + k)
+    A = rng.standard_normal((n, k))
+    C = ops.syrk(_dev(A)).cpu().numpy()
+    ref = A.T.dot(A)
+    assert _relerr(C, ref) < 1e-12
+    assert np.array_equal(C, C.T)
+
+
+@pytest.mark.parametrize("n,d,m", [(500, 10, 20), (2000, 6, 25), (4096, 32, 256), (3000, 64, 512), (900, 7, 33)])
+def test_stats_and_solve_match_oracle(n, d, m):
+    from edrgp_b200 import ops
+    w = op.make_workload(n, d, m, seed=n + m)
+    X, y, Z, ell, sf2, noise = w['X'], w['y'], w['Z'], w['ell'], 1.2, w['noise']
+    pack = ops.InducingPack(_dev(Z), _dev(ell))
+    K, b = ops.kuf(_dev(X), pack, sf2, y=_dev(y))
+    Kfull = K if K.is_contiguous() else None
+    # P through the SYRK kernel on the stored Kfu (even leading dimension)
+    ldk = m + (m & 1)
+    Kbuf = torch.zeros(n, ldk, dtype=torch.float64, device='cuda')
+    Kbuf[:, :m] = K
+    P = ops.syrk(Kbuf, m)
+    Pref, bref, yy = op.inducing_stats_chunked(X, y, Z, ell, sf2)
+    assert _relerr(P.cpu().numpy(), Pref) < 1e-11
+    assert _relerr(b.cpu().numpy(), bref) < 1e-11
+    Kmm = ops.kmm(pack, sf2)
+    Kmm_ref = op.kuu(Z, ell, sf2)
+    assert _relerr(Kmm.cpu().numpy(), Kmm_ref) < 1e-12
+    res = ops.solve(Kmm, P, b, 1.0 / noise)
+    torch.cuda.synchronize()
+    assert res.info.cpu().tolist() == [0, 0]
+    ref = op.solve_from_stats(Kmm_ref, Pref, bref, yy, n, sf2, noise)
+    # alpha amplifies rounding by cond(Kuu + beta P); compare what the path consumes: mu = Kfu alpha
+    mu = K.cpu().numpy().dot(res.alpha.cpu().numpy())
+    mu_ref = op.kuf_faithful(X, Z, ell, sf2).dot(ref['alpha'])
+    assert _relerr(mu, mu_ref) < 1e-8
+    sc = res.scalars.cpu().numpy()
+    assert abs(sc[0] - np.trace(ref['A'])) < 1e-9 * abs(np.trace(ref['A']))
+    assert abs(sc[1] - np.sum(np.log(np.diag(ref['LB'])))) < 1e-9 * abs(np.sum(np.log(np.diag(ref['LB']))))
+    beta = 1.0 / noise
+    bound = (-0.5 * n * (np.log(2 * np.pi) - np.log(beta)) - 0.5 * beta * yy - 0.5 * (beta * n * sf2 - sc[0])
+             - sc[1] + 0.5 * sc[2])
+    assert abs(bound - ref['bound']) < 1e-9 * abs(ref['bound'])
+    # Cholesky factors themselves
+    Lm = np.tril(res.Lm.cpu().numpy())
+    assert _relerr(Lm, ref['Lm']) < 1e-9
+
+
+@pytest.mark.parametrize("m,nrhs", [(20, 1), (100, 7), (512, 512), (33, 65)])
+def test_trsm(m, nrhs):
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(m)
+    A = rng.standard_normal((m, m)); A = A.dot(A.T) + m * np.eye(m)
+    L = np.linalg.cholesky(A)
+    B = rng.standard_normal((m, nrhs))
+    for trans in (False, True):
+        X = ops.trsm(_dev(L), _dev(B), trans).cpu().numpy()
+        ref = gpy.dtrtrs(L, B, lower=1, trans=int(trans))
+        assert _relerr(X, ref) < 1e-11
+
+
+def test_potrf_reports_indefinite():
+    from edrgp_b200 import ops
+    A = np.eye(40); A[17, 17] = -1.0
+    res = ops.solve(_dev(A), _dev(np.zeros((40, 40))), _dev(np.zeros(40)), 1.0)
+    torch.cuda.synchronize()
+    assert res.info.cpu().tolist()[0] == 18
+
+
+@pytest.mark.parametrize("d", [2, 3, 10, 32, 64, 65, 128, 200])
+def test_eigh_matches_lapack(d):
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(d)
+    G = rng.standard_normal((3 * d + 5, d)) * np.linspace(3.0, 0.1, d)
+    C = G.T.dot(G)
+    evals, comps = ops.eigh(_dev(C))
+    evals, comps = evals.cpu().numpy(), comps.cpu().numpy()
+    lam = np.linalg.eigvalsh(C)[::-1]
+    assert np.allclose(evals, lam, rtol=1e-12, atol=1e-12 * lam[0])
+    assert np.max(np.abs(comps.dot(comps.T) - np.eye(d))) < 1e-12
+    assert np.max(np.abs(comps.dot(C).dot(comps.T) - np.diag(evals))) < 1e-11 * lam[0]
+    k = min(3, d)
+    cref, _, _ = op.edr_from_gram(C, k)
+    assert op.principal_angle(comps[:k], cref) < 1e-6
