@@ -21,7 +21,7 @@ SIGNATURES = {
     'edrgp_sm_count': (_int, []),
     'edrgp_pack_bytes': (_sz, [_int, _int]),
     'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
-    'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp]),
+    'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
     'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_syrk_workspace_bytes': (_sz, [_i64, _int]),
@@ -31,6 +31,10 @@ SIGNATURES = {
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_trsm': (_int, [_c_dp, _int, _c_dp, _int, _int, _c_dp]),
     'edrgp_eigh': (_int, [_c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_col_moments_workspace_bytes': (_sz, [_int]),
+    'edrgp_col_moments': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_standardize': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
 }
 
 

@@ -57,14 +57,14 @@ static int check_x(const char* who, const double* X, int64_t n, int d, const dou
 }
 
 int edrgp_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu, int64_t ldk,
-              const double* y, double* b, void* stream) {
+              const double* y, double* b, double* mu, void* stream) {
   int rc = check_x("kuf", X, n, d, pack, m);
   if (rc) return rc;
   if (Kfu && (ldk < m || (ldk & 1) || !aligned16(Kfu))) return fail(EDRGP_ERR_ARG, "kuf: ldk must be even, >= m; Kfu 16-byte aligned");
   if ((y == nullptr) != (b == nullptr)) return fail(EDRGP_ERR_ARG, "kuf: y and b go together");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kuf: no CUDA device");
-  cudaError_t e = edrgp::launch_kuf(X, n, d, pack, m, sf2, Kfu, ldk, y, b, sms, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_kuf(X, n, d, pack, m, sf2, Kfu, ldk, y, b, mu, sms, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf");
 }
 
@@ -113,7 +113,7 @@ int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, do
     return fail(EDRGP_ERR_ARG, "kmm: Kmm must be 16-byte aligned with an even leading dimension >= m");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kmm: no CUDA device");
-  cudaError_t e = edrgp::launch_kuf(Zp, m, d, pack, m, sf2, Kmm, ldk, nullptr, nullptr, sms, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_kuf(Zp, m, d, pack, m, sf2, Kmm, ldk, nullptr, nullptr, nullptr, sms, (cudaStream_t)stream);
   if (e == cudaSuccess) e = edrgp::launch_kmm_fix(Kmm, m, ldk, sf2, jitter, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kmm");
 }
@@ -139,6 +139,39 @@ int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void
   if (!C || !evals || !comps || !workspace || d <= 0) return fail(EDRGP_ERR_ARG, "eigh: bad argument");
   cudaError_t e = edrgp::launch_eigh(C, d, (double*)workspace, evals, comps, sweeps, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "eigh");
+}
+
+size_t edrgp_col_moments_workspace_bytes(int d) {
+  int sms = sm_count_cached();
+  if (sms <= 0) sms = 160;
+  return edrgp::col_moments_workspace_bytes(d, sms);
+}
+
+int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, double* out, void* workspace,
+                      void* stream) {
+  if (!X || !out || !workspace || n <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "col_moments: bad argument");
+  if (d > 512) return fail(EDRGP_ERR_UNSUPPORTED, "col_moments: d > 512");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "col_moments: no CUDA device");
+  cudaError_t e = edrgp::launch_col_moments(X, n, d, shift, out, (double*)workspace, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "col_moments");
+}
+
+int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,
+                      void* stream) {
+  if (!X || !mean || !scale || !out || n <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "standardize: bad argument");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "standardize: no CUDA device");
+  cudaError_t e = edrgp::launch_standardize(X, n, d, mean, scale, out, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "standardize");
+}
+
+int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, double* out, void* stream) {
+  if (!X || !V || !out || n <= 0 || d <= 0 || k <= 0) return fail(EDRGP_ERR_ARG, "project: bad argument");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "project: no CUDA device");
+  cudaError_t e = edrgp::launch_project(X, n, d, V, k, out, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "project");
 }
 
 }  // extern "C"

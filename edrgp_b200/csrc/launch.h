@@ -11,7 +11,7 @@ bool grad_gram_fused(int d);
 cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pack, int m, double* G, double* C,
                              double* Cpart, int sms, cudaStream_t st);
 cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
-                       int64_t ldk, const double* y, double* b, int sms, cudaStream_t st);
+                       int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st);
 
 size_t syrk_workspace_bytes(int64_t n, int k, int sms);
 cudaError_t launch_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, double* workspace,
@@ -24,5 +24,13 @@ cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, d
                          double* alpha, double* cvec, double* scalars, int* info, double* workspace,
                          cudaStream_t st);
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st);
+
+size_t col_moments_workspace_bytes(int d, int sms);
+cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, double* out, double* workspace,
+                               int sms, cudaStream_t st);
+cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,
+                               int sms, cudaStream_t st);
+cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, int k, double* out, int sms,
+                           cudaStream_t st);
 
 }  // namespace edrgp

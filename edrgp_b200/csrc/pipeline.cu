@@ -94,6 +94,7 @@ struct PipeParams {
   int m;
   const double* y;
   double* b;
+  double* mu;       // kuf only: mu_i = sum_j K_ij coef_j (posterior mean when coef = alpha)
 };
 
 // Producer warp: streams the X row tiles and the inducing tiles of every row tile of this CTA.
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
     const bool v0 = ra < p.n, v1 = rb < p.n;
     double y0 = 0.0, y1 = 0.0;
     if (p.y != nullptr) { if (v0) y0 = p.y[ra]; if (v1) y1 = p.y[rb]; }
+    double mu0 = 0.0, mu1 = 0.0;
     for (int mt = 0; mt < p.mtiles; ++mt) {
       const double* zt = zbuf + (size_t)zs * L::TILE;
       mbar_wait(&zfull[zs], zph);
@@ -416,6 +418,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)) * c.x, k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0)) * c.y;
         double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)) * c.x, k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0)) * c.y;
+        mu0 += k00 + k01; mu1 += k10 + k11;
         if (p.Kfu != nullptr) {
           // ldk even (host guarantees) and j even -> 16-byte stores
           if (j + 1 < p.m) {
@@ -440,6 +443,11 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
       __syncwarp();
       if (lane == 0) mbar_arrive(&zempty[zs]);
       if (++zs == NS) { zs = 0; zph ^= 1; }
+    }
+    if (p.mu != nullptr) {
+      mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
+      mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
+      if (t == 0) { if (v0) p.mu[ra] = mu0; if (v1) p.mu[rb] = mu1; }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&xempty[xs]);
@@ -516,10 +524,10 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
 }
 
 cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
-                       int64_t ldk, const double* y, double* b, int sms, cudaStream_t st) {
+                       int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st) {
   PipeParams p{};
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
-  p.ntiles = (n + BM - 1) / BM; p.sf2 = sf2; p.Kfu = Kfu; p.ldk = ldk; p.m = m; p.y = y; p.b = b;
+  p.ntiles = (n + BM - 1) / BM; p.sf2 = sf2; p.Kfu = Kfu; p.ldk = ldk; p.m = m; p.y = y; p.b = b; p.mu = mu;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
   switch (padded_dim(d)) {
     case 16: return launch_kuf_t<16, 2, 4>(p, grid, st);

@@ -56,8 +56,9 @@ class InducingPack(object):
         return self
 
 
-def kuf(X, pack, sf2, y=None, out=None, want_K=True):
-    """Kfu (n, m) and, if y is given, b = Kfu^T y."""
+def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
+    """Kfu (n, m) and, if y is given, b = Kfu^T y.  want_mu: returns (K, b, mu) with
+    mu = Kfu @ coef (the coefficients stored in the pack)."""
     lib = _lib.load()
     X = pad_even(X)
     _need_cuda(X, y)
@@ -67,10 +68,13 @@ def kuf(X, pack, sf2, y=None, out=None, want_K=True):
     if want_K:
         K = out if out is not None else torch.empty(n, ldk, dtype=F64, device=X.device)
     b = torch.zeros(pack.m, dtype=F64, device=X.device) if y is not None else None
+    mu = torch.empty(n, dtype=F64, device=X.device) if want_mu else None
     _lib.check(lib.edrgp_kuf(_ptr(X), n, X.shape[1], _ptr(pack.buf), pack.m, float(sf2), _ptr(K), ldk,
-                             _ptr(y), _ptr(b), _stream()), 'edrgp_kuf')
+                             _ptr(y), _ptr(b), _ptr(mu), _stream()), 'edrgp_kuf')
     if K is not None and ldk != pack.m:
         K = K[:, :pack.m]
+    if want_mu:
+        return K, b, mu
     return K, b
 
 
@@ -168,3 +172,39 @@ def eigh(C):
     ws = torch.empty(d * d, dtype=F64, device=C.device)
     _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
     return evals, comps
+
+
+def col_moments(X, shift=None):
+    """(sum_i (x - shift), sum_i (x - shift)^2) per column, each of shape (d,)."""
+    lib = _lib.load()
+    if X.dim() == 1:
+        X = X[:, None]
+    _need_cuda(X, shift)
+    n, d = X.shape
+    out = torch.empty(2 * d, dtype=F64, device=X.device)
+    ws = torch.empty(lib.edrgp_col_moments_workspace_bytes(d) // 8, dtype=F64, device=X.device)
+    _lib.check(lib.edrgp_col_moments(_ptr(X), n, d, _ptr(shift), _ptr(out), _ptr(ws), _stream()),
+               'edrgp_col_moments')
+    return out[:d], out[d:]
+
+
+def standardize(X, mean, scale, out=None):
+    lib = _lib.load()
+    X2 = X[:, None] if X.dim() == 1 else X
+    _need_cuda(X2, mean, scale)
+    n, d = X2.shape
+    res = torch.empty_like(X2) if out is None else out
+    _lib.check(lib.edrgp_standardize(_ptr(X2), n, d, _ptr(mean), _ptr(scale), _ptr(res), _stream()),
+               'edrgp_standardize')
+    return res[:, 0] if X.dim() == 1 else res
+
+
+def project(X, V):
+    """X (n, d) @ V^T with V (k, d): EDR.transform."""
+    lib = _lib.load()
+    _need_cuda(X, V)
+    n, d = X.shape
+    k = V.shape[0]
+    out = torch.empty(n, k, dtype=F64, device=X.device)
+    _lib.check(lib.edrgp_project(_ptr(X), n, d, _ptr(V), k, _ptr(out), _stream()), 'edrgp_project')
+    return out

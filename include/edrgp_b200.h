@@ -57,11 +57,13 @@ int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, 
 /* ---------------------------------------------------------------------------------------------
  * K1  cross-covariance  Kfu = sf2 * exp(-0.5 * clip(|x/l|^2 + |z/l|^2 - 2 (x/l).(z/l), 0)).
  * Replaces GPy RBF.K(X, Z) (edrgp/gp_model/base.py:69 through VarDTC.inference, and :187).
- * Kfu is (n, ldk) row-major with ldk >= m.  Also optionally accumulates b += Kfu^T y (y may be
- * NULL).  b must be zeroed by the caller.
+ * Kfu is (n, ldk) row-major with ldk >= m, ldk even; may be NULL.  Optionally accumulates
+ * b += Kfu^T y (y, b may be NULL; b must be zeroed by the caller) and writes the row sums
+ * mu_i = sum_j Kfu_ij coef_j (mu may be NULL) -- with coef = alpha in the pack this is the posterior
+ * mean K(x, Z) alpha of GPy Posterior._raw_predict (edrgp/gp_model/base.py:187).
  * ------------------------------------------------------------------------------------------- */
 int edrgp_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2,
-              double* Kfu, int64_t ldk, const double* y, double* b, void* stream);
+              double* Kfu, int64_t ldk, const double* y, double* b, double* mu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1+K4+K5 fused  posterior-mean gradients and their outer product.
@@ -124,6 +126,24 @@ int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* str
  * ------------------------------------------------------------------------------------------- */
 int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace,
                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Streaming row kernels around the path (HBM-bound).
+ *  edrgp_col_moments: out[q] = sum_i (x_iq - shift_q), out[d + q] = sum_i (x_iq - shift_q)^2
+ *      (shift may be NULL).  Two calls give the mean and the centred second moment of
+ *      StandardScaler (edrgp/edr.py:161-162) and of GPy's Standardize on y; the sums are what an
+ *      n-sharded run all-reduces.  d <= 512.
+ *  edrgp_standardize: out = (X - mean) / scale, elementwise by column (in place allowed).
+ *  edrgp_project:     out (n, k) = X (n, d) V^T, V (k, d) row-major: EDR.transform
+ *      (edrgp/edr.py:261-289, edrgp/base.py:462).
+ * ------------------------------------------------------------------------------------------- */
+size_t edrgp_col_moments_workspace_bytes(int d);
+int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, double* out,
+                      void* workspace, void* stream);
+int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale,
+                      double* out, void* stream);
+int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, double* out,
+                  void* stream);
 
 #ifdef __cplusplus
 }
