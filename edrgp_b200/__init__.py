@@ -2,5 +2,12 @@
 
 Drop-in for edr-gp's ``SparseGaussianProcessRegressor`` + ``SVDTransformer`` +
 ``EffectiveDimensionalityReduction`` on that path; see DESIGN.md and INTEGRATION.md.
+The CUDA library (``libedrgp_b200.so``, C ABI in ``include/edrgp_b200.h``) is loaded on first use;
+there is no CPU fallback.
 """
 __version__ = '0.1.0'
+
+from .gp_model import SparseGaussianProcessRegressor          # noqa: F401
+from .transformer import GramEighTransformer                  # noqa: F401
+from .edr import EffectiveDimensionalityReduction, EDR        # noqa: F401
+from .utils import discrepancy, subspace_variance_ratio_from_gram   # noqa: F401

@@ -25,14 +25,20 @@ SIGNATURES = {
     'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
     'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_syrk_workspace_bytes': (_sz, [_i64, _int]),
-    'edrgp_syrk': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _c_dp, _c_dp]),
+    'edrgp_syrk': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_inducing_stats': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _c_dp, _i64, _c_dp, _int, _c_dp, _c_dp]),
+    'edrgp_gemm_tn_workspace_bytes': (_sz, [_i64, _int, _int]),
+    'edrgp_gemm_tn': (_int, [_c_dp, _i64, _int, _c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
     'edrgp_kmm': (_int, [_c_dp, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _c_dp]),
     'edrgp_solve_workspace_bytes': (_sz, [_int]),
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_trsm': (_int, [_c_dp, _int, _c_dp, _int, _int, _c_dp]),
     'edrgp_eigh': (_int, [_c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_col_moments_workspace_bytes': (_sz, [_int]),
-    'edrgp_col_moments': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_col_moments': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp]),
+    'edrgp_weights_workspace_bytes': (_sz, [_i64, _int]),
+    'edrgp_weights': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _c_dp, _c_dp, _dbl, _dbl, _c_dp, _i64, _c_dp,
+                             _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_standardize': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
 }

@@ -92,17 +92,74 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
 size_t edrgp_syrk_workspace_bytes(int64_t n, int k) {
   int sms = sm_count_cached();
   if (sms <= 0) sms = 160;
-  return edrgp::syrk_workspace_bytes(n, k, sms);
+  return edrgp::gemm_tn_workspace_bytes(n, k, k, 1, sms);
 }
 
-int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, void* workspace,
-               void* stream) {
-  if (!A || !C || !workspace || n <= 0 || k <= 0 || lda < k || ldc < k) return fail(EDRGP_ERR_ARG, "syrk: bad argument");
-  if ((lda & 1) || !aligned16(A)) return fail(EDRGP_ERR_ARG, "syrk: lda must be even and A 16-byte aligned");
+static int check_tall(const char* who, const double* A, int64_t n, int k, int64_t lda) {
+  if (!A || n <= 0 || k <= 0 || lda < k) return fail(EDRGP_ERR_ARG, "%s: bad argument", who);
+  if ((lda & 1) || !aligned16(A)) return fail(EDRGP_ERR_ARG, "%s: leading dimension must be even, matrix 16-byte aligned", who);
+  return EDRGP_OK;
+}
+
+int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, int accumulate,
+               void* workspace, void* stream) {
+  int rc = check_tall("syrk", A, n, k, lda);
+  if (rc) return rc;
+  if (!C || !workspace || ldc < k) return fail(EDRGP_ERR_ARG, "syrk: bad argument");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "syrk: no CUDA device");
-  cudaError_t e = edrgp::launch_syrk(A, n, k, lda, C, ldc, (double*)workspace, sms, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_gemm_tn(A, lda, k, nullptr, 0, 0, n, 1, nullptr, C, ldc, nullptr, accumulate,
+                                        (double*)workspace, sms, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "syrk");
+}
+
+int edrgp_inducing_stats(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double* P, int64_t ldp,
+                         double* b_yy, int accumulate, void* workspace, void* stream) {
+  int rc = check_tall("inducing_stats", Kfu, n, m, ldk);
+  if (rc) return rc;
+  if (!y || !P || !b_yy || !workspace || ldp < m) return fail(EDRGP_ERR_ARG, "inducing_stats: bad argument");
+  if (!aligned16(y)) return fail(EDRGP_ERR_ARG, "inducing_stats: y must be 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "inducing_stats: no CUDA device");
+  cudaError_t e = edrgp::launch_gemm_tn(Kfu, ldk, m, nullptr, 0, 0, n, 1, y, P, ldp, b_yy, accumulate,
+                                        (double*)workspace, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "inducing_stats");
+}
+
+size_t edrgp_gemm_tn_workspace_bytes(int64_t n, int ka, int kb) {
+  int sms = sm_count_cached();
+  if (sms <= 0) sms = 160;
+  return edrgp::gemm_tn_workspace_bytes(n, ka, kb, 0, sms);
+}
+
+int edrgp_gemm_tn(const double* A, int64_t lda, int ka, const double* B, int64_t ldb, int kb, int64_t n, double* C,
+                  int64_t ldc, int accumulate, void* workspace, void* stream) {
+  int rc = check_tall("gemm_tn", A, n, ka, lda);
+  if (rc) return rc;
+  rc = check_tall("gemm_tn", B, n, kb, ldb);
+  if (rc) return rc;
+  if (!C || !workspace || ldc < kb) return fail(EDRGP_ERR_ARG, "gemm_tn: bad argument");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "gemm_tn: no CUDA device");
+  cudaError_t e = edrgp::launch_gemm_tn(A, lda, ka, B, ldb, kb, n, 0, nullptr, C, ldc, nullptr, accumulate,
+                                        (double*)workspace, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "gemm_tn");
+}
+
+size_t edrgp_weights_workspace_bytes(int64_t n, int m) { return edrgp::weights_workspace_bytes(n, m); }
+
+int edrgp_weights(const double* Kfu, int64_t n, int m, int64_t ldk, const double* M, int64_t ldm, const double* y,
+                  const double* alpha, double c_ya, double c_km, double* T, int64_t ldt, double* rowsum,
+                  double* colsum, int accumulate, void* workspace, void* stream) {
+  int rc = check_tall("weights", Kfu, n, m, ldk);
+  if (rc) return rc;
+  if (!M || ldm < m || (ldm & 1) || !aligned16(M)) return fail(EDRGP_ERR_ARG, "weights: M needs an even leading dimension >= m and 16-byte alignment");
+  if (T && (ldt < m || (ldt & 1) || !aligned16(T))) return fail(EDRGP_ERR_ARG, "weights: T needs an even leading dimension >= m and 16-byte alignment");
+  if ((y == nullptr) != (alpha == nullptr)) return fail(EDRGP_ERR_ARG, "weights: y and alpha go together");
+  if ((rowsum || colsum) && !workspace) return fail(EDRGP_ERR_ARG, "weights: sums need a workspace");
+  cudaError_t e = edrgp::launch_weights(Kfu, n, m, ldk, M, ldm, y, alpha, c_ya, c_km, T, ldt, rowsum, colsum, accumulate,
+                                        (double*)workspace, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "weights");
 }
 
 int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, double jitter, double* Kmm,
@@ -147,13 +204,14 @@ size_t edrgp_col_moments_workspace_bytes(int d) {
   return edrgp::col_moments_workspace_bytes(d, sms);
 }
 
-int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, double* out, void* workspace,
-                      void* stream) {
+int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight, double* out,
+                      int accumulate, void* workspace, void* stream) {
   if (!X || !out || !workspace || n <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "col_moments: bad argument");
   if (d > 512) return fail(EDRGP_ERR_UNSUPPORTED, "col_moments: d > 512");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "col_moments: no CUDA device");
-  cudaError_t e = edrgp::launch_col_moments(X, n, d, shift, out, (double*)workspace, sms, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_col_moments(X, n, d, shift, weight, out, accumulate, (double*)workspace, sms,
+                                            (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "col_moments");
 }
 

@@ -13,9 +13,11 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
 cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
                        int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st);
 
-size_t syrk_workspace_bytes(int64_t n, int k, int sms);
-cudaError_t launch_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, double* workspace,
-                        int sms, cudaStream_t st);
+// C (+)= A^T B (sym: B = A, upper tiles mirrored; optional y: bout[0..ka) (+)= A^T y, bout[ka] (+)= y^T y)
+size_t gemm_tn_workspace_bytes(int64_t n, int ka, int kb, int sym, int sms);
+cudaError_t launch_gemm_tn(const double* A, int64_t lda, int ka, const double* B, int64_t ldb, int kb, int64_t n,
+                           int sym, const double* y, double* C, int64_t ldc, double* bout, int accumulate,
+                           double* workspace, int sms, cudaStream_t st);
 cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t st);
 cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
                         cudaStream_t st);
@@ -26,8 +28,12 @@ cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, d
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st);
 
 size_t col_moments_workspace_bytes(int d, int sms);
-cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, double* out, double* workspace,
-                               int sms, cudaStream_t st);
+cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
+                               double* out, int accumulate, double* workspace, int sms, cudaStream_t st);
+size_t weights_workspace_bytes(int64_t n, int m);
+cudaError_t launch_weights(const double* K, int64_t n, int m, int64_t ldk, const double* M, int64_t ldm, const double* y,
+                           const double* alpha, double c_ya, double c_km, double* T, int64_t ldt, double* rowsum,
+                           double* colsum, int accumulate, double* workspace, cudaStream_t st);
 cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,
                                int sms, cudaStream_t st);
 cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, int k, double* out, int sms,

@@ -416,9 +416,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
       for (int nb = 0; nb < MT / 8; ++nb) {
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
-        double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)) * c.x, k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0)) * c.y;
-        double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)) * c.x, k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0)) * c.y;
-        mu0 += k00 + k01; mu1 += k10 + k11;
+        // entries are stored without the pack coefficient; only the row sums mu carry it
+        const double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)), k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0));
+        const double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)), k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0));
+        mu0 += fma(k00, c.x, k01 * c.y); mu1 += fma(k10, c.x, k11 * c.y);
         if (p.Kfu != nullptr) {
           // ldk even (host guarantees) and j even -> 16-byte stores
           if (j + 1 < p.m) {

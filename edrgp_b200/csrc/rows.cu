@@ -12,10 +12,11 @@ namespace edrgp {
 
 constexpr int CM_THREADS = 256;
 
-// part[blk][0][q] = sum_i (x_iq - shift_q),  part[blk][1][q] = sum_i (x_iq - shift_q)^2
+// part[blk][0][q] = sum_i w_i (x_iq - shift_q),  part[blk][1][q] = sum_i w_i (x_iq - shift_q)^2
 // over the rows of this CTA; deterministic two-stage reduction (no atomics).
 __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* __restrict__ X, int64_t n, int d,
                                                                  const double* __restrict__ shift,
+                                                                 const double* __restrict__ weight,
                                                                  double* __restrict__ part) {
   extern __shared__ double sh[];     // [CM_THREADS / cols_lanes][2][d] folded below
   // thread layout: lanes walk the columns (coalesced), thread rows walk the rows
@@ -30,13 +31,15 @@ __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* _
   if (active) {
     for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + tr; r < n; r += (int64_t)gridDim.x * rows_per_pass) {
       const double* xr = X + r * d;
+      const double w = weight ? weight[r] : 1.0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int q = tc + c * lanes;
         if (c < ncol && q < d) {
           const double v = xr[q] - (shift ? shift[q] : 0.0);
-          s1[c] += v;
-          s2[c] = fma(v, v, s2[c]);
+          const double wv = w * v;
+          s1[c] += wv;
+          s2[c] = fma(wv, v, s2[c]);
         }
       }
     }
@@ -61,13 +64,14 @@ __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* _
   }
 }
 
-__global__ void col_moments_reduce_kernel(const double* __restrict__ part, int nblk, int d, double* __restrict__ out) {
+__global__ void col_moments_reduce_kernel(const double* __restrict__ part, int nblk, int d, double* __restrict__ out,
+                                          int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over 2*d
   if (i >= 2 * d) return;
   const int k = i / d, q = i - k * d;
   double s = 0.0;
   for (int b = 0; b < nblk; ++b) s += part[((size_t)b * 2 + k) * d + q];
-  out[i] = s;
+  out[i] = accumulate ? out[i] + s : s;
 }
 
 __global__ void standardize_kernel(const double* __restrict__ X, int64_t total, int d, const double* __restrict__ mean,
@@ -115,18 +119,18 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
 
 size_t col_moments_workspace_bytes(int d, int sms) { return (size_t)sms * 4 * 2 * d * sizeof(double); }
 
-cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, double* out, double* workspace,
-                               int sms, cudaStream_t st) {
+cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
+                               double* out, int accumulate, double* workspace, int sms, cudaStream_t st) {
   if (d > 512) return cudaErrorInvalidValue;
   int grid = sms * 4;
   const int lanes = d < 32 ? d : 32;
   const int rows_per_pass = CM_THREADS / lanes;
   const int64_t need = (n + rows_per_pass - 1) / rows_per_pass;
   if (grid > need) grid = (int)need;
-  col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, workspace);
+  col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, weight, workspace);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  col_moments_reduce_kernel<<<(2 * d + 127) / 128, 128, 0, st>>>(workspace, grid, d, out);
+  col_moments_reduce_kernel<<<(2 * d + 127) / 128, 128, 0, st>>>(workspace, grid, d, out, accumulate);
   return cudaGetLastError();
 }
 

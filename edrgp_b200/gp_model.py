@@ -1,0 +1,162 @@
+"""sklearn-style estimator shell around the device model: drop-in for edr-gp's
+``SparseGaussianProcessRegressor`` (``edrgp/gp_model/regression.py:80-157``) with the methods of
+its ``_BaseGP`` (``edrgp/gp_model/base.py:46-257``): ``fit``, ``predict``, ``predict_variance``,
+``predict_gradient``, ``save``, ``load`` -- same constructor parameters, argument meaning and
+errors.  The GPy model behind it is replaced by ``edrgp_b200.model.SparseGPRegression``.
+
+Only what the hot path needs is provided: the RBF kernel (ARD or not) with a Gaussian likelihood.
+Other GPy kernels, sums of kernels, uncertain inputs and mean functions raise
+``NotImplementedError`` instead of silently doing something else.
+"""
+import pickle
+from copy import deepcopy
+
+import numpy as np
+from sklearn.base import BaseEstimator, RegressorMixin
+from sklearn.utils import check_X_y, check_array, assert_all_finite
+from sklearn.utils.validation import check_is_fitted
+
+from . import model as _model
+
+_KERNELS = {'RBF': _model.RBF, 'rbf': _model.RBF}
+
+
+class _BaseGP(BaseEstimator):
+    """Common estimator logic (mirrors ``edrgp/gp_model/base.py:_BaseGP``)."""
+
+    def fit(self, X, y, **opt_kws):
+        """Fit the model: build it on the device, then run ``method`` (``'optimize'``,
+        ``'optimize_restarts'`` or ``'fixed'``) with ``messages=False, max_iters=1000`` defaults
+        (edrgp/gp_model/base.py:46-70)."""
+        X, y = self._check_data(X, y)
+        self.n_features_ = X.shape[1]
+        kernel = self._make_kernel()
+        self.estimator_ = self._get_model(X, y, kernel)
+        opt_kws.setdefault('messages', False)
+        opt_kws.setdefault('max_iters', 1000)
+        getattr(self.estimator_, self.method)(**opt_kws)
+        return self
+
+    def _check_data(self, X, y):
+        X, y = check_X_y(X, y, accept_sparse=False, dtype=np.float64)
+        return X, y[:, np.newaxis]
+
+    def _check_input(self, X):
+        X = check_array(X, accept_sparse=False, dtype=np.float64)
+        if X.shape[1] != self.n_features_:
+            raise ValueError("X has {} features per sample; expecting {}".format(X.shape[1], self.n_features_))
+        return X
+
+    def _make_kernel(self):
+        """Kernel from names + options (edrgp/gp_model/base.py:111-147).  ``None`` lets the model
+        pick its default (RBF, as GPy does); a ready ``edrgp_b200.model.RBF`` passes through."""
+        if self.kernels is None:
+            return None
+        if isinstance(self.kernels, _model.RBF):
+            return self.kernels.copy()
+        kernels = [self.kernels] if isinstance(self.kernels, str) else list(self.kernels)
+        options = self.kernel_options
+        if isinstance(options, dict):
+            options = [options]
+        input_dim = {'input_dim': self.n_features_}
+        if options is None:
+            options = [dict(input_dim) for _ in kernels]
+        elif len(kernels) == len(options):
+            options = deepcopy(options)
+            for opt in options:
+                opt.update(input_dim)
+        else:
+            raise ValueError("kernels and kernel_options differ in length")
+        if len(kernels) != 1:
+            raise NotImplementedError("sums of kernels are outside the B200 path (RBF only)")
+        if kernels[0] not in _KERNELS:
+            raise NotImplementedError("kernel %r is outside the B200 path (RBF only)" % (kernels[0],))
+        return _KERNELS[kernels[0]](**options[0])
+
+    def _check_predict(self, X):
+        X = self._check_input(X)
+        check_is_fitted(self, 'estimator_')
+        return X
+
+    def predict(self, X):
+        """Posterior mean, shape (n,) (edrgp/gp_model/base.py:169-189)."""
+        X = self._check_predict(X)
+        y_pred = self.estimator_.predict(X, want_variance=False)[0][:, 0]
+        assert_all_finite(y_pred)
+        return y_pred
+
+    def predict_variance(self, X):
+        """Predictive variance, shape (n, 1) (edrgp/gp_model/base.py:191-206)."""
+        X = self._check_predict(X)
+        return self.estimator_.predict(X)[1]
+
+    def predict_gradient(self, X):
+        """Gradient of the posterior mean, shape (n, d) (edrgp/gp_model/base.py:208-222)."""
+        X = self._check_predict(X)
+        return self.estimator_.predictive_gradients(X)[0][:, :, 0]
+
+    def save(self, model_path):
+        """Save the fitted model to ``model_path`` (+ '.pickle'), edrgp/gp_model/base.py:224-239.
+        The file holds plain arrays (hyper-parameters, Z, alpha, Cholesky factors)."""
+        check_is_fitted(self, 'estimator_')
+        if not model_path.endswith('.pickle'):
+            model_path += '.pickle'
+        with open(model_path, 'wb') as f:
+            pickle.dump({'format': 'edrgp_b200/1', 'state': self.estimator_.state_dict(),
+                         'n_features_': self.n_features_}, f)
+
+    def load(self, model_path):
+        """Load a model saved by ``save`` (edrgp/gp_model/base.py:242-257)."""
+        if not model_path.endswith('.pickle'):
+            model_path += '.pickle'
+        with open(model_path, 'rb') as f:
+            blob = pickle.load(f)
+        if not isinstance(blob, dict) or blob.get('format') != 'edrgp_b200/1':
+            raise ValueError("not an edrgp_b200 model file")
+        self.estimator_ = _model.FittedSparseGP(blob['state'])
+        self.n_features_ = blob['n_features_']
+
+
+class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
+    """Sparse Gaussian process regression on B200 (drop-in for
+    ``edrgp.gp_model.SparseGaussianProcessRegressor``, edrgp/gp_model/regression.py:80-157).
+
+    Parameters are the reference's; ``method`` additionally accepts ``'fixed'`` (keep the initial
+    or injected hyper-parameters: what the parity harness and the benchmark use), and
+    ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time.
+    """
+
+    def __init__(self, kernels=None, kernel_options=None, Z=None, num_inducing=10, Y_metadata=None,
+                 X_variance=None, normalizer=True, mean_function=None, method='optimize', chunk_rows=262144):
+        self.kernels = kernels
+        self.kernel_options = kernel_options
+        self.Z = Z
+        self.num_inducing = num_inducing
+        self.Y_metadata = Y_metadata
+        self.X_variance = X_variance
+        self.normalizer = normalizer
+        self.mean_function = mean_function
+        self.method = method
+        self.chunk_rows = chunk_rows
+
+    def _get_model(self, X, y, kernel):
+        return _model.SparseGPRegression(X, y, kernel=kernel, Z=self.Z, num_inducing=self.num_inducing,
+                                         X_variance=self.X_variance, mean_function=self.mean_function,
+                                         normalizer=self.normalizer, chunk_rows=self.chunk_rows)
+
+    def _check_data(self, X, y):
+        # device-resident rows (torch CUDA tensors) skip the host validators: this rank's shard
+        import torch
+        if isinstance(X, torch.Tensor):
+            if X.dim() != 2 or y.shape[0] != X.shape[0]:
+                raise ValueError("X must be (n, d) and y (n,)")
+            return X, y.reshape(-1, 1)
+        return _BaseGP._check_data(self, X, y)
+
+    def _check_input(self, X):
+        import torch
+        if isinstance(X, torch.Tensor):
+            if X.shape[1] != self.n_features_:
+                raise ValueError("X has {} features per sample; expecting {}".format(X.shape[1], self.n_features_))
+            return X
+        return _BaseGP._check_input(self, X)

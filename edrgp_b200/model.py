@@ -1,0 +1,585 @@
+"""Device-resident sparse GP regression model: the object edr-gp keeps as ``estimator_``.
+
+Stands in for ``GPy.models.SparseGPRegression`` as edr-gp builds and uses it
+(``edrgp/gp_model/regression.py:153-157``: construction; ``edrgp/gp_model/base.py:65-69``:
+``optimize`` / ``optimize_restarts``; ``:187,206``: ``predict``; ``:222``: ``predictive_gradients``;
+``edrgp/tests/test_edr.py:49-50``: ``log_likelihood()[0][0]``).  The arithmetic is GPy's VarDTC
+(VFE) inference for an RBF kernel with a Gaussian likelihood, regrouped so that everything that
+scales with the number of points n runs as row-sharded CUDA kernels through the C ABI
+(``include/edrgp_b200.h``) and only m x m / d x d quantities are reduced across GPUs:
+
+    pass 1  Kfu block -> HBM; P = Kfu^T Kfu, b = Kfu^T y, y^T y           [edrgp_kuf, edrgp_inducing_stats]
+            all-reduce {P, b, yy}; Kuu; Cholesky chain -> alpha, bound   [edrgp_kmm, edrgp_solve]
+    pass 2  (optimisation only) T = Kfu o dL/dKfu; T^T X, T 1, T^T 1, sum_i (T 1)_i x_i^2
+                                                       [edrgp_weights, edrgp_gemm_tn, edrgp_col_moments]
+            all-reduce {T^T X, T^T 1, moments}; host assembles dL/d{Z, variance, lengthscale, noise}
+    sweep   posterior-mean gradients and their Gram matrix                [edrgp_grad_gram]
+
+There is no CPU fallback: every method needs the CUDA library and a CUDA device.
+"""
+import numpy as np
+import torch
+from scipy import optimize as sopt
+
+from . import dist, ops
+
+F64 = torch.float64
+CONST_JITTER = 1e-8                      # GPy VarDTC.const_jitter
+_LIM_VAL = 36.0                          # paramz.transformations._lim_val
+_LOG_LIM_VAL = float(np.log(np.finfo(np.float64).max))
+
+
+# ------------------------------------------------------------------------------------------------
+# paramz Logexp transform (positive parameters are optimised through log(1 + exp(x)))
+# ------------------------------------------------------------------------------------------------
+def _logexp_f(x):
+    return np.where(x > _LIM_VAL, x, np.log1p(np.exp(np.clip(x, -_LOG_LIM_VAL, _LIM_VAL))))
+
+
+def _logexp_finv(f):
+    return np.where(f > _LIM_VAL, f, np.log(np.expm1(f)))
+
+
+def _logexp_gradfactor(f, df):
+    return df * np.where(f > _LIM_VAL, 1., -np.expm1(-f))
+
+
+class RBF(object):
+    """Hyper-parameter holder with the surface of ``GPy.kern.RBF`` that edr-gp touches
+    (``edrgp/gp_model/base.py:111-147`` builds it from ``'RBF'`` + ``kernel_options``)."""
+
+    name = 'rbf'
+
+    def __init__(self, input_dim, variance=1., lengthscale=None, ARD=False, **unused):
+        self.input_dim = int(input_dim)
+        self.ARD = bool(ARD)
+        self.variance = float(variance)
+        if lengthscale is None:
+            lengthscale = np.ones(self.input_dim if self.ARD else 1)
+        lengthscale = np.atleast_1d(np.asarray(lengthscale, dtype=np.float64)).copy()
+        if self.ARD and lengthscale.size == 1:
+            lengthscale = np.ones(self.input_dim) * lengthscale
+        if not self.ARD and lengthscale.size != 1:
+            raise ValueError("Only 1 lengthscale needed for non-ARD kernel")
+        self.lengthscale = lengthscale
+
+    def copy(self):
+        return RBF(self.input_dim, self.variance, self.lengthscale.copy(), self.ARD)
+
+    def full_lengthscale(self):
+        return self.lengthscale if self.ARD else np.full(self.input_dim, self.lengthscale[0])
+
+
+class Standardize(object):
+    """``GPy.util.normalizer.Standardize`` with the moments reduced on the device / across ranks."""
+
+    def scale_by_device(self, y_dev, n_total):
+        s1, _ = ops.col_moments(y_dev)
+        s1 = s1.clone()
+        dist.allreduce_sum_(s1)
+        mean = s1 / n_total
+        _, s2 = ops.col_moments(y_dev, shift=mean)
+        s2 = s2.clone()
+        dist.allreduce_sum_(s2)
+        self.mean = float(mean[0])
+        self.std = float(torch.sqrt(s2 / n_total)[0])
+
+    def normalize_device(self, y_dev):
+        dev = y_dev.device
+        return ops.standardize(y_dev, torch.tensor([self.mean], dtype=F64, device=dev),
+                               torch.tensor([self.std], dtype=F64, device=dev))
+
+    def inverse_mean(self, X):
+        return (X * self.std) + self.mean
+
+    def inverse_variance(self, var):
+        return var * (self.std ** 2)
+
+
+def _as_device(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=F64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+
+
+def _backsub_both_sides(L, X, transpose='left'):
+    """GPy.util.linalg.backsub_both_sides on the device: L^-T X L^-1 ('left') or L^-1 X L^-T."""
+    trans = transpose == 'left'
+    tmp = ops.trsm(L, X.clone(), trans)
+    tmp = ops.trsm(L, tmp.t().contiguous(), trans)
+    return tmp.t().contiguous()
+
+
+class SparseGPRegression(object):
+    """Sparse GP regression (VFE / VarDTC, RBF kernel, Gaussian noise) on one GPU shard.
+
+    Parameters mirror ``GPy.models.SparseGPRegression`` as called from
+    ``edrgp/gp_model/regression.py:153-157``.  ``X`` / ``Y`` are this rank's rows (host arrays or
+    CUDA tensors); in a multi-process run every rank passes its own shard and the same ``Z`` (or
+    ``Z=None`` with the same NumPy seed).
+    """
+
+    def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, X_variance=None, mean_function=None,
+                 normalizer=None, device=None, chunk_rows=262144, cache_bytes=None):
+        if X_variance is not None or mean_function is not None:
+            raise NotImplementedError("uncertain inputs / mean functions are outside the B200 path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("edrgp_b200 needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.X = ops.pad_even(_as_device(X, self.device))          # (n_local, d_even)
+        self.n_local, self.d_even = self.X.shape
+        self.input_dim = X.shape[1]
+        Yd = _as_device(Y, self.device).reshape(-1)
+        if Yd.shape[0] != self.n_local:
+            raise ValueError("X and Y row counts differ")
+        cnt = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
+        dist.allreduce_sum_(cnt)
+        self.num_data = int(round(float(cnt[0])))
+        self.kern = RBF(self.input_dim) if kernel is None else kernel
+        if self.kern.input_dim != self.input_dim:
+            raise ValueError("kernel input_dim does not match X")
+
+        if Z is None:
+            Zh = self._draw_inducing(min(int(num_inducing), self.num_data))
+        else:
+            Zh = np.array(Z, dtype=np.float64)
+            if Zh.ndim != 2 or Zh.shape[1] != self.input_dim:
+                raise ValueError("Z must have shape (num_inducing, n_features)")
+        self.Z = Zh
+        self.num_inducing = Zh.shape[0]
+        self.noise_variance = 1.0                                  # GPy likelihoods.Gaussian() default
+
+        if normalizer is True:
+            self.normalizer = Standardize()
+        elif normalizer is False or normalizer is None:
+            self.normalizer = None
+        else:
+            self.normalizer = normalizer
+        if self.normalizer is not None:
+            self.normalizer.scale_by_device(Yd, self.num_data)
+            self.Y_normalized = self.normalizer.normalize_device(Yd)
+        else:
+            self.Y_normalized = Yd
+        self.chunk_rows = int(max(1024, min(chunk_rows, max(self.n_local, 1))))
+        self.chunk_rows += self.chunk_rows & 1                    # even chunks keep y slices 16-byte aligned
+        self.cache_bytes = cache_bytes
+        self.optimization_runs = []
+        self.fix_Z = False
+        self._Kcache = None
+        self._need_grad = False
+        self.kernel_launches = 0
+        self.parameters_changed()
+
+    # -------------------------------------------------------------------------------------------
+    # inducing inputs: GPy takes ``X[np.random.permutation(n)[:m]]``; with sharded rows every rank
+    # draws the same global permutation and contributes the rows it owns.
+    # -------------------------------------------------------------------------------------------
+    def _draw_inducing(self, m):
+        idx = np.random.permutation(self.num_data)[:m]
+        lo, _ = dist.shard_bounds(self.num_data) if dist.is_distributed() else (0, self.n_local)
+        if dist.is_distributed():
+            # shards may be uneven in principle: exchange the true offsets
+            sizes = torch.zeros(dist.world_size(), dtype=F64, device=self.device)
+            sizes[dist.rank()] = self.n_local
+            dist.allreduce_sum_(sizes)
+            lo = int(round(float(sizes[:dist.rank()].sum())))
+        Zd = torch.zeros(m, self.input_dim, dtype=F64, device=self.device)
+        local = idx - lo
+        mine = np.nonzero((local >= 0) & (local < self.n_local))[0]
+        if mine.size:
+            rows = torch.as_tensor(local[mine], device=self.device)
+            Zd[torch.as_tensor(mine, device=self.device)] = self.X[rows, :self.input_dim]
+        dist.allreduce_sum_(Zd)
+        return Zd.cpu().numpy()
+
+    # -------------------------------------------------------------------------------------------
+    # pass 1 + solve (+ pass 2)
+    # -------------------------------------------------------------------------------------------
+    def _chunks(self):
+        for s in range(0, self.n_local, self.chunk_rows):
+            yield s, min(self.n_local, s + self.chunk_rows)
+
+    def _kbuffers(self, want_cache):
+        m = self.num_inducing
+        ldk = m + (m & 1)
+        if want_cache and self._Kcache is None:
+            need = self.n_local * ldk * 8
+            budget = self.cache_bytes
+            if budget is None:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                budget = int(0.5 * free)
+            if need <= budget:
+                self._Kcache = torch.empty(self.n_local, ldk, dtype=F64, device=self.device)
+        if getattr(self, '_Kbuf', None) is None or self._Kbuf.shape[1] != ldk:
+            rows = min(self.chunk_rows, self.n_local)
+            self._Kbuf = torch.empty(rows, ldk, dtype=F64, device=self.device)
+        return ldk
+
+    def parameters_changed(self):
+        """Recompute the posterior (alpha), the VFE bound and -- while optimising -- its gradient."""
+        dev = self.device
+        m, d = self.num_inducing, self.input_dim
+        sf2 = float(self.kern.variance)
+        ell = np.ones(self.d_even)
+        ell[:d] = self.kern.full_lengthscale()
+        self._ell_dev = torch.as_tensor(ell, device=dev)
+        Zp = np.zeros((m, self.d_even))
+        Zp[:, :d] = self.Z
+        self._Z_dev = torch.as_tensor(Zp, device=dev)
+        beta = 1.0 / max(float(self.noise_variance), CONST_JITTER)
+        need_grad = self._need_grad
+        ldk = self._kbuffers(need_grad)
+
+        self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
+        P = torch.empty(m, m, dtype=F64, device=dev)
+        byy = torch.empty(m + 1, dtype=F64, device=dev)
+        y = self.Y_normalized
+        for i, (s, e) in enumerate(self._chunks()):
+            Kc = self._Kcache[s:e] if self._Kcache is not None else self._Kbuf[:e - s]
+            ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
+            ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
+            self.kernel_launches += 4
+        if self.n_local == 0:
+            P.zero_(); byy.zero_()
+        dist.allreduce_sum_(P, byy)
+        Kmm = ops.kmm(self._pack, sf2, CONST_JITTER)
+        res = ops.solve(Kmm, P, byy[:m].contiguous(), beta)
+        self.kernel_launches += 8
+        info = res.info.cpu().tolist()
+        if info[0] != 0 or info[1] != 0:
+            raise np.linalg.LinAlgError("not positive definite: chol(Kuu) info=%d, chol(I + A) info=%d" % tuple(info))
+        sc = res.scalars.cpu().numpy()
+        trA, sumlogLB, data_fit = float(sc[0]), float(sc[1]), float(sc[2])
+        yy = float(byy[m])
+        n = self.num_data
+        bound = (-0.5 * n * (np.log(2. * np.pi) - np.log(beta)) - 0.5 * beta * yy
+                 - 0.5 * (beta * n * sf2 - trA) - sumlogLB + 0.5 * data_fit)
+        self._log_marginal_likelihood = np.array([[bound]])
+        self._solve = res
+        self._beta = beta
+        self.alpha = res.alpha                                   # GPy posterior.woodbury_vector (m,)
+        self._woodbury_inv = None
+        if need_grad:
+            self._gradients(P, res, beta, sf2, ell[:d], trA, data_fit, yy, ldk)
+
+    def _gradients(self, P, res, beta, sf2, ell, trA, data_fit, yy, ldk):
+        dev = self.device
+        m, d, n = self.num_inducing, self.input_dim, self.num_data
+        eye = torch.eye(m, dtype=F64, device=dev)
+        c = res.c
+        E = _backsub_both_sides(res.LB, eye + torch.outer(c, c), 'left')        # DBi_plus_BiPBi
+        dL_dpsi2 = (0.5 * beta) * _backsub_both_sides(res.Lm, eye - E, 'left')
+        dL_dKmm = _backsub_both_sides(res.Lm, -0.5 * E - 0.5 * res.B + eye, 'left')
+        sumAE = float(((res.B - eye) * E).sum())
+        self.kernel_launches += 12
+
+        # ---- pass 2 over the rows: T = Kfu o dL/dKfu and its contractions
+        Mmat = ops.even_ld(0.5 * (dL_dpsi2 + dL_dpsi2.t()))
+        S = torch.zeros(m, self.d_even, dtype=F64, device=dev)
+        cs = torch.zeros(m, dtype=F64, device=dev)
+        mom = torch.zeros(2 * self.d_even, dtype=F64, device=dev)
+        if getattr(self, '_Tbuf', None) is None or self._Tbuf.shape[1] != ldk:
+            self._Tbuf = torch.empty(min(self.chunk_rows, self.n_local), ldk, dtype=F64, device=dev)
+        y = self.Y_normalized
+        for i, (s, e) in enumerate(self._chunks()):
+            if self._Kcache is not None:
+                Kc = self._Kcache[s:e]
+            else:
+                Kc = self._Kbuf[:e - s]
+                ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
+                self.kernel_launches += 1
+            Tc = self._Tbuf[:e - s]
+            rs = ops.weights(Kc, Mmat, m, y=y[s:e], alpha=self.alpha, c_ya=beta, c_km=2.0, T=Tc,
+                             want_rowsum=True, colsum=cs, accumulate=True)
+            ops.gemm_tn(Tc, self.X[s:e], ka=m, out=S, accumulate=True)
+            ops.col_moments(self.X[s:e], weight=rs, out=mom, accumulate=True)
+            self.kernel_launches += 6
+        dist.allreduce_sum_(S, cs, mom)
+        S = S[:, :d]
+        R = mom[self.d_even:self.d_even + d]                     # sum_i rowsum(T)_i x_iq^2
+        Z = self._Z_dev[:, :d]
+        il2 = torch.as_tensor(1.0 / ell ** 2, device=dev)
+        il3 = torch.as_tensor(1.0 / ell ** 3, device=dev)
+        sumT = cs.sum()
+        gZ = (S - cs[:, None] * Z) * il2
+        glen = (R - 2.0 * (Z * S).sum(0) + (cs[:, None] * Z * Z).sum(0)) * il3
+        gvar = sumT / sf2
+
+        # ---- Kuu part: T_mm = K(Z, Z) o dL/dKmm (GPy symmetrises through tmp + tmp.T)
+        Kzz = ops.kmm(self._pack, sf2, 0.0)
+        Tm = Kzz * (0.5 * (dL_dKmm + dL_dKmm.t()))
+        rs_m = Tm.sum(1)
+        TZ = ops.gemm_tn(ops.even_ld(Tm), self._Z_dev, ka=m)[:, :d]         # Tm symmetric: Tm^T Z = Tm Z
+        gZ = gZ + 2.0 * (TZ - rs_m[:, None] * Z) * il2
+        glen = glen + 2.0 * ((rs_m[:, None] * Z * Z).sum(0) - (Z * TZ).sum(0)) * il3
+        gvar = gvar + Tm.sum() / sf2
+        self.kernel_launches += 3
+
+        # ---- Kdiag part and the noise (GPy _compute_dL_dR + Gaussian.exact_inference_gradients)
+        gvar = float(gvar) - 0.5 * beta * n
+        dL_dR = (-0.5 * n * beta + 0.5 * yy * beta ** 2 + 0.5 * (n * sf2 * beta ** 2 - trA * beta)
+                 + beta * (0.5 * sumAE - data_fit))
+        self.grad_variance = gvar
+        glen = glen.cpu().numpy()
+        self.grad_lengthscale = glen if self.kern.ARD else np.atleast_1d(glen.sum())
+        self.grad_noise = float(dL_dR)
+        self.grad_Z = gZ.cpu().numpy()
+
+    def log_likelihood(self):
+        """The VFE bound as a (1, 1) array, like GPy (edrgp/tests/test_edr.py:49-50)."""
+        return self._log_marginal_likelihood
+
+    # -------------------------------------------------------------------------------------------
+    # paramz-style optimisation: parameters in GPy order (Z, rbf.variance, rbf.lengthscale, noise)
+    # -------------------------------------------------------------------------------------------
+    def _positive(self):
+        return np.concatenate([[self.kern.variance], self.kern.lengthscale, [self.noise_variance]])
+
+    def _get_optimizer_array(self):
+        pos = _logexp_finv(self._positive())
+        return pos if self.fix_Z else np.concatenate([self.Z.ravel(), pos])
+
+    def _set_optimizer_array(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        nz = 0 if self.fix_Z else self.Z.size
+        if nz:
+            self.Z = x[:nz].reshape(self.Z.shape).copy()
+        pos = _logexp_f(x[nz:])
+        self.kern.variance = float(pos[0])
+        self.kern.lengthscale = pos[1:1 + self.kern.lengthscale.size].copy()
+        self.noise_variance = float(pos[-1])
+        self.parameters_changed()
+
+    def _transformed_gradients(self):
+        gpos = np.concatenate([[self.grad_variance], self.grad_lengthscale, [self.grad_noise]])
+        gpos = _logexp_gradfactor(self._positive(), gpos)
+        return gpos if self.fix_Z else np.concatenate([self.grad_Z.ravel(), gpos])
+
+    _fail_count = 0
+    _allowed_failures = 10
+
+    def _objective_grads(self, x):
+        try:
+            self._set_optimizer_array(x)
+            obj = -float(np.sum(self.log_likelihood()))
+            grads = -self._transformed_gradients()
+            self._fail_count = 0
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError, FloatingPointError):
+            if self._fail_count >= self._allowed_failures:
+                raise
+            self._fail_count += 1
+            return np.inf, np.clip(np.zeros_like(x), -1e10, 1e10)
+        if dist.is_distributed():
+            # every rank must walk the same L-BFGS trajectory: take rank 0's view of (f, g)
+            buf = torch.as_tensor(np.concatenate([[obj], grads]), device=self.device)
+            dist.broadcast_(buf, 0)
+            buf = buf.cpu().numpy()
+            obj, grads = float(buf[0]), buf[1:]
+        return obj, np.clip(grads, -1e10, 1e10)
+
+    def optimize(self, optimizer=None, start=None, messages=False, max_iters=1000, **kwargs):
+        """L-BFGS-B on the negative VFE bound (paramz ``Model.optimize`` with its default optimiser)."""
+        if optimizer not in (None, 'lbfgsb', 'lbfgs', 'bfgs'):
+            raise NotImplementedError("only the default L-BFGS-B optimiser is provided")
+        x0 = self._get_optimizer_array() if start is None else np.asarray(start, dtype=np.float64)
+        if max_iters <= 0 or x0.size == 0:
+            return self
+        self._need_grad = True
+        try:
+            x_opt, f_opt, info = sopt.fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters, maxiter=max_iters)
+        finally:
+            self._need_grad = False
+        self._set_optimizer_array(x_opt)
+        self.optimization_runs.append((f_opt, x_opt, info))
+        self._Kcache = None
+        return self
+
+    def optimize_restarts(self, num_restarts=10, robust=False, verbose=False, **kwargs):
+        """paramz ``Model.optimize_restarts``: first run from the current point, then random starts."""
+        initial = self._get_optimizer_array().copy()
+        first = len(self.optimization_runs)
+        for i in range(num_restarts):
+            try:
+                if i > 0:
+                    self._set_optimizer_array(np.random.normal(size=initial.size))
+                self.optimize(**kwargs)
+                if verbose:
+                    print("Optimization restart {0}/{1}, f = {2}".format(i + 1, num_restarts,
+                                                                         self.optimization_runs[-1][0]))
+            except Exception:
+                if not robust:
+                    raise
+        runs = self.optimization_runs[first:]
+        if runs:
+            best = int(np.argmin([r[0] for r in runs]))
+            self._set_optimizer_array(runs[best][1])
+        else:
+            self._set_optimizer_array(initial)
+        return self
+
+    def fixed(self, **kwargs):
+        """Keep the current hyper-parameters (``method='fixed'``): the posterior is already in place."""
+        return self
+
+    def set_hyperparameters(self, variance=None, lengthscale=None, noise_variance=None, Z=None):
+        """Inject hyper-parameters (parity harness and benchmarks run at fixed values)."""
+        if variance is not None:
+            self.kern.variance = float(variance)
+        if lengthscale is not None:
+            ls = np.atleast_1d(np.asarray(lengthscale, dtype=np.float64)).copy()
+            if ls.size != self.kern.lengthscale.size:
+                raise ValueError("lengthscale has the wrong size")
+            self.kern.lengthscale = ls
+        if noise_variance is not None:
+            self.noise_variance = float(noise_variance)
+        if Z is not None:
+            Z = np.array(Z, dtype=np.float64)
+            if Z.shape != self.Z.shape:
+                raise ValueError("Z has the wrong shape")
+            self.Z = Z
+        self.parameters_changed()
+        return self
+
+    # -------------------------------------------------------------------------------------------
+    # prediction surface
+    # -------------------------------------------------------------------------------------------
+    def _grad_scale(self, scale_by_normalizer=True):
+        if self.normalizer is not None and scale_by_normalizer:
+            return float(self.normalizer.std)
+        return 1.0
+
+    def _grad_pack(self, scale):
+        return ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, float(self.kern.variance) * scale)
+
+    def gradient_gram(self, X=None, want_G=False, want_C=True, scale_by_normalizer=True, G_out=None):
+        """Posterior-mean gradients of this rank's rows and their Gram matrix, on the device.
+
+        Returns ``(G or None, C or None)``; C is NOT reduced across ranks (callers all-reduce it
+        together with whatever else they need).  ``X=None`` uses the training rows.
+        """
+        Xd = self.X if X is None else ops.pad_even(_as_device(X, self.device))
+        pack = self._grad_pack(self._grad_scale(scale_by_normalizer))
+        d = self.input_dim
+        if Xd.shape[0] == 0:
+            G = torch.empty(0, d, dtype=F64, device=self.device) if want_G else None
+            return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
+        fused = self.d_even <= 64
+        G, C = ops.grad_gram(Xd, pack, want_G=want_G or (want_C and not fused), want_C=want_C and fused, G_out=G_out)
+        self.kernel_launches += 3
+        if want_C and not fused:
+            C = ops.syrk(G)
+            self.kernel_launches += 2
+        if self.d_even != d:
+            if G is not None:
+                G = G[:, :d].contiguous()
+            if C is not None:
+                C = C[:d, :d].contiguous()
+        return (G if want_G else None), C
+
+    def predictive_gradients(self, Xnew, scale_by_normalizer=True):
+        """``GP.predictive_gradients``: (mean Jacobian (n, d, 1), None).  edr-gp keeps only
+        ``[0][:, :, 0]`` (edrgp/gp_model/base.py:222); the variance gradient GPy also returns (built
+        from an n x n matrix and discarded by edr-gp) is not computed.  Newer GPy multiplies the
+        Jacobian by std(y) when a normaliser is set; ``scale_by_normalizer`` selects that."""
+        G, _ = self.gradient_gram(Xnew, want_G=True, want_C=False, scale_by_normalizer=scale_by_normalizer)
+        return G.cpu().numpy()[:, :, None], None
+
+    def woodbury_inv(self):
+        """GPy posterior.woodbury_inv = Lm^-T (I - (I + A)^-1) Lm^-1, (m, m) on the device."""
+        if self._woodbury_inv is None:
+            m = self.num_inducing
+            eye = torch.eye(m, dtype=F64, device=self.device)
+            Bi = eye - _backsub_both_sides(self._solve.LB, eye, 'left')
+            self._woodbury_inv = _backsub_both_sides(self._solve.Lm, Bi, 'left')
+        return self._woodbury_inv
+
+    def predict(self, Xnew, want_variance=True):
+        """``GP.predict``: (mean (n, 1), variance (n, 1)) with the likelihood noise added and the
+        target normalisation undone."""
+        Xd = ops.pad_even(_as_device(Xnew, self.device))
+        n = Xd.shape[0]
+        m = self.num_inducing
+        sf2 = float(self.kern.variance)
+        pack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, 1.0)
+        mu = torch.empty(n, dtype=F64, device=self.device)
+        var = torch.empty(n, dtype=F64, device=self.device) if want_variance else None
+        W = ops.even_ld(self.woodbury_inv()) if want_variance else None
+        rows = max(2, min(self.chunk_rows, n))
+        ldk = m + (m & 1)
+        Kb = torch.empty(rows, ldk, dtype=F64, device=self.device) if want_variance else None
+        for s in range(0, n, rows):
+            e = min(n, s + rows)
+            K, _, mu_c = ops.kuf(Xd[s:e], pack, sf2, out=None if Kb is None else Kb[:e - s], want_K=want_variance,
+                                 want_mu=True)
+            mu[s:e] = mu_c
+            if want_variance:
+                q = ops.weights(Kb[:e - s], W, m, c_km=1.0, want_rowsum=True)
+                var[s:e] = torch.clamp(sf2 - q, min=1e-15) + float(self.noise_variance)
+        mu = mu.cpu().numpy()[:, None]
+        if var is not None:
+            var = var.cpu().numpy()[:, None]
+        if self.normalizer is not None:
+            mu = self.normalizer.inverse_mean(mu)
+            if var is not None:
+                var = self.normalizer.inverse_variance(var)
+        return mu, var
+
+    # -------------------------------------------------------------------------------------------
+    # persistence: plain arrays (edrgp/gp_model/base.py:224-257 pickles the GPy model)
+    # -------------------------------------------------------------------------------------------
+    def state_dict(self):
+        st = {'Z': self.Z.copy(), 'variance': self.kern.variance, 'lengthscale': self.kern.lengthscale.copy(),
+              'ARD': self.kern.ARD, 'noise_variance': self.noise_variance, 'input_dim': self.input_dim,
+              'alpha': self.alpha.cpu().numpy(), 'num_data': self.num_data,
+              'log_likelihood': float(self._log_marginal_likelihood[0, 0]),
+              'Lm': self._solve.Lm.cpu().numpy(), 'LB': self._solve.LB.cpu().numpy()}
+        if self.normalizer is not None:
+            st['y_mean'], st['y_std'] = self.normalizer.mean, self.normalizer.std
+        return st
+
+
+class FittedSparseGP(SparseGPRegression):
+    """A model restored from ``state_dict`` (no training rows): prediction surface only."""
+
+    def __init__(self, state, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("edrgp_b200 needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.input_dim = int(state['input_dim'])
+        self.d_even = self.input_dim + (self.input_dim & 1)
+        self.kern = RBF(self.input_dim, state['variance'], state['lengthscale'], state['ARD'])
+        self.Z = np.array(state['Z'], dtype=np.float64)
+        self.num_inducing = self.Z.shape[0]
+        self.noise_variance = float(state['noise_variance'])
+        self.num_data = int(state['num_data'])
+        self.n_local = 0
+        self.chunk_rows = 262144
+        self.kernel_launches = 0
+        self.optimization_runs = []
+        if 'y_mean' in state:
+            self.normalizer = Standardize()
+            self.normalizer.mean, self.normalizer.std = float(state['y_mean']), float(state['y_std'])
+        else:
+            self.normalizer = None
+        self._log_marginal_likelihood = np.array([[float(state['log_likelihood'])]])
+        ell = np.ones(self.d_even)
+        ell[:self.input_dim] = self.kern.full_lengthscale()
+        self._ell_dev = torch.as_tensor(ell, device=self.device)
+        Zp = np.zeros((self.num_inducing, self.d_even))
+        Zp[:, :self.input_dim] = self.Z
+        self._Z_dev = torch.as_tensor(Zp, device=self.device)
+        self.alpha = torch.as_tensor(np.asarray(state['alpha'], dtype=np.float64), device=self.device)
+        sr = ops.SolveResult()
+        sr.Lm = torch.as_tensor(np.asarray(state['Lm'], dtype=np.float64), device=self.device)
+        sr.LB = torch.as_tensor(np.asarray(state['LB'], dtype=np.float64), device=self.device)
+        self._solve = sr
+        self._woodbury_inv = None
+        self.X = None
+
+    def parameters_changed(self):
+        raise RuntimeError("a restored model has no training rows; refit to change hyper-parameters")
+
+    def gradient_gram(self, X=None, **kw):
+        if X is None:
+            raise ValueError("a restored model has no training rows: pass X")
+        return SparseGPRegression.gradient_gram(self, X, **kw)

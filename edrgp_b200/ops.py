@@ -102,17 +102,56 @@ def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
     return G, C
 
 
-def syrk(A, k=None):
-    """C = A[:, :k]^T A[:, :k] for a tall (n, lda) tensor (lda even)."""
+def syrk(A, k=None, out=None, accumulate=False):
+    """C (+)= A[:, :k]^T A[:, :k] for a tall (n, lda) tensor (lda even)."""
     lib = _lib.load()
-    _need_cuda(A)
+    _need_cuda(A, out)
     n, lda = A.shape
     k = lda if k is None else k
     if lda % 2:
         raise ValueError("syrk needs an even leading dimension")
-    C = torch.empty(k, k, dtype=F64, device=A.device)
+    C = out if out is not None else torch.empty(k, k, dtype=F64, device=A.device)
     ws = torch.empty(max(1, lib.edrgp_syrk_workspace_bytes(n, k) // 8), dtype=F64, device=A.device)
-    _lib.check(lib.edrgp_syrk(_ptr(A), n, k, lda, _ptr(C), k, _ptr(ws), _stream()), 'edrgp_syrk')
+    _lib.check(lib.edrgp_syrk(_ptr(A), n, k, lda, _ptr(C), k, int(bool(accumulate and out is not None)),
+                              _ptr(ws), _stream()), 'edrgp_syrk')
+    return C
+
+
+def inducing_stats(K, y, m=None, P=None, b_yy=None, accumulate=False):
+    """P (+)= K^T K, b_yy[:m] (+)= K^T y, b_yy[m] (+)= y^T y from a stored cross-covariance block
+    K (n, ldk) (ldk even, first m columns used)."""
+    lib = _lib.load()
+    _need_cuda(K, y, P, b_yy)
+    n, ldk = K.shape
+    m = ldk if m is None else m
+    if ldk % 2:
+        raise ValueError("inducing_stats needs an even leading dimension")
+    fresh = P is None or b_yy is None
+    if P is None:
+        P = torch.empty(m, m, dtype=F64, device=K.device)
+    if b_yy is None:
+        b_yy = torch.empty(m + 1, dtype=F64, device=K.device)
+    ws = torch.empty(max(1, lib.edrgp_syrk_workspace_bytes(n, m) // 8), dtype=F64, device=K.device)
+    _lib.check(lib.edrgp_inducing_stats(_ptr(K), n, m, ldk, _ptr(y), _ptr(P), m, _ptr(b_yy),
+                                        int(bool(accumulate and not fresh)), _ptr(ws), _stream()),
+               'edrgp_inducing_stats')
+    return P, b_yy
+
+
+def gemm_tn(A, B, ka=None, kb=None, out=None, accumulate=False):
+    """C (+)= A[:, :ka]^T B[:, :kb] for tall row-major A (n, lda), B (n, ldb)."""
+    lib = _lib.load()
+    _need_cuda(A, B, out)
+    n, lda = A.shape
+    ldb = B.shape[1]
+    ka = lda if ka is None else ka
+    kb = ldb if kb is None else kb
+    if lda % 2 or ldb % 2 or B.shape[0] != n:
+        raise ValueError("gemm_tn needs even leading dimensions and matching row counts")
+    C = out if out is not None else torch.empty(ka, kb, dtype=F64, device=A.device)
+    ws = torch.empty(max(1, lib.edrgp_gemm_tn_workspace_bytes(n, ka, kb) // 8), dtype=F64, device=A.device)
+    _lib.check(lib.edrgp_gemm_tn(_ptr(A), lda, ka, _ptr(B), ldb, kb, n, _ptr(C), kb,
+                                 int(bool(accumulate and out is not None)), _ptr(ws), _stream()), 'edrgp_gemm_tn')
     return C
 
 
@@ -128,7 +167,7 @@ def kmm(pack, sf2, jitter=1e-8):
 
 
 class SolveResult(object):
-    __slots__ = ('alpha', 'c', 'Lm', 'LB', 'scalars', 'info')
+    __slots__ = ('alpha', 'c', 'Lm', 'LB', 'B', 'scalars', 'info')
 
 
 def solve(Kmm, P, b, beta):
@@ -145,6 +184,7 @@ def solve(Kmm, P, b, beta):
     out.scalars = torch.empty(4, dtype=F64, device=dev)
     out.info = torch.zeros(2, dtype=torch.int32, device=dev)
     ws = torch.empty(lib.edrgp_solve_workspace_bytes(m) // 8, dtype=F64, device=dev)
+    out.B = ws[:m * m].view(m, m)            # I + A = I + beta Lm^-1 P Lm^-T, kept by the chain
     _lib.check(lib.edrgp_solve(_ptr(Kmm), _ptr(P), _ptr(b), m, float(beta), _ptr(out.LB), _ptr(out.alpha),
                                _ptr(out.c), _ptr(out.scalars), _ptr(out.info), _ptr(ws), _stream()), 'edrgp_solve')
     return out
@@ -174,18 +214,47 @@ def eigh(C):
     return evals, comps
 
 
-def col_moments(X, shift=None):
-    """(sum_i (x - shift), sum_i (x - shift)^2) per column, each of shape (d,)."""
+def col_moments(X, shift=None, weight=None, out=None, accumulate=False):
+    """(sum_i w_i (x - shift), sum_i w_i (x - shift)^2) per column, each of shape (d,)."""
     lib = _lib.load()
     if X.dim() == 1:
         X = X[:, None]
-    _need_cuda(X, shift)
+    _need_cuda(X, shift, weight, out)
     n, d = X.shape
-    out = torch.empty(2 * d, dtype=F64, device=X.device)
+    acc = int(bool(accumulate and out is not None))
+    if out is None:
+        out = torch.empty(2 * d, dtype=F64, device=X.device)
     ws = torch.empty(lib.edrgp_col_moments_workspace_bytes(d) // 8, dtype=F64, device=X.device)
-    _lib.check(lib.edrgp_col_moments(_ptr(X), n, d, _ptr(shift), _ptr(out), _ptr(ws), _stream()),
-               'edrgp_col_moments')
+    _lib.check(lib.edrgp_col_moments(_ptr(X), n, d, _ptr(shift), _ptr(weight), _ptr(out), acc, _ptr(ws),
+                                     _stream()), 'edrgp_col_moments')
     return out[:d], out[d:]
+
+
+def even_ld(M):
+    """Row-major (r, c) tensor with an even leading dimension (zero padding column if c is odd)."""
+    if M.shape[1] % 2 == 0:
+        return M.contiguous()
+    out = torch.zeros(M.shape[0], M.shape[1] + 1, dtype=F64, device=M.device)
+    out[:, :M.shape[1]] = M
+    return out
+
+
+def weights(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, want_rowsum=False, colsum=None,
+            accumulate=False):
+    """T = K o (c_ya y alpha^T + c_km K M); returns (rowsum or None).  K (n, ldk), M (m, ldm) with even
+    leading dimensions; T (n, ldt) is filled when given; colsum (m) is (+)= T^T 1 when given."""
+    lib = _lib.load()
+    _need_cuda(K, M, y, alpha, T, colsum)
+    n, ldk = K.shape
+    m = ldk if m is None else m
+    rowsum = torch.empty(n, dtype=F64, device=K.device) if want_rowsum else None
+    ws = None
+    if want_rowsum or colsum is not None:
+        ws = torch.empty(max(1, lib.edrgp_weights_workspace_bytes(n, m) // 8), dtype=F64, device=K.device)
+    _lib.check(lib.edrgp_weights(_ptr(K), n, m, ldk, _ptr(M), M.shape[1], _ptr(y), _ptr(alpha), float(c_ya),
+                                 float(c_km), _ptr(T), 0 if T is None else T.shape[1], _ptr(rowsum), _ptr(colsum),
+                                 int(bool(accumulate)), _ptr(ws), _stream()), 'edrgp_weights')
+    return rowsum
 
 
 def standardize(X, mean, scale, out=None):

@@ -1,0 +1,85 @@
+"""``GramEighTransformer``: drop-in for edr-gp's ``SVDTransformer`` (``edrgp/utils.py:81-175``,
+"PCA without centering and scaling") that never forms the n x n ``U`` of a full SVD.
+
+The right singular vectors of G are the eigenvectors of C = G^T G and S^2 its eigenvalues, so
+``fit(G)`` reduces G to the d x d Gram matrix on the FP64 tensor pipe (``edrgp_syrk``) and
+eigendecomposes it with the Jacobi kernel (``edrgp_eigh``).  ``fit_gram(C)`` takes a Gram matrix
+that is already on hand -- the fused gradient kernel produces it without G ever leaving the chip.
+"""
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils import check_array
+
+from . import dist, ops
+
+F64 = torch.float64
+
+
+class GramEighTransformer(BaseEstimator, TransformerMixin):
+    """Linear dimensionality reduction without centring.
+
+    Parameters
+    ----------
+    n_components : int, float or None
+        As ``SVDTransformer``: None keeps all; an int keeps that many; a float in (0, 1) keeps the
+        smallest number of components whose cumulative variance ratio reaches it.
+
+    Attributes
+    ----------
+    components_ : (n_components, n_features)   rows = directions, descending variance
+    subspace_variance_ : (n_components,)        S^2 of the gradients (eigenvalues of G^T G)
+    subspace_variance_ratio_ : (n_components,)  S^2 / sum(S^2)
+    gram_ : (n_features, n_features)            the Gram matrix that was decomposed
+    """
+
+    def __init__(self, n_components=None):
+        self.n_components = n_components
+
+    def fit(self, X, y=None):
+        """Fit on gradients X (n, d): host array or CUDA tensor (this rank's rows)."""
+        if isinstance(X, torch.Tensor):
+            Xd = X.to(dtype=F64).contiguous()
+            if not Xd.is_cuda:
+                Xd = Xd.cuda()
+        else:
+            X = check_array(X, dtype=np.float64)
+            Xd = torch.as_tensor(np.ascontiguousarray(X), device='cuda')
+        n, d = Xd.shape
+        C = ops.syrk(ops.pad_even(Xd))[:d, :d].contiguous()
+        cnt = torch.tensor([float(n)], dtype=F64, device=C.device)
+        dist.allreduce_sum_(C, cnt)
+        return self.fit_gram(C, int(round(float(cnt[0]))))
+
+    def fit_gram(self, C, n_samples=None):
+        """Fit from C = G^T G (d, d), already summed over all rows (and ranks)."""
+        if not isinstance(C, torch.Tensor):
+            C = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64), device='cuda')
+        d = C.shape[0]
+        evals, comps = ops.eigh(C)
+        S2 = np.clip(evals.cpu().numpy(), 0.0, np.inf)
+        comps = comps.cpu().numpy()
+        total = S2.sum()
+        ratio = S2 / total if total > 0 else np.zeros_like(S2)
+        nc = self.n_components
+        k = d
+        if nc is None:
+            k = d
+        elif isinstance(nc, (int, np.integer)) and 0 < nc <= d:
+            k = int(nc)
+        elif isinstance(nc, float) and 0 < nc < 1:
+            k = int(np.sum(np.cumsum(ratio) < nc, dtype=int)) + 1
+        if n_samples is not None:
+            k = min(int(n_samples), k)
+        self.gram_ = C.cpu().numpy()
+        self.components_ = comps[:k, :]
+        self.subspace_variance_ = S2[:k]
+        self.subspace_variance_ratio_ = ratio[:k]
+        return self
+
+    def transform(self, X):
+        """Project X (n, d) on the components: host in, host out; CUDA tensor in, CUDA tensor out."""
+        if isinstance(X, torch.Tensor):
+            V = torch.as_tensor(np.ascontiguousarray(self.components_), device=X.device)
+            return ops.project(X.contiguous(), V)
+        return np.asarray(X).dot(self.components_.T)

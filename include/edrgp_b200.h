@@ -58,9 +58,10 @@ int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, 
  * K1  cross-covariance  Kfu = sf2 * exp(-0.5 * clip(|x/l|^2 + |z/l|^2 - 2 (x/l).(z/l), 0)).
  * Replaces GPy RBF.K(X, Z) (edrgp/gp_model/base.py:69 through VarDTC.inference, and :187).
  * Kfu is (n, ldk) row-major with ldk >= m, ldk even; may be NULL.  Optionally accumulates
- * b += Kfu^T y (y, b may be NULL; b must be zeroed by the caller) and writes the row sums
- * mu_i = sum_j Kfu_ij coef_j (mu may be NULL) -- with coef = alpha in the pack this is the posterior
- * mean K(x, Z) alpha of GPy Posterior._raw_predict (edrgp/gp_model/base.py:187).
+ * b += Kfu^T y (y, b may be NULL; b must be zeroed by the caller; atomics -- the deterministic
+ * route is edrgp_inducing_stats) and writes mu_i = sum_j Kfu_ij coef_j (mu may be NULL): with
+ * coef = alpha in the pack this is the posterior mean K(x, Z) alpha of GPy Posterior._raw_predict
+ * (edrgp/gp_model/base.py:187).  The stored entries never carry the pack coefficient.
  * ------------------------------------------------------------------------------------------- */
 int edrgp_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2,
               double* Kfu, int64_t ldk, const double* y, double* b, double* mu, void* stream);
@@ -81,14 +82,42 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
                     double* G, double* C, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * K2 / K5  C = A^T A for a tall row-major A (n, lda), k columns (k <= lda, lda even, A 16-byte
- * aligned).  Replaces GPy tdot (dsyrk) inside VarDTC.inference for P = Kuf Kfu
- * (edrgp/gp_model/base.py:69) and the Gram matrix of the gradients when d > 64
- * (edrgp/utils.py:140).  C (k, ldc) is overwritten, full symmetric.
+ * K2 / K5  tall-skinny reductions on the FP64 tensor pipe.  All matrices row-major, leading
+ * dimensions even, base pointers 16-byte aligned; results are deterministic (fixed-order split-K
+ * reduction, no atomics); accumulate != 0 adds to the output instead of overwriting it (row chunks).
+ *
+ *  edrgp_syrk            C (k, ldc) (+)= A^T A, full symmetric.  Replaces GPy tdot (dsyrk) and the
+ *                        Gram matrix behind np.linalg.svd(G) when d > 64 (edrgp/utils.py:140).
+ *  edrgp_inducing_stats  P (m, ldp) (+)= Kfu^T Kfu,  b_yy[0..m) (+)= Kfu^T y,  b_yy[m] (+)= y^T y:
+ *                        the n-reduced statistics of GPy VarDTC.inference (psi2 = tdot(psi1^T),
+ *                        psi1^T Y, trYYT) reached from edrgp/gp_model/base.py:69.
+ *  edrgp_gemm_tn         C (ka, ldc) (+)= A^T B for A (n, lda), B (n, ldb): T^T X of the
+ *                        hyper-parameter gradients (GPy Stationary.gradients_X w.r.t. Z and
+ *                        update_gradients_full, reached from model.optimize, base.py:69).
+ * workspace: edrgp_syrk_workspace_bytes(n, k) for the first two, edrgp_gemm_tn_workspace_bytes.
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_syrk_workspace_bytes(int64_t n, int k);
-int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc,
+int edrgp_syrk(const double* A, int64_t n, int k, int64_t lda, double* C, int64_t ldc, int accumulate,
                void* workspace, void* stream);
+int edrgp_inducing_stats(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double* P,
+                         int64_t ldp, double* b_yy, int accumulate, void* workspace, void* stream);
+size_t edrgp_gemm_tn_workspace_bytes(int64_t n, int ka, int kb);
+int edrgp_gemm_tn(const double* A, int64_t lda, int ka, const double* B, int64_t ldb, int kb, int64_t n,
+                  double* C, int64_t ldc, int accumulate, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * T = Kfu o (c_ya * y alpha^T + c_km * Kfu M) for a stored cross-covariance block Kfu (n, ldk) and an
+ * (m, ldm) matrix M; optional outputs T (n, ldt), rowsum (n) = T 1, colsum (m) (+)= T^T 1.
+ *  - M = dL/dpsi2, c_ya = beta, c_km = 2:  T = Kfu o dL/dKfu of GPy VarDTC.inference, the weight
+ *    matrix of Stationary.update_gradients_full / gradients_X (model.optimize,
+ *    edrgp/gp_model/base.py:69);
+ *  - M = woodbury_inv, c_ya = 0 (y = alpha = NULL), c_km = 1: rowsum_i = k_i^T W k_i of the
+ *    predictive variance (GPy Posterior._raw_predict, edrgp/gp_model/base.py:206).
+ * ------------------------------------------------------------------------------------------- */
+size_t edrgp_weights_workspace_bytes(int64_t n, int m);
+int edrgp_weights(const double* Kfu, int64_t n, int m, int64_t ldk, const double* M, int64_t ldm,
+                  const double* y, const double* alpha, double c_ya, double c_km, double* T, int64_t ldt,
+                  double* rowsum, double* colsum, int accumulate, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kuu = K(Z, Z) with the diagonal forced to sf2 + jitter (GPy Stationary._unscaled_dist zeroes the
@@ -129,8 +158,8 @@ int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void
 
 /* ---------------------------------------------------------------------------------------------
  * Streaming row kernels around the path (HBM-bound).
- *  edrgp_col_moments: out[q] = sum_i (x_iq - shift_q), out[d + q] = sum_i (x_iq - shift_q)^2
- *      (shift may be NULL).  Two calls give the mean and the centred second moment of
+ *  edrgp_col_moments: out[q] (+)= sum_i w_i (x_iq - shift_q), out[d + q] (+)= sum_i w_i (x_iq - shift_q)^2
+ *      (shift, weight may be NULL; weight = rowsum(T) gives the lengthscale-gradient moment).  Two calls give the mean and the centred second moment of
  *      StandardScaler (edrgp/edr.py:161-162) and of GPy's Standardize on y; the sums are what an
  *      n-sharded run all-reduces.  d <= 512.
  *  edrgp_standardize: out = (X - mean) / scale, elementwise by column (in place allowed).
@@ -138,8 +167,8 @@ int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void
  *      (edrgp/edr.py:261-289, edrgp/base.py:462).
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_col_moments_workspace_bytes(int d);
-int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, double* out,
-                      void* workspace, void* stream);
+int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
+                      double* out, int accumulate, void* workspace, void* stream);
 int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale,
                       double* out, void* stream);
 int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, double* out,

@@ -28,6 +28,44 @@ def test_syrk_matches_numpy(n, k):
     assert np.array_equal(C, C.T)
 
 
+@pytest.mark.parametrize("n,m", [(1000, 20), (4097, 256), (33333, 512), (777, 33), (15, 130), (1, 6)])
+def test_inducing_stats_match_numpy_and_accumulate(n, m):
+    """P = K^T K, b = K^T y, yy = y^T y in one deterministic pass; two row chunks accumulate."""
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(n + m)
+    ldk = m + (m & 1)
+    K = rng.standard_normal((n, ldk))
+    y = rng.standard_normal(n)
+    P, byy = ops.inducing_stats(_dev(K), _dev(y), m)
+    Kc = K[:, :m]
+    assert _relerr(P.cpu().numpy(), Kc.T.dot(Kc)) < 1e-12
+    assert _relerr(byy[:m].cpu().numpy(), Kc.T.dot(y)) < 1e-12
+    assert abs(float(byy[m]) - y.dot(y)) < 1e-12 * y.dot(y)
+    assert np.array_equal(P.cpu().numpy(), P.cpu().numpy().T)
+    if n >= 2:
+        h = n // 2 + (n // 2) % 2          # even split keeps y 16-byte aligned
+        if 0 < h < n:
+            P2, byy2 = ops.inducing_stats(_dev(K[:h]), _dev(y[:h]), m)
+            ops.inducing_stats(_dev(K[h:]), _dev(y[h:]), m, P=P2, b_yy=byy2, accumulate=True)
+            assert _relerr(P2.cpu().numpy(), Kc.T.dot(Kc)) < 1e-12
+            assert _relerr(byy2[:m].cpu().numpy(), Kc.T.dot(y)) < 1e-12
+    # run-to-run determinism
+    P3, byy3 = ops.inducing_stats(_dev(K), _dev(y), m)
+    assert torch.equal(P, P3) and torch.equal(byy, byy3)
+
+
+@pytest.mark.parametrize("n,ka,kb", [(1000, 20, 6), (5000, 256, 64), (20000, 512, 64), (777, 34, 10), (4000, 130, 200)])
+def test_gemm_tn_matches_numpy(n, ka, kb):
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(n + ka)
+    A = rng.standard_normal((n, ka))
+    B = rng.standard_normal((n, kb))
+    C = ops.gemm_tn(_dev(A), _dev(B))
+    assert _relerr(C.cpu().numpy(), A.T.dot(B)) < 1e-12
+    C = ops.gemm_tn(_dev(A), _dev(B), out=C, accumulate=True)
+    assert _relerr(C.cpu().numpy(), 2 * A.T.dot(B)) < 1e-12
+
+
 @pytest.mark.parametrize("n,d,m", [(500, 10, 20), (2000, 6, 25), (4096, 32, 256), (3000, 64, 512), (900, 7, 33)])
 def test_stats_and_solve_match_oracle(n, d, m):
     from edrgp_b200 import ops

@@ -1,0 +1,170 @@
+"""Parity of the device model / estimator / EDR classes against the CPU oracle (the NumPy
+restatement of GPy) on the same seeded inputs, through the public Python API (which reaches the
+kernels through the C ABI).
+
+Tolerances: posterior mean, gradients, EDR matrices 1e-8 relative (BASELINE.json north_star);
+principal angle 1e-6.  alpha itself amplifies rounding by cond(Kuu + beta P), so it is compared
+through what the path consumes (K alpha and the gradients)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import gpy_restatement as gpy          # noqa: E402  (the checker, never the product)
+from oracle import pipeline as op                  # noqa: E402
+from oracle import estimator as oest               # noqa: E402
+
+
+def _relerr(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+
+
+def _oracle_model(w, normalizer=None, ARD=True):
+    kern = gpy.RBF(w['X'].shape[1], w['sf2'], w['ell'] if ARD else float(np.mean(w['ell'])), ARD=ARD)
+    mod = gpy.SparseGPRegression(w['X'], w['y'][:, None], kernel=kern, Z=w['Z'], normalizer=normalizer)
+    mod.noise_variance = w['noise']
+    mod.parameters_changed()
+    return mod
+
+
+def _device_model(w, normalizer=None, ARD=True, **kw):
+    from edrgp_b200 import model
+    kern = model.RBF(w['X'].shape[1], w['sf2'], w['ell'] if ARD else float(np.mean(w['ell'])), ARD=ARD)
+    mod = model.SparseGPRegression(w['X'], w['y'][:, None], kernel=kern, Z=w['Z'], normalizer=normalizer, **kw)
+    mod.set_hyperparameters(noise_variance=w['noise'])
+    return mod
+
+
+@pytest.mark.parametrize("n,d,m", [(500, 10, 20), (1500, 7, 33), (4096, 32, 256), (2500, 64, 512)])
+@pytest.mark.parametrize("normalizer", [None, True])
+def test_posterior_bound_and_predictions(n, d, m, normalizer):
+    w = op.make_workload(n, d, m, seed=n + m, k_true=2)
+    w['y'] = 3.0 * w['y'] + 1.5                      # make the normaliser do something
+    ref = _oracle_model(w, normalizer)
+    mod = _device_model(w, normalizer, chunk_rows=1024)
+    ll, ll_ref = mod.log_likelihood(), ref.log_likelihood()
+    assert ll.shape == (1, 1)
+    assert abs(ll[0, 0] - ll_ref[0, 0]) < 1e-9 * abs(ll_ref[0, 0])
+    Xnew = np.random.RandomState(5).standard_normal((333, d))
+    mu, var = mod.predict(Xnew)
+    mu_ref, var_ref = ref.predict(Xnew)
+    assert mu.shape == (333, 1) and var.shape == (333, 1)
+    assert _relerr(mu, mu_ref) < 1e-8
+    assert _relerr(var, var_ref) < 1e-8
+    G = mod.predictive_gradients(Xnew)[0]
+    G_ref = ref.predictive_gradients(Xnew)[0]
+    assert G.shape == (333, d, 1)
+    assert _relerr(G, G_ref) < 1e-8
+
+
+@pytest.mark.parametrize("n,d,m,ARD", [(400, 6, 25, True), (700, 5, 16, False), (2000, 32, 130, True)])
+def test_hyperparameter_gradients_match_oracle(n, d, m, ARD):
+    """dL/d{Z, variance, lengthscale, noise} of the VFE bound (GPy SparseGP._update_gradients)."""
+    w = op.make_workload(n, d, m, seed=n, k_true=2)
+    ref = _oracle_model(w, True, ARD)
+    mod = _device_model(w, True, ARD, chunk_rows=1024)
+    mod._need_grad = True
+    mod.parameters_changed()
+    mod._need_grad = False
+    assert abs(mod.grad_variance - ref.grad_variance) < 1e-8 * max(1.0, abs(ref.grad_variance))
+    assert abs(mod.grad_noise - ref.grad_noise) < 1e-8 * max(1.0, abs(ref.grad_noise))
+    assert _relerr(mod.grad_lengthscale, ref.grad_lengthscale) < 1e-7
+    assert _relerr(mod.grad_Z, ref.grad_Z) < 1e-7
+    # and through the Logexp transform, as the optimiser sees them
+    assert _relerr(mod._transformed_gradients(), ref._transformed_gradients()) < 1e-7
+
+
+def test_gradient_cache_and_recompute_agree():
+    w = op.make_workload(3000, 8, 40, seed=3, k_true=2)
+    a = _device_model(w, True, chunk_rows=1024, cache_bytes=0)          # recompute Kfu in pass 2
+    b = _device_model(w, True, chunk_rows=1024)                          # cached Kfu
+    for mod in (a, b):
+        mod._need_grad = True
+        mod.parameters_changed()
+    assert a._Kcache is None and b._Kcache is not None
+    assert np.array_equal(a.grad_Z, b.grad_Z)
+    assert a.grad_variance == b.grad_variance
+
+
+def test_optimize_improves_bound_like_the_oracle():
+    """L-BFGS trajectories are not comparable at 1e-8; the reached bound is."""
+    w = op.make_workload(600, 4, 15, seed=9, k_true=1)
+    from edrgp_b200 import model
+    np.random.seed(0)
+    ref = gpy.SparseGPRegression(w['X'], w['y'][:, None], kernel=gpy.RBF(4, ARD=True), Z=w['Z'], normalizer=True)
+    ll0 = float(ref.log_likelihood()[0, 0])
+    ref.optimize(max_iters=60)
+    mod = model.SparseGPRegression(w['X'], w['y'][:, None], kernel=model.RBF(4, ARD=True), Z=w['Z'], normalizer=True)
+    assert abs(float(mod.log_likelihood()[0, 0]) - ll0) < 1e-9 * abs(ll0)
+    mod.optimize(max_iters=60)
+    ll_ref, ll_dev = float(ref.log_likelihood()[0, 0]), float(mod.log_likelihood()[0, 0])
+    assert ll_dev > ll0 + 10.0
+    assert abs(ll_dev - ll_ref) < 1e-3 * abs(ll_ref)
+
+
+def test_sparse_vs_dense_loglik_like_reference_test():
+    """edrgp/tests/test_edr.py:33-50 with the data drawn from the restated RBF prior: the sparse bound
+    of the B200 estimator stays within 0.5 nats of the dense GP's log-likelihood."""
+    from edrgp_b200 import SparseGaussianProcessRegressor
+    np.random.seed(101)
+    N = 50
+    noise_var = 0.05
+    X = np.linspace(0, 10, 50)[:, None]
+    k = gpy.RBF(1)
+    y = np.random.multivariate_normal(np.zeros(N), k.K(X) + np.eye(N) * np.sqrt(noise_var))
+    gp = oest.GaussianProcessRegressor()
+    gp.fit(X, y)
+    sgp = SparseGaussianProcessRegressor(num_inducing=12)
+    sgp.fit(X, y)
+    assert abs(gp.estimator_.log_likelihood() - sgp.estimator_.log_likelihood()[0][0]) < 0.5
+
+
+def test_estimator_errors_and_persistence(tmp_path):
+    from sklearn.exceptions import NotFittedError
+    from edrgp_b200 import SparseGaussianProcessRegressor
+    w = op.make_workload(300, 5, 12, seed=1, k_true=1)
+    est = SparseGaussianProcessRegressor('RBF', {'ARD': True}, num_inducing=12, method='fixed')
+    with pytest.raises(NotFittedError):
+        est.n_features_ = 5
+        est.predict(w['X'])
+    np.random.seed(4)
+    est.fit(w['X'], w['y'])
+    with pytest.raises(ValueError):
+        est.predict_gradient(np.zeros((3, 4)))
+    with pytest.raises(ValueError):
+        SparseGaussianProcessRegressor(['RBF'], [{'ARD': True}, {}]).fit(w['X'], w['y'])
+    with pytest.raises(NotImplementedError):
+        SparseGaussianProcessRegressor('Matern32').fit(w['X'], w['y'])
+    with pytest.raises(ValueError):
+        est.fit(np.full((10, 5), np.nan), np.zeros(10))
+    g = est.predict_gradient(w['X'][:50])
+    p = str(tmp_path / 'model')
+    est.save(p)
+    est2 = SparseGaussianProcessRegressor()
+    est2.load(p)
+    assert np.array_equal(est2.predict_gradient(w['X'][:50]), g)
+    assert np.array_equal(est2.predict(w['X'][:50]), est.predict(w['X'][:50]))
+    assert _relerr(est2.predict_variance(w['X'][:50]), est.predict_variance(w['X'][:50])) < 1e-12
+
+
+def test_transformer_matches_svd():
+    from edrgp_b200 import GramEighTransformer
+    rng = np.random.RandomState(0)
+    G = rng.standard_normal((5000, 12)) * np.linspace(4, 0.2, 12)
+    Vh, S2, ratio = op.svd_faithful(G, 4)
+    tr = GramEighTransformer(n_components=4).fit(G)
+    assert tr.components_.shape == (4, 12)
+    assert np.allclose(tr.subspace_variance_, S2, rtol=1e-11)
+    assert np.allclose(tr.subspace_variance_ratio_, ratio, rtol=1e-11)
+    assert op.principal_angle(tr.components_, Vh) < 1e-6
+    for a, b in zip(tr.components_, Vh):                 # same directions up to sign
+        assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-9
+    assert np.allclose(tr.transform(G), G.dot(tr.components_.T))
+    tr2 = GramEighTransformer(n_components=0.9).fit(G)
+    assert tr2.components_.shape[0] == int(np.sum(np.cumsum(S2_all(G)) < 0.9)) + 1
+
+
+def S2_all(G):
+    s = np.linalg.svd(G, compute_uv=False) ** 2
+    return s / s.sum()
