@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 sparse-GP posterior-gradient EDR path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): EDR fit points/sec at n=4M, d=64, m=512.  One *step* is one
+fixed-hyper-parameter EDR sweep over the whole synthetic data set ("full
+sweep"): Kfu blocks -> inducing statistics P, b, yy -> [all-reduce] -> m x m Cholesky chain -> alpha
+-> posterior-mean gradients -> G^T G -> [all-reduce] -> eigh -> EDR directions.  The n = 4M rows
+are sharded over the N ranks (strong scaling: the named shape is the total).
+
+  value  rows / s with the rows already resident in HBM (device tensors passed to the same API)
+  e2e    rows / s through the public estimator API with HOST (pinned) buffers: every step copies X
+         and y to the device and reads the EDR directions back
+  roofline          the dominant kernel (symmetric DMMA reduction P = Kfu^T Kfu) against the FP64
+                    tensor-pipe peak measured live by edrgp_fp64_probe
+  roofline_pipeline the fused Kuf + gradient + G^T G kernel (the north-star 60 % target)
+  cpu_baseline      the NumPy oracle (oracle/pipeline.py, kind "port": GPy is not installable
+                    here) timed on the box's host cores on a bounded row sample of the same workload
+
+--impl reference times that CPU port alone, on all host threads, each step a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "EDR fit points/sec at n=4M,d=64,m=512"
+UNIT = "points/s"
+N_TOTAL, D, M, K_TRUE = 4_000_000, 64, 512, 3
+NOISE, SF2 = 0.1, 1.0
+
+
+def flops_per_point(d, m):
+    """Algorithmic FP64 flops per point of one sweep (symmetric halves NOT
+    discounted): stats 2md + 2m^2 + 3m, pipeline 4md + 2d^2 + m."""
+    return {'stats': 2.0 * m * d + 2.0 * m * m + 3.0 * m, 'pipeline': 4.0 * m * d + 2.0 * d * d + m,
+            'syrk': 2.0 * m * m + 2.0 * m, 'syrk_executed': 1.0 * m * (m + 128) + 2.0 * m}
+
+
+def hyper(d, seed=0):
+    return np.sqrt(d) * (1. + 0.5 * np.random.RandomState(seed + 1).uniform(size=d))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_sweep(X, y, Z, ell, sf2, noise, k):
+    from oracle import pipeline as op
+    n = X.shape[0]
+    P, b, yy = op.inducing_stats_chunked(X, y, Z, ell, sf2)
+    Kmm = op.kuu(Z, ell, sf2)
+    sol = op.solve_from_stats(Kmm, P, b, yy, n, sf2, noise)
+    C = op.grad_gram_chunked(X, Z, ell, sf2, sol['alpha'])
+    comps, lam, ratio = op.edr_from_gram(C, k)
+    return comps
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        info = threadpool_info()
+        return max([i.get('num_threads', 1) for i in info] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_cpu_sample(rows, d, m, seed=0):
+    from oracle import pipeline as op
+    w = op.make_workload(rows, d, m, seed=seed, k_true=K_TRUE)
+    w['ell'] = hyper(d, seed)
+    return w
+
+
+def time_cpu(rows, d, m, steps, warmup):
+    w = make_cpu_sample(rows, d, m)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu_sweep(w['X'], w['y'], w['Z'], w['ell'], SF2, NOISE, K_TRUE)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return rows / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rows = args.cpu_rows or 131072
+    cores = cpu_threads()
+    pts, sec = time_cpu(rows, args.d, args.m, args.steps, args.warmup)
+    sample = "%d rows of the same generator per step (n=%d named shape), all host BLAS threads" % (rows, args.n)
+    line = {"impl": "reference", "metric": METRIC, "value": pts, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "n": args.n, "d": args.d, "m": args.m,
+                       "hyperparameters": "fixed", "note": "CPU port of the reference path (GPy not installable): "
+                       "oracle/pipeline.py chunked NumPy/OpenBLAS; O(n^2) steps of the reference replaced as BASELINE.md section 2"},
+            "cpu_baseline": {"value": pts, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pts, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return ("C3 headline: n=%d d=%d m=%d ARD-RBF sparse-GP EDR sweep at fixed hyper-parameters "
+            "(stats + solve + posterior gradients + GtG + eigh), rows sharded over ranks" % (args.n, args.d, args.m))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+    import edrgp_b200 as eb
+    from edrgp_b200 import dist as edist, model as emodel, ops
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        tdist.init_process_group('nccl', device_id=dev)
+    n, d, m = args.n, args.d, args.m
+    lo, hi = edist.shard_bounds(n, rank, world)
+    n_local = hi - lo
+
+    # ---- synthetic data of the named shape: X ~ N(0, I) standardised,
+    # y = sum tanh(X B) + 0.05 eps, B (d x 3) orthonormal; Z = m random rows; fixed ARD lengthscales.
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X = torch.randn(n_local, d, dtype=torch.float64, device=dev, generator=g)
+    Bm = torch.as_tensor(np.linalg.qr(np.random.RandomState(0).standard_normal((d, K_TRUE)))[0], device=dev)
+    y = torch.tanh(X @ Bm).sum(1) + 0.05 * torch.randn(n_local, dtype=torch.float64, device=dev, generator=g)
+    Z0 = X[:m].clone() if rank == 0 else torch.zeros(m, d, dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.broadcast(Z0, 0)
+    Z = Z0.cpu().numpy()
+    ell = hyper(d)
+
+    def make_estimator():
+        return eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, SF2, ell, ARD=True), Z=Z, normalizer=True,
+                                                 method='fixed', noise_var=NOISE, chunk_rows=args.chunk_rows)
+
+    def sweep(Xin, yin):
+        """One fixed-hyper-parameter EDR sweep through the public classes."""
+        est = make_estimator().fit(Xin, yin)
+        _, C = est.estimator_.gradient_gram(want_G=False)
+        C = C.clone()
+        edist.allreduce_sum_(C)
+        tr = eb.GramEighTransformer(n_components=K_TRUE).fit_gram(C, n)
+        return tr.components_
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, flush=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        return float(ms[0]), out
+
+    # ---- device-resident arm
+    for _ in range(max(args.warmup, 3)):
+        comps = sweep(X, y)
+
+    # ---- FP64 tensor-pipe peak (denominator of the roofline): live probe on the warm device,
+    # cross-checked against the standalone microbenchmark recorded under profiles/
+    peak_live = ops.fp64_tensor_peak_tflops()
+    peak_recorded = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'fp64_peak_r01.json')) as f:
+            peak_recorded = float(json.load(f)['fp64_dmma_tflops'])
+    except (OSError, ValueError, KeyError):
+        pass
+    peak = max(peak_live, peak_recorded or 0.0)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    ops.start_timing()
+    total_ms, comps = timed(lambda: sweep(X, y), args.steps)
+    per_op = ops.stop_timing()
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    # quality of the directions found (not a timing): principal angle to the true subspace
+    from edrgp_b200.utils import principal_angle
+    Bt = Bm.cpu().numpy().T
+    lead = comps[0] / np.linalg.norm(comps[0])
+    angle_lead = float(np.arcsin(min(1.0, np.linalg.norm(lead - Bt.T.dot(Bt.dot(lead))))))
+    angle = principal_angle(comps, Bt)
+
+    # ---- end-to-end arm: host (pinned) rows in, directions out, every step
+    Xh = torch.empty(n_local, d, dtype=torch.float64, pin_memory=True)
+    yh = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    Xh.copy_(X); yh.copy_(y)
+    torch.cuda.synchronize()
+    Xnp, ynp = Xh.numpy(), yh.numpy()
+    del X, y
+    torch.cuda.empty_cache()
+
+    def sweep_host():
+        return sweep(Xnp, ynp)          # host arrays straight into the public API
+
+    for _ in range(2):
+        sweep_host()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_ms, comps_h = timed(sweep_host, e2e_steps)
+    e2e_value = n / (e2e_ms / e2e_steps * 1e-3)
+    h2d = (n * d + n) * 8
+    d2h = (K_TRUE * d + d + d * d) * 8 + 64
+
+    if rank != 0:
+        if world > 1:
+            tdist.destroy_process_group()
+        return
+
+    fl = flops_per_point(d, m)
+    syrk_ms, syrk_n = per_op.get('inducing_stats', (0.0, 1))
+    pipe_ms, pipe_n = per_op.get('grad_gram', (0.0, 1))
+    kuf_ms, _ = per_op.get('kuf', (0.0, 1))
+    solve_ms, _ = per_op.get('solve', (0.0, 1))
+    eigh_ms, _ = per_op.get('eigh', (0.0, 1))
+    steps = args.steps
+    rows_per_launch_syrk = n_local * steps / max(syrk_n, 1)
+    syrk_avg_ms = syrk_ms / max(syrk_n, 1)
+    syrk_tf = fl['syrk'] * rows_per_launch_syrk / (syrk_avg_ms * 1e-3) / 1e12 if syrk_avg_ms else 0.0
+    syrk_tf_exec = fl['syrk_executed'] * rows_per_launch_syrk / (syrk_avg_ms * 1e-3) / 1e12 if syrk_avg_ms else 0.0
+    pipe_avg_ms = pipe_ms / max(pipe_n, 1)
+    pipe_tf = fl['pipeline'] * n_local / (pipe_avg_ms * 1e-3) / 1e12 if pipe_avg_ms else 0.0
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rows = args.cpu_rows or 524288
+        pts, sec = time_cpu(rows, d, m, 1, 1)
+        cpu = {"value": pts, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": "%d rows of the same generator, one sweep after one warm-up (%.1f s); oracle/pipeline.py "
+                         "chunked NumPy/OpenBLAS on all host threads" % (rows, sec)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "n": n, "d": d, "m": m, "rows_per_rank": n_local,
+                   "hyperparameters": "fixed (lengthscales sqrt(d)(1+u/2), variance 1, noise 0.1)",
+                   "l2": "inputs (%.2f GB X per rank + %.1f GB Kfu blocks) exceed the 126 MB L2; no flush needed"
+                         % (n_local * d * 8 / 1e9, n_local * m * 8 / 1e9),
+                   "chunk_rows": args.chunk_rows, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                "api": "SparseGaussianProcessRegressor(method='fixed').fit(X_host, y_host) -> gradient_gram -> "
+                       "GramEighTransformer.fit_gram -> components_ (host)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (P = Kfu^T Kfu, b, yy; symmetric DMMA reduction)",
+                     "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
+                     "traffic": None,
+                     "achieved_executed": syrk_tf_exec, "frac_executed": syrk_tf_exec / peak if peak else None,
+                     "peak_live": peak_live, "peak_recorded": peak_recorded,
+                     "peak_source": "measured FP64 DMMA (mma.sync m8n8k4 f64) peak of this pool's B200: the larger of "
+                                    "the live probe in this process (edrgp_fp64_probe, CUDA events) and the standalone "
+                                    "microbenchmark recorded in profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has "
+                                    "no FP64 figure",
+                     "note": "achieved counts the ALGORITHMIC 2 m^2 + 2 m flops per row (SURVEY 8d, symmetry not "
+                             "discounted); achieved_executed counts the m (m + 128) + 2 m the kernel issues",
+                     "avg_launch_ms": syrk_avg_ms, "launches": syrk_n, "share_of_step": syrk_ms / total_ms},
+        "roofline_pipeline": {"bound": "tensor", "kernel": "grad_gram_kernel (fused Kuf + gradient + GtG)",
+                              "achieved": pipe_tf, "peak": peak, "unit": "TFLOP/s",
+                              "frac": pipe_tf / peak if peak else None, "avg_launch_ms": pipe_avg_ms,
+                              "launches": pipe_n, "share_of_step": pipe_ms / total_ms,
+                              "algorithmic_flops_per_point": fl['pipeline'], "exps_per_point": m},
+        "stage_ms_per_step": {"kuf": kuf_ms / steps, "inducing_stats": syrk_ms / steps, "solve": solve_ms / steps,
+                              "grad_gram": pipe_ms / steps, "eigh": eigh_ms / steps},
+        "sweep_tflops_algorithmic": (fl['stats'] + fl['pipeline']) * n / (ms_per_step * 1e-3) / 1e12,
+        "quality": {"leading_direction_angle_to_true_subspace_rad": angle_lead,
+                    "largest_principal_angle_k3_rad": angle,
+                    "note": "fixed, un-optimised hyper-parameters; y = sum tanh(x.b_k) is dominated by one "
+                            "direction, so only the leading direction is expected to lie in span(B)"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=N_TOTAL)
+    ap.add_argument('--d', type=int, default=D)
+    ap.add_argument('--m', type=int, default=M)
+    ap.add_argument('--chunk-rows', type=int, default=524288)
+    ap.add_argument('--cpu-rows', type=int, default=0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -19,6 +19,8 @@ SIGNATURES = {
     'edrgp_version': (_int, []),
     'edrgp_last_error': (ctypes.c_char_p, []),
     'edrgp_sm_count': (_int, []),
+    'edrgp_launch_count': (ctypes.c_uint64, []),
+    'edrgp_fp64_probe': (_int, [_c_dp, _int, ctypes.POINTER(ctypes.c_double), _c_dp]),
     'edrgp_pack_bytes': (_sz, [_int, _int]),
     'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
     'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),

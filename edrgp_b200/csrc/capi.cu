@@ -1,9 +1,15 @@
 // extern "C" entry points of libedrgp_b200.so (declared in include/edrgp_b200.h).
+#include <atomic>
 #include <cstdio>
 #include <cstdarg>
 #include "../../include/edrgp_b200.h"
 #include "common.cuh"
 #include "launch.h"
+
+namespace edrgp {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace edrgp
 
 namespace {
 thread_local char g_err[512] = "";
@@ -32,6 +38,15 @@ extern "C" {
 int edrgp_version(void) { return 100; }
 const char* edrgp_last_error(void) { return g_err; }
 int edrgp_sm_count(void) { return sm_count_cached(); }
+uint64_t edrgp_launch_count(void) { return edrgp::g_launches.load(std::memory_order_relaxed); }
+
+int edrgp_fp64_probe(double* scratch, int iters, double* flops, void* stream) {
+  if (!scratch || iters <= 0) return fail(EDRGP_ERR_ARG, "fp64_probe: bad argument");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "fp64_probe: no CUDA device");
+  cudaError_t e = edrgp::launch_dmma_probe(scratch, iters, sms, flops, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "fp64_probe");
+}
 
 size_t edrgp_pack_bytes(int m, int d) {
   if (m <= 0 || d <= 0) return 0;

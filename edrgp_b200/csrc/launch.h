@@ -5,6 +5,9 @@
 
 namespace edrgp {
 
+// every kernel launch of the library is counted (edrgp_launch_count): bench.py reports it
+void count_launch();
+
 cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
                         double* pack, cudaStream_t st);
 bool grad_gram_fused(int d);
@@ -38,5 +41,7 @@ cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* 
                                int sms, cudaStream_t st);
 cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, int k, double* out, int sms,
                            cudaStream_t st);
+
+cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

@@ -62,7 +62,7 @@ static cudaError_t gemm_small(int M, int N, int K, double alpha, const double* A
                               int lower_only, cudaStream_t st) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   dim3 grid((N + NBK - 1) / NBK, (M + NBK - 1) / NBK);
-  gemm_small_kernel<<<grid, 256, 0, st>>>(M, N, K, alpha, A, sai, sak, B, sbk, sbj, beta, C, ldc, lower_only);
+  gemm_small_kernel<<<grid, 256, 0, st>>>(M, N, K, alpha, A, sai, sak, B, sbk, sbj, beta, C, ldc, lower_only); count_launch();
   return cudaGetLastError();
 }
 
@@ -131,10 +131,10 @@ cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t s
   if (e != cudaSuccess) return e;
   for (int k0 = 0; k0 < m; k0 += NBK) {
     const int nb = min(NBK, m - k0);
-    potf2_kernel<<<1, 32, 0, st>>>(A, ld, k0, nb, info);
+    potf2_kernel<<<1, 32, 0, st>>>(A, ld, k0, nb, info); count_launch();
     const int rest = m - k0 - nb;
     if (rest > 0) {
-      potrf_panel_kernel<<<(rest + NBK - 1) / NBK, 32, 0, st>>>(A, ld, k0, nb, m, info);
+      potrf_panel_kernel<<<(rest + NBK - 1) / NBK, 32, 0, st>>>(A, ld, k0, nb, m, info); count_launch();
       // A22 -= L21 L21^T (lower blocks only)
       double* A22 = A + (int64_t)(k0 + nb) * ld + k0 + nb;
       const double* L21 = A + (int64_t)(k0 + nb) * ld + k0;
@@ -194,7 +194,7 @@ cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs
   if (!trans) {
     for (int b = 0; b < nblk; ++b) {
       const int k0 = b * NBK, nb = min(NBK, m - k0);
-      trsm_diag_kernel<<<(nrhs + 31) / 32, 32, 0, st>>>(L, ldl, k0, nb, B, ldb, nrhs, 0);
+      trsm_diag_kernel<<<(nrhs + 31) / 32, 32, 0, st>>>(L, ldl, k0, nb, B, ldb, nrhs, 0); count_launch();
       const int rest = m - k0 - nb;
       if (rest > 0) {   // B[rest] -= L[rest, blk] X_blk
         e = gemm_small(rest, nrhs, nb, -1.0, L + (int64_t)(k0 + nb) * ldl + k0, ldl, 1, B + (int64_t)k0 * ldb, ldb, 1,
@@ -205,7 +205,7 @@ cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs
   } else {
     for (int b = nblk - 1; b >= 0; --b) {
       const int k0 = b * NBK, nb = min(NBK, m - k0);
-      trsm_diag_kernel<<<(nrhs + 31) / 32, 32, 0, st>>>(L, ldl, k0, nb, B, ldb, nrhs, 1);
+      trsm_diag_kernel<<<(nrhs + 31) / 32, 32, 0, st>>>(L, ldl, k0, nb, B, ldb, nrhs, 1); count_launch();
       if (k0 > 0) {     // B[0:k0] -= L[blk, 0:k0]^T X_blk
         e = gemm_small(k0, nrhs, nb, -1.0, L + (int64_t)k0 * ldl, 1, ldl, B + (int64_t)k0 * ldb, ldb, 1, 1.0, B, ldb, 0,
                        st);
@@ -290,16 +290,16 @@ cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, d
   if ((e = cudaMemcpyAsync(T1, P, (size_t)m * m * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
   if ((e = launch_trsm(Kmm, m, m, T1, m, m, 0, st)) != cudaSuccess) return e;
   dim3 tg((m + 31) / 32, (m + 31) / 32), tb(32, 8);
-  transpose_kernel<<<tg, tb, 0, st>>>(T1, m, T2);
+  transpose_kernel<<<tg, tb, 0, st>>>(T1, m, T2); count_launch();
   if ((e = launch_trsm(Kmm, m, m, T2, m, m, 0, st)) != cudaSuccess) return e;
-  make_B_kernel<<<nb2, 256, 0, st>>>(T2, m, beta, Bmat);
+  make_B_kernel<<<nb2, 256, 0, st>>>(T2, m, beta, Bmat); count_launch();
   // keep I + A for the trace before factorising in place: T1 <- B
   if ((e = cudaMemcpyAsync(T1, Bmat, (size_t)m * m * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
   if ((e = launch_potrf(Bmat, m, m, info + 1, st)) != cudaSuccess) return e;
-  scale_copy_kernel<<<(m + 255) / 256, 256, 0, st>>>(b, beta, m, cvec);
+  scale_copy_kernel<<<(m + 255) / 256, 256, 0, st>>>(b, beta, m, cvec); count_launch();
   if ((e = launch_trsm(Kmm, m, m, cvec, 1, 1, 0, st)) != cudaSuccess) return e;
   if ((e = launch_trsm(Bmat, m, m, cvec, 1, 1, 0, st)) != cudaSuccess) return e;
-  solve_scalars_kernel<<<1, 256, 0, st>>>(T1, Bmat, cvec, m, scalars);
+  solve_scalars_kernel<<<1, 256, 0, st>>>(T1, Bmat, cvec, m, scalars); count_launch();
   if ((e = cudaMemcpyAsync(alpha, cvec, (size_t)m * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
   if ((e = launch_trsm(Bmat, m, m, alpha, 1, 1, 1, st)) != cudaSuccess) return e;
   if ((e = launch_trsm(Kmm, m, m, alpha, 1, 1, 1, st)) != cudaSuccess) return e;
@@ -307,7 +307,7 @@ cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, d
 }
 
 cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitter, cudaStream_t st) {
-  kmm_fix_kernel<<<(unsigned)(((int64_t)m * m + 255) / 256), 256, 0, st>>>(K, m, ld, sf2, jitter);
+  kmm_fix_kernel<<<(unsigned)(((int64_t)m * m + 255) / 256), 256, 0, st>>>(K, m, ld, sf2, jitter); count_launch();
   return cudaGetLastError();
 }
 
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* __restrict__ 
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
   const int dd = d + (d & 1), np = dd / 2;
   const size_t smem = (size_t)np * (2 * sizeof(double) + 2 * sizeof(int));
-  jacobi_eigh_kernel<<<1, 1024, smem, st>>>(A, d, V, evals, comps, 60, sweeps);
+  jacobi_eigh_kernel<<<1, 1024, smem, st>>>(A, d, V, evals, comps, 60, sweeps); count_launch();
   return cudaGetLastError();
 }
 

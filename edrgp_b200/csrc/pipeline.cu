@@ -471,7 +471,7 @@ static cudaError_t launch_grad_gram_t(const PipeParams& p, int grid, cudaStream_
   auto kern = grad_gram_kernel<DP, FUSE, XS, NS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
-  kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p);
+  kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p); count_launch();
   return cudaGetLastError();
 }
 
@@ -481,7 +481,7 @@ static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) 
   auto kern = kuf_kernel<DP, XS, NS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
-  kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p);
+  kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p); count_launch();
   return cudaGetLastError();
 }
 
@@ -491,7 +491,7 @@ cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, 
   const int mtiles = (m + MT - 1) / MT;
   const int warps_needed = mtiles * MT;
   const int blocks = (warps_needed * 32 + 255) / 256;
-  pack_inducing_kernel<<<blocks, 256, 0, st>>>(Z, ell, coef, coef_scale, m, d, dp, pack);
+  pack_inducing_kernel<<<blocks, 256, 0, st>>>(Z, ell, coef, coef_scale, m, d, dp, pack); count_launch();
   return cudaGetLastError();
 }
 
@@ -518,7 +518,7 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
   }
   if (e != cudaSuccess) return e;
   if (C != nullptr && dp <= 64) {
-    reduce_gram_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(Cpart, grid, dp, d, C);
+    reduce_gram_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(Cpart, grid, dp, d, C); count_launch();
     e = cudaGetLastError();
   }
   return e;

@@ -127,10 +127,10 @@ cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* 
   const int rows_per_pass = CM_THREADS / lanes;
   const int64_t need = (n + rows_per_pass - 1) / rows_per_pass;
   if (grid > need) grid = (int)need;
-  col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, weight, workspace);
+  col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, weight, workspace); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  col_moments_reduce_kernel<<<(2 * d + 127) / 128, 128, 0, st>>>(workspace, grid, d, out, accumulate);
+  col_moments_reduce_kernel<<<(2 * d + 127) / 128, 128, 0, st>>>(workspace, grid, d, out, accumulate); count_launch();
   return cudaGetLastError();
 }
 
@@ -139,7 +139,7 @@ cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* 
   const int64_t total = n * d;
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-  standardize_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, total, d, mean, scale, out);
+  standardize_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, total, d, mean, scale, out); count_launch();
   return cudaGetLastError();
 }
 
@@ -154,10 +154,12 @@ cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, i
       cudaError_t e = cudaFuncSetAttribute(project_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    if (kc <= 4)
+    if (kc <= 4) {
       project_kernel<4><<<(unsigned)blocks, 256, smem, st>>>(X, n, d, V + (int64_t)c0 * d, kc, d, out + c0, k);
-    else
+    } else {
       project_kernel<16><<<(unsigned)blocks, 256, smem, st>>>(X, n, d, V + (int64_t)c0 * d, kc, d, out + c0, k);
+    }
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -214,13 +214,13 @@ cudaError_t launch_gemm_tn(const double* A, int64_t lda, int ka, const double* B
   const size_t smem = (size_t)SST * STAGE_DOUBLES * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gemm_tn_kernel<<<p.ntiles * p.ksplit, 256, smem, st>>>(p);
+  gemm_tn_kernel<<<p.ntiles * p.ksplit, 256, smem, st>>>(p); count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int64_t total = (int64_t)p.ka * p.kb + (p.y ? p.ka + 1 : 0);
   gemm_tn_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, p.ksplit, p.ka, p.kb, sym,
                                                                          accumulate, C, ldc, p.bpart,
-                                                                         p.y ? bout : nullptr);
+                                                                         p.y ? bout : nullptr); count_launch();
   return cudaGetLastError();
 }
 

@@ -214,13 +214,13 @@ cudaError_t launch_weights(const double* K, int64_t n, int m, int64_t ldk, const
   cudaError_t e = cudaFuncSetAttribute(weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (nrb * p.ntj > 0x7fffffffLL) return cudaErrorInvalidValue;
-  weights_kernel<<<(unsigned)(nrb * p.ntj), 256, smem, st>>>(p);
+  weights_kernel<<<(unsigned)(nrb * p.ntj), 256, smem, st>>>(p); count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (rowsum || colsum) {
     const int64_t total = n + m;
     weights_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.rs_part, p.ntj, n, rowsum, p.cs_part, nrb, m,
-                                                                         colsum, accumulate);
+                                                                         colsum, accumulate); count_launch();
     e = cudaGetLastError();
   }
   return e;

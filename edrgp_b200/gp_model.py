@@ -123,11 +123,14 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
     Parameters are the reference's; ``method`` additionally accepts ``'fixed'`` (keep the initial
     or injected hyper-parameters: what the parity harness and the benchmark use), and
-    ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time.
+    ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time, and
+    ``noise_var`` sets the initial Gaussian noise variance (GPy's default 1.0; the dense
+    ``GaussianProcessRegressor`` of the reference has the same parameter).
     """
 
     def __init__(self, kernels=None, kernel_options=None, Z=None, num_inducing=10, Y_metadata=None,
-                 X_variance=None, normalizer=True, mean_function=None, method='optimize', chunk_rows=262144):
+                 X_variance=None, normalizer=True, mean_function=None, method='optimize', chunk_rows=262144,
+                 noise_var=1.0):
         self.kernels = kernels
         self.kernel_options = kernel_options
         self.Z = Z
@@ -138,20 +141,48 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         self.mean_function = mean_function
         self.method = method
         self.chunk_rows = chunk_rows
+        self.noise_var = noise_var
 
     def _get_model(self, X, y, kernel):
         return _model.SparseGPRegression(X, y, kernel=kernel, Z=self.Z, num_inducing=self.num_inducing,
                                          X_variance=self.X_variance, mean_function=self.mean_function,
-                                         normalizer=self.normalizer, chunk_rows=self.chunk_rows)
+                                         normalizer=self.normalizer, chunk_rows=self.chunk_rows,
+                                         noise_var=self.noise_var)
 
     def _check_data(self, X, y):
-        # device-resident rows (torch CUDA tensors) skip the host validators: this rank's shard
+        """Validation of ``check_X_y`` (edrgp/gp_model/base.py:72-91) split so that the O(n d) part
+        runs where the data is going anyway: shapes and dtypes on the host, the non-finite scan on
+        the device after the copy.  CUDA tensors (this rank's shard) are taken as they are."""
         import torch
         if isinstance(X, torch.Tensor):
             if X.dim() != 2 or y.shape[0] != X.shape[0]:
                 raise ValueError("X must be (n, d) and y (n,)")
-            return X, y.reshape(-1, 1)
-        return _BaseGP._check_data(self, X, y)
+            Xd = X.to(device='cuda', dtype=torch.float64)
+            yd = y.to(device='cuda', dtype=torch.float64).reshape(-1, 1)
+        else:
+            X = np.asarray(X)
+            y = np.asarray(y)
+            if X.ndim != 2:
+                raise ValueError("Expected 2D array, got %dD array instead" % X.ndim)
+            if y.ndim == 2 and y.shape[1] == 1:
+                y = y[:, 0]
+            if y.ndim != 1:
+                raise ValueError("y should be a 1d array, got an array of shape {} instead.".format(y.shape))
+            if X.shape[0] != y.shape[0]:
+                raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]"
+                                 % (X.shape[0], y.shape[0]))
+            if X.shape[0] < 1 or X.shape[1] < 1:
+                raise ValueError("Found array with %d sample(s) and %d feature(s) while a minimum of 1 is required."
+                                 % X.shape)
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            Xd = torch.from_numpy(X).to('cuda', non_blocking=True)
+            yd = torch.from_numpy(y).to('cuda', non_blocking=True).reshape(-1, 1)
+        if not bool(torch.isfinite(Xd).all()):
+            raise ValueError("Input X contains NaN or infinity.")
+        if not bool(torch.isfinite(yd).all()):
+            raise ValueError("Input y contains NaN or infinity.")
+        return Xd, yd
 
     def _check_input(self, X):
         import torch

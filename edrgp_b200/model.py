@@ -99,7 +99,7 @@ class Standardize(object):
 def _as_device(a, device):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=F64).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device, non_blocking=True)
 
 
 def _backsub_both_sides(L, X, transpose='left'):
@@ -120,7 +120,7 @@ class SparseGPRegression(object):
     """
 
     def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, X_variance=None, mean_function=None,
-                 normalizer=None, device=None, chunk_rows=262144, cache_bytes=None):
+                 normalizer=None, device=None, chunk_rows=262144, cache_bytes=None, noise_var=1.0):
         if X_variance is not None or mean_function is not None:
             raise NotImplementedError("uncertain inputs / mean functions are outside the B200 path")
         if not torch.cuda.is_available():
@@ -147,7 +147,7 @@ class SparseGPRegression(object):
                 raise ValueError("Z must have shape (num_inducing, n_features)")
         self.Z = Zh
         self.num_inducing = Zh.shape[0]
-        self.noise_variance = 1.0                                  # GPy likelihoods.Gaussian() default
+        self.noise_variance = float(noise_var)                     # GPy likelihoods.Gaussian() default: 1.0
 
         if normalizer is True:
             self.normalizer = Standardize()

@@ -17,6 +17,41 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# optional per-op CUDA-event timing (bench.py's roofline): name -> [(start, end), ...]
+_TIMING = None
+
+
+class _Timed(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _TIMING.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
+def start_timing():
+    """Begin collecting CUDA-event pairs around the contraction ops on the current stream."""
+    global _TIMING
+    _TIMING = {}
+
+
+def stop_timing():
+    """Stop collecting; returns {op name: (total ms, launches)} (synchronises)."""
+    global _TIMING
+    t, _TIMING = _TIMING, None
+    torch.cuda.synchronize()
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (t or {}).items()}
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is None:
@@ -69,8 +104,9 @@ def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
         K = out if out is not None else torch.empty(n, ldk, dtype=F64, device=X.device)
     b = torch.zeros(pack.m, dtype=F64, device=X.device) if y is not None else None
     mu = torch.empty(n, dtype=F64, device=X.device) if want_mu else None
-    _lib.check(lib.edrgp_kuf(_ptr(X), n, X.shape[1], _ptr(pack.buf), pack.m, float(sf2), _ptr(K), ldk,
-                             _ptr(y), _ptr(b), _ptr(mu), _stream()), 'edrgp_kuf')
+    with _Timed('kuf'):
+        _lib.check(lib.edrgp_kuf(_ptr(X), n, X.shape[1], _ptr(pack.buf), pack.m, float(sf2), _ptr(K), ldk,
+                                 _ptr(y), _ptr(b), _ptr(mu), _stream()), 'edrgp_kuf')
     if K is not None and ldk != pack.m:
         K = K[:, :pack.m]
     if want_mu:
@@ -92,8 +128,9 @@ def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
     if want_C:
         C = torch.empty(d, d, dtype=F64, device=X.device)
         ws = torch.empty(lib.edrgp_grad_gram_workspace_bytes(d) // 8, dtype=F64, device=X.device)
-    _lib.check(lib.edrgp_grad_gram(_ptr(X), n, d, _ptr(pack.buf), pack.m, _ptr(G), _ptr(C), _ptr(ws),
-                                   _stream()), 'edrgp_grad_gram')
+    with _Timed('grad_gram'):
+        _lib.check(lib.edrgp_grad_gram(_ptr(X), n, d, _ptr(pack.buf), pack.m, _ptr(G), _ptr(C), _ptr(ws),
+                                       _stream()), 'edrgp_grad_gram')
     if d != d_user:
         if G is not None:
             G = G[:, :d_user].contiguous()
@@ -132,9 +169,10 @@ def inducing_stats(K, y, m=None, P=None, b_yy=None, accumulate=False):
     if b_yy is None:
         b_yy = torch.empty(m + 1, dtype=F64, device=K.device)
     ws = torch.empty(max(1, lib.edrgp_syrk_workspace_bytes(n, m) // 8), dtype=F64, device=K.device)
-    _lib.check(lib.edrgp_inducing_stats(_ptr(K), n, m, ldk, _ptr(y), _ptr(P), m, _ptr(b_yy),
-                                        int(bool(accumulate and not fresh)), _ptr(ws), _stream()),
-               'edrgp_inducing_stats')
+    with _Timed('inducing_stats'):
+        _lib.check(lib.edrgp_inducing_stats(_ptr(K), n, m, ldk, _ptr(y), _ptr(P), m, _ptr(b_yy),
+                                            int(bool(accumulate and not fresh)), _ptr(ws), _stream()),
+                   'edrgp_inducing_stats')
     return P, b_yy
 
 
@@ -185,8 +223,9 @@ def solve(Kmm, P, b, beta):
     out.info = torch.zeros(2, dtype=torch.int32, device=dev)
     ws = torch.empty(lib.edrgp_solve_workspace_bytes(m) // 8, dtype=F64, device=dev)
     out.B = ws[:m * m].view(m, m)            # I + A = I + beta Lm^-1 P Lm^-T, kept by the chain
-    _lib.check(lib.edrgp_solve(_ptr(Kmm), _ptr(P), _ptr(b), m, float(beta), _ptr(out.LB), _ptr(out.alpha),
-                               _ptr(out.c), _ptr(out.scalars), _ptr(out.info), _ptr(ws), _stream()), 'edrgp_solve')
+    with _Timed('solve'):
+        _lib.check(lib.edrgp_solve(_ptr(Kmm), _ptr(P), _ptr(b), m, float(beta), _ptr(out.LB), _ptr(out.alpha),
+                                   _ptr(out.c), _ptr(out.scalars), _ptr(out.info), _ptr(ws), _stream()), 'edrgp_solve')
     return out
 
 
@@ -210,7 +249,8 @@ def eigh(C):
     evals = torch.empty(d, dtype=F64, device=C.device)
     comps = torch.empty(d, d, dtype=F64, device=C.device)
     ws = torch.empty(d * d, dtype=F64, device=C.device)
-    _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
+    with _Timed('eigh'):
+        _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
     return evals, comps
 
 
@@ -277,3 +317,27 @@ def project(X, V):
     out = torch.empty(n, k, dtype=F64, device=X.device)
     _lib.check(lib.edrgp_project(_ptr(X), n, d, _ptr(V), k, _ptr(out), _stream()), 'edrgp_project')
     return out
+
+
+def launch_count():
+    """Number of CUDA kernels the library has launched in this process."""
+    return int(_lib.load().edrgp_launch_count())
+
+
+def fp64_tensor_peak_tflops(iters=20000, reps=6):
+    """Measured FP64 DMMA throughput (TFLOP/s) of the current device: CUDA-event timing of the
+    register-only probe kernel, best of ``reps`` after one warm-up."""
+    import ctypes
+    lib = _lib.load()
+    scratch = torch.zeros(256, dtype=F64, device='cuda')
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for r in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.edrgp_fp64_probe(_ptr(scratch), int(iters), ctypes.byref(flops), _stream()), 'edrgp_fp64_probe')
+        e1.record()
+        e1.synchronize()
+        if r:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

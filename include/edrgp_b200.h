@@ -38,6 +38,13 @@ int edrgp_version(void);
 const char* edrgp_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int edrgp_sm_count(void);
+/* number of CUDA kernels this library has launched in this process so far */
+uint64_t edrgp_launch_count(void);
+
+/* FP64 tensor-pipe (DMMA) peak probe: enqueues a register-only mma.sync f64 kernel; scratch is a
+ * device buffer of >= 256 doubles; *flops (host) receives the FP64 flops the launch executes.  The
+ * caller times it with CUDA events: the live roofline denominator of bench.py. */
+int edrgp_fp64_probe(double* scratch, int iters, double* flops, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Inducing-point pack.  Replaces the per-call `Z / lengthscale` and `sum(square(Z / l), 1)` of

@@ -1,0 +1,72 @@
+"""The C-ABI library loads and exports every symbol include/edrgp_b200.h declares, and the ctypes
+table mirrors the header one to one.  No compute calls: runs without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'edrgp_b200.h')
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(edrgp_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_the_path():
+    names = _declared()
+    for must in ('edrgp_kuf', 'edrgp_grad_gram', 'edrgp_inducing_stats', 'edrgp_solve', 'edrgp_eigh',
+                 'edrgp_weights', 'edrgp_gemm_tn', 'edrgp_project', 'edrgp_col_moments'):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from edrgp_b200 import build, _lib
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    for name in _declared():
+        assert hasattr(lib, name), name
+
+
+def test_ctypes_table_mirrors_header():
+    from edrgp_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r'\b%s\s*\(([^;]*)\)\s*;' % name, src)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else len(params.split(','))
+        assert n == len(args), (name, n, len(args))
+
+
+def test_version_and_error_calls_work_without_gpu():
+    from edrgp_b200 import _lib
+    lib = _lib.load()
+    assert lib.edrgp_version() >= 100
+    assert lib.edrgp_pack_bytes(512, 64) == (64 + 16 * 32 * (64 + 2 + 2)) * 8
+    # argument errors are reported before any CUDA call
+    rc = lib.edrgp_kuf(0, 10, 4, 0, 3, 1.0, 0, 4, 0, 0, 0, 0)
+    assert rc == -1
+    assert b'kuf' in lib.edrgp_last_error()
+
+
+def test_product_path_fails_loudly_without_cuda():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import numpy as np
+    import edrgp_b200 as eb
+    with pytest.raises(Exception):
+        eb.SparseGaussianProcessRegressor(method='fixed').fit(np.zeros((10, 2)), np.zeros(10))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'edrgp_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn

@@ -1,0 +1,90 @@
+"""Multi-rank host logic on CPU: two gloo processes (127.0.0.1).  Checks the packed all-reduce and
+broadcast helpers, the contiguous row sharding, and the shard-sum algebra of the path (SURVEY.md
+section 4(iv), 8(e)): statistics {P, b, yy} and the Gram matrix C reduced over row shards equal the
+single-process result, and every rank derives the same alpha and EDR directions from them.  The
+per-shard arithmetic here is the oracle's (no GPU in this container); the CUDA path performs the
+same two reductions through the same helpers (edrgp_b200/dist.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.multiprocessing as mp      # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as tdist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    tdist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from edrgp_b200 import dist
+        from oracle import pipeline as op
+        assert dist.is_distributed() and dist.world_size() == world and dist.rank() == rank
+        # packed all-reduce of tensors of different shapes
+        a = torch.full((3, 2), float(rank + 1), dtype=torch.float64)
+        b = torch.arange(5, dtype=torch.float64) * (rank + 1)
+        dist.allreduce_sum_(a, b)
+        assert torch.equal(a, torch.full((3, 2), 3.0, dtype=torch.float64))
+        assert torch.equal(b, torch.arange(5, dtype=torch.float64) * 3)
+        z = torch.full((4,), float(rank), dtype=torch.float64)
+        dist.broadcast_(z, 0)
+        assert torch.equal(z, torch.zeros(4, dtype=torch.float64))
+
+        n, d, m = 3001, 6, 25
+        w = op.make_workload(n, d, m, seed=2, k_true=2)
+        lo, hi = dist.shard_bounds(n)
+        Xs, ys = w['X'][lo:hi], w['y'][lo:hi]
+        P, bb, yy = op.inducing_stats_chunked(Xs, ys, w['Z'], w['ell'], w['sf2'], chunk=512)
+        Pt, bt, yt = torch.from_numpy(P), torch.from_numpy(bb), torch.tensor([yy], dtype=torch.float64)
+        dist.allreduce_sum_(Pt, bt, yt)
+        sol = op.solve_from_stats(op.kuu(w['Z'], w['ell'], w['sf2']), Pt.numpy(), bt.numpy(), float(yt[0]), n,
+                                  w['sf2'], w['noise'])
+        C = torch.from_numpy(op.grad_gram_chunked(Xs, w['Z'], w['ell'], w['sf2'], sol['alpha'], chunk=512))
+        dist.allreduce_sum_(C)
+        comps, lam, _ = op.edr_from_gram(C.numpy(), 2)
+        out[rank] = {'lo': lo, 'hi': hi, 'alpha': sol['alpha'], 'bound': sol['bound'], 'C': C.numpy(), 'comps': comps}
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_two_rank_shard_sum_equals_single_process():
+    from oracle import pipeline as op
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    n, d, m = 3001, 6, 25
+    assert (r0['lo'], r0['hi'], r1['lo'], r1['hi']) == (0, 1501, 1501, 3001)
+    # every rank ends with the same reduced quantities
+    assert np.array_equal(r0['C'], r1['C']) and np.array_equal(r0['alpha'], r1['alpha'])
+    w = op.make_workload(n, d, m, seed=2, k_true=2)
+    P, b, yy = op.inducing_stats_chunked(w['X'], w['y'], w['Z'], w['ell'], w['sf2'])
+    sol = op.solve_from_stats(op.kuu(w['Z'], w['ell'], w['sf2']), P, b, yy, n, w['sf2'], w['noise'])
+    C = op.grad_gram_chunked(w['X'], w['Z'], w['ell'], w['sf2'], sol['alpha'])
+    assert abs(r0['bound'] - sol['bound']) < 1e-10 * abs(sol['bound'])
+    assert np.max(np.abs(r0['C'] - C)) < 1e-9 * np.max(np.abs(C))
+    comps, _, _ = op.edr_from_gram(C, 2)
+    assert op.principal_angle(r0['comps'], comps) < 1e-6
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from edrgp_b200 import dist
+    for n in (0, 1, 7, 4_000_000, 4_000_001):
+        for w in (1, 2, 4, 8):
+            b = [dist.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1

@@ -167,3 +167,30 @@ def test_reference_scaling(reference_edrgp):
     edr = EffectiveDimensionalityReduction(est, SVDTransformer(), normalize=False)
     x2 = edr.fit_transform(StandardScaler().fit_transform(X), y, max_iters=50)
     assert np.allclose(x1, x2)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kw", [dict(n_components=2, step=None, normalize=True),
+                                dict(n_components=1, step=2, normalize=True),
+                                dict(n_components=None, step=0.97, normalize=False)])
+def test_reference_loop_matches_unmodified_reference(reference_edrgp, kw):
+    """oracle/reference_loop.py (what the GPU box uses as the orchestration oracle) against the
+    UNMODIFIED reference classes driven with the same oracle estimator: bit-identical."""
+    from edrgp.edr import EffectiveDimensionalityReduction
+    from edrgp.utils import SVDTransformer
+    from oracle import reference_loop as rl
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((300, 6)) * np.linspace(2, .5, 6) + 1.0
+    B = np.linalg.qr(rng.standard_normal((6, 2)))[0]
+    y = np.tanh(X.dot(B)).sum(1)
+    np.random.seed(3)
+    ref = EffectiveDimensionalityReduction(SparseGaussianProcessRegressor('RBF', {'ARD': True}, num_inducing=15),
+                                           SVDTransformer(), **kw)
+    ref.fit(X, y, max_iters=5)
+    np.random.seed(3)
+    out = rl.fit_reference_style(X, y, num_inducing=15, max_iters=5, **kw)
+    assert ref.num_iter == out['num_iter']
+    assert np.array_equal(ref.components_, out['components_'])
+    assert np.array_equal(ref.subspace_variance_ratio_, out['subspace_variance_ratio_'])
+    assert np.array_equal(ref.subspace_gradients_, out['subspace_gradients_'])
+    assert np.array_equal(ref._first_gradients_, out['_first_gradients_'])
