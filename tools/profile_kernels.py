@@ -1,0 +1,23 @@
+"""Runs the three n-scale kernels of the sweep once each after a warm-up, at one 512k-row block of the
+headline shape (d=64, m=512), for ncu captures:  kuf_kernel, gemm_tn_kernel, grad_gram_kernel."""
+import sys
+import torch
+sys.path.insert(0, '.')
+from edrgp_b200 import ops
+
+n, d, m = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (524288, 64, 512)))
+g = torch.Generator(device='cuda').manual_seed(0)
+X = torch.randn(n, d, dtype=torch.float64, device='cuda', generator=g)
+y = torch.randn(n, dtype=torch.float64, device='cuda', generator=g)
+Z = X[:m].contiguous()
+ell = (d ** 0.5) * (1 + 0.5 * torch.rand(d, dtype=torch.float64, device='cuda', generator=g))
+alpha = torch.randn(m, dtype=torch.float64, device='cuda', generator=g)
+pack = ops.InducingPack(Z, ell)
+gpack = ops.InducingPack(Z, ell, alpha, 1.0)
+K = torch.empty(n, m, dtype=torch.float64, device='cuda')
+for it in range(2):
+    ops.kuf(X, pack, 1.0, out=K)
+    P, byy = ops.inducing_stats(K, y, m)
+    G, C = ops.grad_gram(X, gpack, want_G=False)
+torch.cuda.synchronize()
+print("ok", float(P[0, 0]), float(C[0, 0]))
