@@ -6,25 +6,22 @@
 // hyper-parameter gradient of the VFE bound.  Output tiles are 128 x 128; the n rows are split over
 // CTAs (split-K) so that tiles x splits fills the chip, each CTA writing its partial tile to a
 // workspace that a second kernel sums in a fixed order (deterministic, no atomics).  Row chunks of
-// 16 are staged through a 4-deep cp.async ring; the shared-memory row stride 132 == 4 (mod 16)
-// makes both DMMA fragment loads bank-conflict free.
+// 32 are staged through a 3-deep ring by a TMA producer warp (cp.async.bulk, one row slice per
+// lane) with mbarrier full/empty hand-off; the shared-memory row stride 132 == 4 (mod 16) makes both
+// DMMA fragment loads bank-conflict free.
 #include "common.cuh"
 #include "launch.h"
 
 namespace edrgp {
 
 constexpr int TB = 128;        // output tile edge
-constexpr int KC = 16;         // rows per pipeline stage
-constexpr int SST = 4;         // stages
+constexpr int KC = 32;         // rows per pipeline stage (one producer lane per row)
+constexpr int SST = 3;         // stages
 constexpr int SS = TB + 4;     // smem row stride (doubles)
 constexpr int STAGE_DOUBLES = 2 * KC * SS + KC;   // A rows, B rows, y slice
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int GT_WARPS = 8;    // compute warps; warp 8 is the TMA producer
+constexpr size_t GT_BAR_OFF = (size_t)SST * STAGE_DOUBLES * sizeof(double);
+constexpr size_t GT_SMEM = GT_BAR_OFF + 2 * SST * sizeof(uint64_t);
 
 struct GemmTnParams {
   const double* A;
@@ -42,11 +39,17 @@ struct GemmTnParams {
   double* bpart;   // [ksplit][ka + 1]
 };
 
-__global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTnParams p) {
+// Operand staging is done by a dedicated producer warp with TMA bulk copies (one 1 KB row slice
+// per lane and operand, SASS UBLKCP) completing on an mbarrier full/empty ring: the 8 compute warps
+// issue nothing but LDS + DMMA in the main loop.  (With cp.async issued by the compute warps the
+// address arithmetic of all warps lines up behind each barrier and idles the DMMA pipe ~20 % of the
+// time: tools/dmma_limits.cu, profiles/r01_ncu_top_kernels.txt.)
+__global__ void __launch_bounds__((GT_WARPS + 1) * 32, 1) gemm_tn_kernel(const GemmTnParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);   // [SST][STAGE_DOUBLES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + GT_BAR_OFF);
+  uint64_t* empty = full + SST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   int tile = blockIdx.x % p.ntiles, split = blockIdx.x / p.ntiles;
   int ti, tj;
   if (p.sym) {
@@ -64,52 +67,67 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTnParams p) {
   const int64_t r_end = min(p.n, r_begin + p.rows_per_split);
   const int nchunks = r_end > r_begin ? (int)((r_end - r_begin + KC - 1) / KC) : 0;
 
+  if (tid == 0) {
+    for (int i = 0; i < SST; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], GT_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == GT_WARPS) {
+    // ------------------------------ producer ------------------------------
+    // 16-byte granules: an odd column count is rounded up (the leading dimensions are even, so the
+    // extra column is in bounds; it only feeds output rows / columns that are never written)
+    const int acols = min(TB, p.ka - ti * TB), bcols = min(TB, p.kb - tj * TB);
+    const uint32_t abytes = (uint32_t)((acols + 1) & ~1) * 8u, bbytes = diag ? 0u : (uint32_t)((bcols + 1) & ~1) * 8u;
+    double yy = 0.0;
+    int stage = 0, ph = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int64_t row_base = r_begin + (int64_t)c * KC;
+      const int valid = (int)min((int64_t)KC, r_end - row_base);
+      double* base = sm + (size_t)stage * STAGE_DOUBLES;
+      mbar_wait(&empty[stage], ph ^ 1);
+      const int64_t row = row_base + lane;
+      const bool ok = lane < valid;
+      if (with_y) {
+        const double yv = ok ? p.y[row] : 0.0;
+        base[2 * KC * SS + lane] = yv;
+        if (ti == 0) yy = fma(yv, yv, yy);
+      }
+      if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)valid * (abytes + bbytes));
+      __syncwarp();
+      if (ok) {
+        bulk_g2s(base + lane * SS, p.A + row * p.lda + (int64_t)ti * TB, abytes, &full[stage]);
+        if (!diag) bulk_g2s(base + KC * SS + lane * SS, p.B + row * p.ldb + (int64_t)tj * TB, bbytes, &full[stage]);
+      } else {
+        // ragged last chunk: rows past the end must read as zeros
+        for (int q = 0; q < TB; ++q) { base[lane * SS + q] = 0.0; if (!diag) base[KC * SS + lane * SS + q] = 0.0; }
+      }
+      if (lane != 0) mbar_arrive(&full[stage]);
+      if (++stage == SST) { stage = 0; ph ^= 1; }
+    }
+    if (with_y && ti == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+      if (lane == 0) p.bpart[(size_t)split * (p.ka + 1) + p.ka] = yy;
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  const int g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;          // warp tile: rows 32*wm.., cols 64*wn..
   double acc[4][8][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  double bacc = 0.0;      // tid < 128: column ti*TB + tid of A^T y;  tid == 128: y^T y
+  double bacc = 0.0;      // column ti*TB + (tid & 127) of A^T y over the rows tid >> 7 of each half stage
 
-  // loader: each stage = 2 operands x KC rows x 128 doubles = 2 x 16 x 64 16-byte pieces (+ 8 for y)
-  auto load_stage = [&](int chunk, int stage) {
-    const int64_t row_base = r_begin + (int64_t)chunk * KC;
-    double* base = sm + (size_t)stage * STAGE_DOUBLES;
-#pragma unroll
-    for (int it = 0; it < (2 * KC * (TB / 2)) / 256; ++it) {
-      const int idx = tid + it * 256;
-      const int op = idx / (KC * (TB / 2));
-      if (op == 1 && diag) continue;
-      const int rr = (idx / (TB / 2)) % KC;
-      const int c2 = idx % (TB / 2);
-      const int col = (op == 0 ? ti : tj) * TB + 2 * c2;
-      const int kk = op == 0 ? p.ka : p.kb;
-      const int64_t row = row_base + rr;
-      // ka, kb and the leading dimensions are even: a 16-byte piece never straddles the edge
-      const bool ok = row < r_end && col < kk;
-      const double* mat = op == 0 ? p.A : p.B;
-      const double* src = ok ? mat + row * (op == 0 ? p.lda : p.ldb) + col : mat;
-      cp_async16(base + (size_t)op * KC * SS + rr * SS + 2 * c2, src, ok ? 16 : 0);
-    }
-    if (with_y && tid < KC / 2) {
-      const int64_t row = row_base + 2 * tid;
-      const int bytes = row + 1 < r_end ? 16 : (row < r_end ? 8 : 0);
-      cp_async16(base + 2 * KC * SS + 2 * tid, bytes ? p.y + row : p.y, bytes);
-    }
-  };
-
-  for (int s = 0; s < SST - 1; ++s) {
-    if (s < nchunks) load_stage(s, s);
-    cp_async_commit();
-  }
+  int stage = 0, ph = 0;
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<SST - 2>();
-    __syncthreads();
-    if (c + SST - 1 < nchunks) load_stage(c + SST - 1, (c + SST - 1) % SST);
-    cp_async_commit();
-    const double* As = sm + (size_t)(c % SST) * STAGE_DOUBLES;
+    const double* As = sm + (size_t)stage * STAGE_DOUBLES;
     const double* Bs = diag ? As : As + KC * SS;
+    mbar_wait(&full[stage], ph);
 #pragma unroll
     for (int ks = 0; ks < KC / 4; ++ks) {
       const double* ar = As + (4 * ks + t) * SS + 32 * wm + g;
@@ -125,17 +143,15 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTnParams p) {
         for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     if (with_y) {
-      const double* ys = As + 2 * KC * SS;
-      if (tid < TB) {
+      const double* ys = As + 2 * KC * SS + (tid >> 7) * (KC / 2);
+      const double* ac = As + (tid >> 7) * (KC / 2) * SS + (tid & (TB - 1));
 #pragma unroll
-        for (int r = 0; r < KC; ++r) bacc = fma(As[r * SS + tid], ys[r], bacc);
-      } else if (tid == TB && ti == 0) {
-#pragma unroll
-        for (int r = 0; r < KC; ++r) bacc = fma(ys[r], ys[r], bacc);
-      }
+      for (int r = 0; r < KC / 2; ++r) bacc = fma(ac[r * SS], ys[r], bacc);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == SST) { stage = 0; ph ^= 1; }
   }
-  cp_async_wait<0>();
 
   double* out = p.part + (size_t)split * p.ka * p.kb;
 #pragma unroll
@@ -151,12 +167,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tn_kernel(const GemmTnParams p) {
     }
   }
   if (with_y) {
-    double* bo = p.bpart + (size_t)split * (p.ka + 1);
-    if (tid < TB) {
-      if (ti * TB + tid < p.ka) bo[ti * TB + tid] = bacc;
-    } else if (tid == TB && ti == 0) {
-      bo[p.ka] = bacc;
-    }
+    // fold the two row halves: all loads of the ring are done once every warp passed its last wait
+    named_bar_sync(1, GT_WARPS * 32);
+    double* ex = sm;          // [128]
+    if (tid >= TB) ex[tid - TB] = bacc;
+    named_bar_sync(1, GT_WARPS * 32);
+    if (tid < TB && ti * TB + tid < p.ka) p.bpart[(size_t)split * (p.ka + 1) + ti * TB + tid] = bacc + ex[tid];
   }
 }
 
@@ -211,10 +227,10 @@ cudaError_t launch_gemm_tn(const double* A, int64_t lda, int ka, const double* B
   gemm_tn_plan(n, p.ka, p.kb, sym, sms, &p);
   p.part = workspace;
   p.bpart = workspace + (size_t)p.ksplit * p.ka * p.kb;
-  const size_t smem = (size_t)SST * STAGE_DOUBLES * sizeof(double);
+  const size_t smem = GT_SMEM;
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gemm_tn_kernel<<<p.ntiles * p.ksplit, 256, smem, st>>>(p); count_launch();
+  gemm_tn_kernel<<<p.ntiles * p.ksplit, (GT_WARPS + 1) * 32, smem, st>>>(p); count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int64_t total = (int64_t)p.ka * p.kb + (p.y ? p.ka + 1 : 0);

@@ -144,10 +144,53 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         self.noise_var = noise_var
 
     def _get_model(self, X, y, kernel):
-        return _model.SparseGPRegression(X, y, kernel=kernel, Z=self.Z, num_inducing=self.num_inducing,
-                                         X_variance=self.X_variance, mean_function=self.mean_function,
-                                         normalizer=self.normalizer, chunk_rows=self.chunk_rows,
-                                         noise_var=self.noise_var)
+        import torch
+        kw = dict(kernel=kernel, Z=self.Z, num_inducing=self.num_inducing, X_variance=self.X_variance,
+                  mean_function=self.mean_function, normalizer=self.normalizer, chunk_rows=self.chunk_rows,
+                  noise_var=self.noise_var)
+        if isinstance(X, torch.Tensor):
+            return _model.SparseGPRegression(X, y, **kw)
+        # Host rows: copy them block by block on a side stream while the statistics pass already
+        # works on the blocks that have arrived; the non-finite scan (sklearn's check_X_y) runs on the
+        # device once the last block is in, before the first host read-back.
+        n, d = X.shape
+        dev = torch.device('cuda', torch.cuda.current_device())
+        de = d + (d & 1)
+        Xd = torch.zeros(n, de, dtype=torch.float64, device=dev) if de != d else \
+            torch.empty(n, d, dtype=torch.float64, device=dev)
+        Xh = torch.from_numpy(X)
+        yd = torch.from_numpy(y).to(dev, non_blocking=True)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)                       # Xd's allocation / zero fill
+        rows = int(max(1024, min(self.chunk_rows, max(n, 1))))
+        rows += rows & 1
+        events = []                                         # (end row, event), in row order
+        state = {'next': 0}
+
+        def loader(s, e):
+            # enqueue copies up to one block beyond e, then make the compute stream wait for rows < e
+            while state['next'] < n and state['next'] < e + rows:
+                s0 = state['next']
+                e0 = min(n, s0 + rows)
+                with torch.cuda.stream(copy_stream):
+                    Xd[s0:e0, :d].copy_(Xh[s0:e0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                events.append((s0, ev))
+                state['next'] = e0
+            while events and events[0][0] < e:
+                main.wait_event(events.pop(0)[1])
+
+        def check():
+            loader(0, n)
+            if not bool(torch.isfinite(Xd).all()):
+                raise ValueError("Input X contains NaN or infinity.")
+            if not bool(torch.isfinite(yd).all()):
+                raise ValueError("Input y contains NaN or infinity.")
+
+        Xd.record_stream(copy_stream)
+        return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check, **kw)
 
     def _check_data(self, X, y):
         """Validation of ``check_X_y`` (edrgp/gp_model/base.py:72-91) split so that the O(n d) part
@@ -159,30 +202,26 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                 raise ValueError("X must be (n, d) and y (n,)")
             Xd = X.to(device='cuda', dtype=torch.float64)
             yd = y.to(device='cuda', dtype=torch.float64).reshape(-1, 1)
-        else:
-            X = np.asarray(X)
-            y = np.asarray(y)
-            if X.ndim != 2:
-                raise ValueError("Expected 2D array, got %dD array instead" % X.ndim)
-            if y.ndim == 2 and y.shape[1] == 1:
-                y = y[:, 0]
-            if y.ndim != 1:
-                raise ValueError("y should be a 1d array, got an array of shape {} instead.".format(y.shape))
-            if X.shape[0] != y.shape[0]:
-                raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]"
-                                 % (X.shape[0], y.shape[0]))
-            if X.shape[0] < 1 or X.shape[1] < 1:
-                raise ValueError("Found array with %d sample(s) and %d feature(s) while a minimum of 1 is required."
-                                 % X.shape)
-            X = np.ascontiguousarray(X, dtype=np.float64)
-            y = np.ascontiguousarray(y, dtype=np.float64)
-            Xd = torch.from_numpy(X).to('cuda', non_blocking=True)
-            yd = torch.from_numpy(y).to('cuda', non_blocking=True).reshape(-1, 1)
-        if not bool(torch.isfinite(Xd).all()):
-            raise ValueError("Input X contains NaN or infinity.")
-        if not bool(torch.isfinite(yd).all()):
-            raise ValueError("Input y contains NaN or infinity.")
-        return Xd, yd
+            if not bool(torch.isfinite(Xd).all()):
+                raise ValueError("Input X contains NaN or infinity.")
+            if not bool(torch.isfinite(yd).all()):
+                raise ValueError("Input y contains NaN or infinity.")
+            return Xd, yd
+        X = np.asarray(X)
+        y = np.asarray(y)
+        if X.ndim != 2:
+            raise ValueError("Expected 2D array, got %dD array instead" % X.ndim)
+        if y.ndim == 2 and y.shape[1] == 1:
+            y = y[:, 0]
+        if y.ndim != 1:
+            raise ValueError("y should be a 1d array, got an array of shape {} instead.".format(y.shape))
+        if X.shape[0] != y.shape[0]:
+            raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]"
+                             % (X.shape[0], y.shape[0]))
+        if X.shape[0] < 1 or X.shape[1] < 1:
+            raise ValueError("Found array with %d sample(s) and %d feature(s) while a minimum of 1 is required."
+                             % X.shape)
+        return np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
 
     def _check_input(self, X):
         import torch

@@ -120,7 +120,8 @@ class SparseGPRegression(object):
     """
 
     def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, X_variance=None, mean_function=None,
-                 normalizer=None, device=None, chunk_rows=262144, cache_bytes=None, noise_var=1.0):
+                 normalizer=None, device=None, chunk_rows=262144, cache_bytes=None, noise_var=1.0,
+                 row_loader=None, pre_sync_check=None, input_dim=None):
         if X_variance is not None or mean_function is not None:
             raise NotImplementedError("uncertain inputs / mean functions are outside the B200 path")
         if not torch.cuda.is_available():
@@ -128,7 +129,8 @@ class SparseGPRegression(object):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.X = ops.pad_even(_as_device(X, self.device))          # (n_local, d_even)
         self.n_local, self.d_even = self.X.shape
-        self.input_dim = X.shape[1]
+        # input_dim: X may arrive already padded to an even width (estimator's overlapped loader)
+        self.input_dim = X.shape[1] if input_dim is None else int(input_dim)
         Yd = _as_device(Y, self.device).reshape(-1)
         if Yd.shape[0] != self.n_local:
             raise ValueError("X and Y row counts differ")
@@ -140,6 +142,9 @@ class SparseGPRegression(object):
             raise ValueError("kernel input_dim does not match X")
 
         if Z is None:
+            if row_loader is not None:               # the draw gathers arbitrary rows: load them all now
+                row_loader(0, self.n_local)
+                row_loader = None
             Zh = self._draw_inducing(min(int(num_inducing), self.num_data))
         else:
             Zh = np.array(Z, dtype=np.float64)
@@ -168,7 +173,13 @@ class SparseGPRegression(object):
         self._Kcache = None
         self._need_grad = False
         self.kernel_launches = 0
+        # row_loader(s, e): called once per row block, right before its first use, to enqueue the
+        # host->device copy of rows s:e of X (the estimator overlaps the copy of block i + 1 with the
+        # statistics of block i); pre_sync_check(): called before the first host read-back.
+        self._row_loader = row_loader
+        self._pre_sync_check = pre_sync_check
         self.parameters_changed()
+        self._row_loader = None
 
     # -------------------------------------------------------------------------------------------
     # inducing inputs: GPy takes ``X[np.random.permutation(n)[:m]]``; with sharded rows every rank
@@ -235,6 +246,8 @@ class SparseGPRegression(object):
         byy = torch.empty(m + 1, dtype=F64, device=dev)
         y = self.Y_normalized
         for i, (s, e) in enumerate(self._chunks()):
+            if self._row_loader is not None:
+                self._row_loader(s, e)
             Kc = self._Kcache[s:e] if self._Kcache is not None else self._Kbuf[:e - s]
             ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
             ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
@@ -245,6 +258,9 @@ class SparseGPRegression(object):
         Kmm = ops.kmm(self._pack, sf2, CONST_JITTER)
         res = ops.solve(Kmm, P, byy[:m].contiguous(), beta)
         self.kernel_launches += 8
+        if getattr(self, '_pre_sync_check', None) is not None:
+            check, self._pre_sync_check = self._pre_sync_check, None
+            check()
         info = res.info.cpu().tolist()
         if info[0] != 0 or info[1] != 0:
             raise np.linalg.LinAlgError("not positive definite: chol(Kuu) info=%d, chol(I + A) info=%d" % tuple(info))
