@@ -26,6 +26,7 @@ SIGNATURES = {
     'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
     'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_grad_gram_cached': (_int, [_c_dp, _i64, _int, _c_dp, _i64, _dbl, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_syrk_workspace_bytes': (_sz, [_i64, _int]),
     'edrgp_syrk': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
     'edrgp_inducing_stats': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _c_dp, _i64, _c_dp, _int, _c_dp, _c_dp]),
@@ -34,8 +35,10 @@ SIGNATURES = {
     'edrgp_kmm': (_int, [_c_dp, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _c_dp]),
     'edrgp_solve_workspace_bytes': (_sz, [_int]),
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_potrf': (_int, [_c_dp, _int, _i64, _c_dp, _c_dp]),
     'edrgp_trsm': (_int, [_c_dp, _int, _c_dp, _int, _int, _c_dp]),
     'edrgp_eigh': (_int, [_c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_count_nonfinite': (_int, [_c_dp, _i64, _c_dp, _c_dp]),
     'edrgp_col_moments_workspace_bytes': (_sz, [_int]),
     'edrgp_col_moments': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_weights_workspace_bytes': (_sz, [_i64, _int]),

@@ -104,6 +104,23 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_gram");
 }
 
+int edrgp_grad_gram_cached(const double* X, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
+                            const double* pack, int m, double* G, double* C, void* workspace, void* stream) {
+  int rc = check_x("grad_gram_cached", X, n, d, pack, m);
+  if (rc) return rc;
+  if (!Kfu || ldk < m || (ldk & 1) || !aligned16(Kfu))
+    return fail(EDRGP_ERR_ARG, "grad_gram_cached: Kfu must be 16-byte aligned with an even leading dimension >= m");
+  if (G && !aligned16(G)) return fail(EDRGP_ERR_ARG, "grad_gram_cached: G must be 16-byte aligned");
+  if (C && !workspace) return fail(EDRGP_ERR_ARG, "grad_gram_cached: C needs a workspace");
+  if (!edrgp::grad_gram_fused(d))
+    return fail(EDRGP_ERR_UNSUPPORTED, "grad_gram_cached: needs d <= 64; use edrgp_grad_gram");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "grad_gram_cached: no CUDA device");
+  cudaError_t e = edrgp::launch_grad_gram_cached(X, n, d, Kfu, ldk, sf2, pack, m, G, C, (double*)workspace, sms,
+                                                 (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_gram_cached");
+}
+
 size_t edrgp_syrk_workspace_bytes(int64_t n, int k) {
   int sms = sm_count_cached();
   if (sms <= 0) sms = 160;
@@ -201,6 +218,12 @@ int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double bet
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "solve");
 }
 
+int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream) {
+  if (!A || !info || m <= 0 || ld < m) return fail(EDRGP_ERR_ARG, "potrf: bad argument");
+  cudaError_t e = edrgp::launch_potrf(A, m, ld, info, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "potrf");
+}
+
 int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream) {
   if (!L || !B || m <= 0 || nrhs <= 0) return fail(EDRGP_ERR_ARG, "trsm: bad argument");
   cudaError_t e = edrgp::launch_trsm(L, m, m, B, nrhs, nrhs, trans, (cudaStream_t)stream);
@@ -228,6 +251,15 @@ int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, co
   cudaError_t e = edrgp::launch_col_moments(X, n, d, shift, weight, out, accumulate, (double*)workspace, sms,
                                             (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "col_moments");
+}
+
+int edrgp_count_nonfinite(const double* X, int64_t total, unsigned int* count, void* stream) {
+  if (!X || !count || total < 0) return fail(EDRGP_ERR_ARG, "count_nonfinite: bad argument");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "count_nonfinite: no CUDA device");
+  if (total == 0) return EDRGP_OK;
+  cudaError_t e = edrgp::launch_count_nonfinite(X, total, count, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "count_nonfinite");
 }
 
 int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,

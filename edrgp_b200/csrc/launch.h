@@ -13,6 +13,9 @@ cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, 
 bool grad_gram_fused(int d);
 cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pack, int m, double* G, double* C,
                              double* Cpart, int sms, cudaStream_t st);
+cudaError_t launch_grad_gram_cached(const double* X, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
+                                    const double* pack, int m, double* G, double* C, double* Cpart, int sms,
+                                    cudaStream_t st);
 cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
                        int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st);
 
@@ -37,6 +40,7 @@ size_t weights_workspace_bytes(int64_t n, int m);
 cudaError_t launch_weights(const double* K, int64_t n, int m, int64_t ldk, const double* M, int64_t ldm, const double* y,
                            const double* alpha, double c_ya, double c_km, double* T, int64_t ldt, double* rowsum,
                            double* colsum, int accumulate, double* workspace, cudaStream_t st);
+cudaError_t launch_count_nonfinite(const double* X, int64_t total, unsigned int* count, int sms, cudaStream_t st);
 cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,
                                int sms, cudaStream_t st);
 cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, int k, double* out, int sms,

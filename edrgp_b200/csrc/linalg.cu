@@ -69,60 +69,81 @@ static cudaError_t gemm_small(int M, int N, int K, double alpha, const double* A
 // ---------------------------------------------------------------------------------------------
 // Cholesky, lower, in place (upper triangle left untouched).  info[0] = 1 + column of the first
 // non-positive pivot (0 = success), like LAPACK dpotrf.
+//
+// One blocked step = two launches: potrf_step_kernel factors the 32 x 32 diagonal block in
+// registers (lane i holds row i; pivots and column entries travel by warp shuffles) and solves the
+// panel below it, every one-warp CTA re-deriving the small factor for itself instead of waiting for
+// another launch; gemm_small_kernel then applies the trailing update.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) potf2_kernel(double* __restrict__ A, int64_t ld, int k0, int nb, int* info) {
-  __shared__ double s[NBK][NBK + 1];
-  const int i = threadIdx.x;
-  for (int c = 0; c < nb; ++c) s[i][c] = (i < nb) ? A[(int64_t)(k0 + i) * ld + k0 + c] : 0.0;
-  __syncwarp();
-  for (int j = 0; j < nb; ++j) {
-    const double ajj = s[j][j];
-    if (!(ajj > 0.0)) {
-      if (i == 0 && atomicCAS(info, 0, k0 + j + 1) == 0) {}
-      return;
+__device__ __forceinline__ void potf2_regs(double (&a)[NBK], int lane, int nb, int k0, int* info) {
+#pragma unroll
+  for (int j = 0; j < NBK; ++j) {
+    const double djj = __shfl_sync(0xffffffffu, a[j], j);
+    if (j < nb && !(djj > 0.0)) {
+      if (info != nullptr && lane == 0) atomicCAS(info, 0, k0 + j + 1);
     }
-    const double ljj = sqrt(ajj);
-    __syncwarp();
-    if (i == j) s[j][j] = ljj;
-    if (i > j && i < nb) s[i][j] /= ljj;
-    __syncwarp();
-    const double lij = s[i][j];
-    for (int c = j + 1; c < nb; ++c)
-      if (i >= c && i < nb) s[i][c] = fma(-lij, s[c][j], s[i][c]);
-    __syncwarp();
+    const double ljj = sqrt(djj);
+    const double lij = lane == j ? ljj : a[j] / ljj;
+    if (lane >= j) a[j] = lij;
+#pragma unroll
+    for (int c = j + 1; c < NBK; ++c) {
+      const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] = fma(-lij, lcj, a[c]);
+    }
   }
-  if (i < nb)
-    for (int c = 0; c <= i; ++c) A[(int64_t)(k0 + i) * ld + k0 + c] = s[i][c];
 }
 
-// rows below the diagonal block:  A21 <- A21 L11^-T   (one thread per row)
-__global__ void __launch_bounds__(32) potrf_panel_kernel(double* __restrict__ A, int64_t ld, int k0, int nb, int m,
-                                                         const int* info) {
-  __shared__ double L[NBK][NBK + 1];
+// CTA 0 also writes the factored diagonal block back; CTA b solves rows k0+nb+32b.. of the panel:
+// A21 <- A21 L11^-T.
+__global__ void __launch_bounds__(32) potrf_step_kernel(double* __restrict__ A, int64_t ld, int k0, int nb, int m,
+                                                        int* info) {
+  __shared__ double S[NBK][NBK + 1];
   __shared__ double X[NBK][NBK + 1];
-  if (*info != 0) return;
-  const int i = threadIdx.x;
-  const int row = k0 + nb + blockIdx.x * NBK + i;
-  for (int c = 0; c < nb; ++c) {
-    L[i][c] = (i < nb && c <= i) ? A[(int64_t)(k0 + i) * ld + k0 + c] : 0.0;
-  }
-  // coalesced load of the 32 x nb block of rows (lane = column)
+  const int lane = threadIdx.x;
+  // coalesced load of the diagonal block (lane = column), padded with the identity
   for (int r = 0; r < NBK; ++r) {
-    const int rr = k0 + nb + blockIdx.x * NBK + r;
-    X[r][i] = (rr < m && i < nb) ? A[(int64_t)rr * ld + k0 + i] : 0.0;
+    double v = (r == lane) ? 1.0 : 0.0;
+    if (r < nb && lane < nb && lane <= r) v = A[(int64_t)(k0 + r) * ld + k0 + lane];
+    S[r][lane] = v;
   }
   __syncwarp();
-  if (row < m) {
-    for (int c = 0; c < nb; ++c) {
-      double v = X[i][c];
-      for (int q = 0; q < c; ++q) v = fma(-X[i][q], L[c][q], v);
-      X[i][c] = v / L[c][c];
+  double a[NBK];
+#pragma unroll
+  for (int c = 0; c < NBK; ++c) a[c] = S[lane][c];
+  potf2_regs(a, lane, nb, k0, blockIdx.x == 0 ? info : nullptr);
+#pragma unroll
+  for (int c = 0; c < NBK; ++c) S[lane][c] = a[c];          // S = L11 (lower; junk above the diagonal unused)
+  __syncwarp();
+  if (blockIdx.x == 0) {
+    for (int r = 0; r < nb; ++r)
+      if (lane <= r && lane < nb) A[(int64_t)(k0 + r) * ld + k0 + lane] = S[r][lane];
+  }
+  const int row0 = k0 + nb + blockIdx.x * NBK;
+  if (row0 >= m) return;
+  for (int r = 0; r < NBK; ++r) {
+    const int rr = row0 + r;
+    X[r][lane] = (rr < m && lane < nb) ? A[(int64_t)rr * ld + k0 + lane] : 0.0;
+  }
+  __syncwarp();
+  {
+    // lane = row of the panel: forward substitution against L11^T, entries kept in registers
+    double x[NBK];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) x[c] = X[lane][c];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) {
+      double v = x[c];
+#pragma unroll
+      for (int q = 0; q < c; ++q) v = fma(-x[q], S[c][q], v);
+      x[c] = v / S[c][c];
     }
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) X[lane][c] = x[c];
   }
   __syncwarp();
   for (int r = 0; r < NBK; ++r) {
-    const int rr = k0 + nb + blockIdx.x * NBK + r;
-    if (rr < m && i < nb) A[(int64_t)rr * ld + k0 + i] = X[r][i];
+    const int rr = row0 + r;
+    if (rr < m && lane < nb) A[(int64_t)rr * ld + k0 + lane] = X[r][lane];
   }
 }
 
@@ -131,10 +152,10 @@ cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t s
   if (e != cudaSuccess) return e;
   for (int k0 = 0; k0 < m; k0 += NBK) {
     const int nb = min(NBK, m - k0);
-    potf2_kernel<<<1, 32, 0, st>>>(A, ld, k0, nb, info); count_launch();
     const int rest = m - k0 - nb;
+    const int ctas = rest > 0 ? (rest + NBK - 1) / NBK : 1;
+    potrf_step_kernel<<<ctas, 32, 0, st>>>(A, ld, k0, nb, m, info); count_launch();
     if (rest > 0) {
-      potrf_panel_kernel<<<(rest + NBK - 1) / NBK, 32, 0, st>>>(A, ld, k0, nb, m, info); count_launch();
       // A22 -= L21 L21^T (lower blocks only)
       double* A22 = A + (int64_t)(k0 + nb) * ld + k0 + nb;
       const double* L21 = A + (int64_t)(k0 + nb) * ld + k0;
@@ -187,10 +208,87 @@ __global__ void __launch_bounds__(32) trsm_diag_kernel(const double* __restrict_
     if (r < nb) B[(int64_t)(k0 + r) * ldb + col] = x[r];
 }
 
+// One right-hand side: the whole solve in ONE CTA (256 threads).  Per 32-block: warp 0 solves the
+// diagonal block with the unknowns in registers (one per lane, shuffles), then all threads update
+// the remaining entries.  x has stride incx.
+__global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ L, int64_t ldl, int m,
+                                                   double* __restrict__ x, int64_t incx, int trans) {
+  extern __shared__ double xs[];             // [m] the vector, then [32][33] diagonal block
+  double* D = xs + ((m + 1) & ~1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < m; i += blockDim.x) xs[i] = x[i * incx];
+  __syncthreads();
+  const int nblk = (m + NBK - 1) / NBK;
+  for (int bb = 0; bb < nblk; ++bb) {
+    const int b = trans ? nblk - 1 - bb : bb;
+    const int k0 = b * NBK, nb = min(NBK, m - k0);
+    // diagonal block -> shared (identity padded): D[r][c] = L[k0+r][k0+c]
+    for (int i = tid; i < NBK * NBK; i += blockDim.x) {
+      const int r = i >> 5, c = i & 31;
+      double v = r == c ? 1.0 : 0.0;
+      if (r < nb && c <= r) v = L[(int64_t)(k0 + r) * ldl + k0 + c];
+      D[r * (NBK + 1) + c] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xi = lane < nb ? xs[k0 + lane] : 0.0;
+      const double inv = 1.0 / D[lane * (NBK + 1) + lane];
+      if (!trans) {
+#pragma unroll
+        for (int j = 0; j < NBK; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, xi * inv, j);      // final x_j (lane j)
+          if (lane == j) xi = xj;
+          else if (lane > j) xi = fma(-D[lane * (NBK + 1) + j], xj, xi);
+        }
+      } else {
+#pragma unroll
+        for (int j = NBK - 1; j >= 0; --j) {
+          const double xj = __shfl_sync(0xffffffffu, xi * inv, j);
+          if (lane == j) xi = xj;
+          else if (lane < j) xi = fma(-D[j * (NBK + 1) + lane], xj, xi);
+        }
+      }
+      if (lane < nb) xs[k0 + lane] = xi;
+    }
+    __syncthreads();
+    if (!trans) {
+      // rows below: x_r -= sum_k L[r][k0+k] x_k
+      for (int r = k0 + nb + tid; r < m; r += blockDim.x) {
+        const double* lr = L + (int64_t)r * ldl + k0;
+        double v = xs[r];
+#pragma unroll 8
+        for (int k = 0; k < NBK; ++k) if (k < nb) v = fma(-lr[k], xs[k0 + k], v);
+        xs[r] = v;
+      }
+    } else {
+      // entries above: x_r -= sum_k L[k0+k][r] x_k   (coalesced over r)
+      for (int r = tid; r < k0; r += blockDim.x) {
+        double v = xs[r];
+#pragma unroll 8
+        for (int k = 0; k < NBK; ++k) if (k < nb) v = fma(-L[(int64_t)(k0 + k) * ldl + r], xs[k0 + k], v);
+        xs[r] = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += blockDim.x) x[i * incx] = xs[i];
+}
+
 cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
                         cudaStream_t st) {
   const int nblk = (m + NBK - 1) / NBK;
   cudaError_t e = cudaSuccess;
+  if (nrhs == 1) {
+    const size_t smem = ((size_t)((m + 1) & ~1) + NBK * (NBK + 1)) * sizeof(double);
+    if (smem <= 200 * 1024) {
+      if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      trsv_kernel<<<1, 256, smem, st>>>(L, ldl, m, B, ldb, trans); count_launch();
+      return cudaGetLastError();
+    }
+  }
   if (!trans) {
     for (int b = 0; b < nblk; ++b) {
       const int k0 = b * NBK, nb = min(NBK, m - k0);
@@ -317,9 +415,9 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 // Output: evals sorted descending, comps[k][:] = k-th eigenvector (rows), sign fixed so that the
 // largest-magnitude entry of every row is positive.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* __restrict__ A, int d, double* __restrict__ V,
+__global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* Ag, int d, double* Vg,
                                                            double* __restrict__ evals, double* __restrict__ comps,
-                                                           int max_sweeps, int* __restrict__ sweeps_out) {
+                                                           int max_sweeps, int* __restrict__ sweeps_out, int use_smem) {
   extern __shared__ double sh[];
   const int dd = d + (d & 1);          // players in the round-robin (one bye if d is odd)
   const int np = dd / 2;
@@ -327,8 +425,14 @@ __global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* __restrict__ 
   double* cs_s = sh + np;              // [np]
   int* pp = reinterpret_cast<int*>(sh + 2 * np);   // [np]
   int* qq = pp + np;                   // [np]
+  // the matrix and the accumulated rotations live in shared memory when they fit (every step is a
+  // chain of dependent reads: ~30 cycles there against ~700 through L2)
+  double* A = use_smem ? sh + 3 * np + (np & 1) : Ag;
+  double* V = use_smem ? A + (size_t)d * d : Vg;
   __shared__ int rotated;
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (use_smem)
+    for (int i = tid; i < d * d; i += nt) A[i] = Ag[i];
   for (int i = tid; i < d * d; i += nt) V[i] = ((i / d) == (i % d)) ? 1.0 : 0.0;
   __syncthreads();
   int sweep = 0;
@@ -411,8 +515,15 @@ __global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* __restrict__ 
 
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
   const int dd = d + (d & 1), np = dd / 2;
-  const size_t smem = (size_t)np * (2 * sizeof(double) + 2 * sizeof(int));
-  jacobi_eigh_kernel<<<1, 1024, smem, st>>>(A, d, V, evals, comps, 60, sweeps); count_launch();
+  size_t smem = (size_t)(3 * np + (np & 1)) * sizeof(double);
+  const size_t mats = (size_t)2 * d * d * sizeof(double);
+  const int use_smem = smem + mats <= 220 * 1024;
+  if (use_smem) smem += mats;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  jacobi_eigh_kernel<<<1, 1024, smem, st>>>(A, d, V, evals, comps, 60, sweeps, use_smem); count_launch();
   return cudaGetLastError();
 }
 

@@ -95,6 +95,7 @@ struct PipeParams {
   const double* y;
   double* b;
   double* mu;       // kuf only: mu_i = sum_j K_ij coef_j (posterior mean when coef = alpha)
+  const double* Kin;   // cached-Kfu gradient kernel: stored entries (n, ldk), read instead of recomputed
 };
 
 // Producer warp: streams the X row tiles and the inducing tiles of every row tile of this CTA.
@@ -131,6 +132,42 @@ __device__ __forceinline__ void producer_loop(const PipeParams& p, double* xbuf,
       if (XS > 1 && mt == 0 && tile + gridDim.x < p.ntiles) issue_x(tile + gridDim.x);
     }
     if (XS == 1 && tile + gridDim.x < p.ntiles) issue_x(tile + gridDim.x);
+  }
+}
+
+// Producer of the cached-Kfu gradient kernel: streams the pack tiles; the X row tile is only needed
+// by the epilogue, so it is requested a few stages into the tile, once the previous tile released it.
+// (The stored Kfu entries are read by the compute warps themselves, as register fragments straight
+// from global memory: 256-byte row slices are too small for the bulk-copy engine -- one UBLKCP per
+// row slice measured 0.6 TB/s.)
+template <int DP, int NS>
+__device__ __forceinline__ void producer_loop_cached(const PipeParams& p, double* xbuf, double* zbuf, uint64_t* xfull,
+                                                     uint64_t* xempty, uint64_t* zfull, uint64_t* zempty, int lane) {
+  using L = Smem<DP, 1, NS>;
+  const double* tiles = p.pack + DP;
+  const uint32_t row_bytes = (uint32_t)p.d * 8u;
+  int xph = 0, zs = 0, zph = 0;
+  const int x_at = p.mtiles > 2 ? 2 : p.mtiles - 1;
+  for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * BM;
+    const int rows = (int)min((int64_t)BM, p.n - row0);
+    for (int mt = 0; mt < p.mtiles; ++mt) {
+      mbar_wait(&zempty[zs], zph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&zfull[zs], (uint32_t)L::TILE * 8u);
+        bulk_g2s(zbuf + (size_t)zs * L::TILE, tiles + (size_t)mt * L::TILE, (uint32_t)L::TILE * 8u, &zfull[zs]);
+      }
+      __syncwarp();
+      if (++zs == NS) { zs = 0; zph ^= 1; }
+      if (mt == x_at) {
+        mbar_wait(&xempty[0], xph ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&xfull[0], (uint32_t)rows * row_bytes);
+        __syncwarp();
+        for (int r = lane; r < rows; r += 32)
+          bulk_g2s(xbuf + (size_t)r * L::S, p.X + (row0 + r) * p.d, row_bytes, &xfull[0]);
+        xph ^= 1;
+      }
+    }
   }
 }
 
@@ -185,9 +222,10 @@ __device__ __forceinline__ void dist_gemm(double (&s)[2][MT / 8][2], const doubl
 // -------------------------------------------------------------------------------------------------
 // K1+K4+K5 fused
 // -------------------------------------------------------------------------------------------------
-template <int DP, bool FUSE_GRAM, int XS, int NS>
+template <int DP, bool FUSE_GRAM, int XS, int NS, bool FROM_K = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const PipeParams p) {
   using L = Smem<DP, XS, NS>;
+  static_assert(!FROM_K || XS == 1, "the cached-Kfu variant keeps one X buffer");
   constexpr int S = L::S;
   constexpr int NB = DP / 8;                         // 8-wide feature blocks
   constexpr int CBLK = FUSE_GRAM ? (NB * NB + WARPS - 1) / WARPS : 1;   // Gram blocks per warp
@@ -215,7 +253,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
   __syncthreads();
 
   if (warp == WARPS) {
-    producer_loop<DP, XS, NS>(p, xbuf, zbuf, xfull, xempty, zfull, zempty, lane);
+    if (FROM_K) producer_loop_cached<DP, NS>(p, xbuf, zbuf, xfull, xempty, zfull, zempty, lane);
+    else producer_loop<DP, XS, NS>(p, xbuf, zbuf, xfull, xempty, zfull, zempty, lane);
     return;
   }
 
@@ -230,35 +269,78 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
     const int64_t row0 = tile * BM;
     double* xt = xbuf + (size_t)xs * BM * S;
     double* xw = xt + r0 * S;
-    mbar_wait(&xfull[xs], xph);
-    row_half_norms<DP>(xw, il2s, hxs + r0, lane);
-    __syncwarp();
-    const double hx0 = hxs[r0 + g], hx1 = hxs[r0 + g + 8];
+    double hx0 = 0.0, hx1 = 0.0;
     const double* xr0 = xw + g * S;
     const double* xr1 = xw + (g + 8) * S;
+    if (!FROM_K) {
+      mbar_wait(&xfull[xs], xph);
+      row_half_norms<DP>(xw, il2s, hxs + r0, lane);
+      __syncwarp();
+      hx0 = hxs[r0 + g]; hx1 = hxs[r0 + g + 8];
+    }
 
     double acc[2][NB][2];
 #pragma unroll
     for (int qb = 0; qb < NB; ++qb) { acc[0][qb][0] = acc[0][qb][1] = acc[1][qb][0] = acc[1][qb][1] = 0.0; }
     double rs0 = 0.0, rs1 = 0.0;
 
+    // cached variant: this lane's 16 stored Kfu entries of one inducing tile (rows g, g + 8 of the
+    // warp; columns 8 nb + {2t, 2t + 1}), fetched one tile ahead straight from global memory
+    double2 kf[2][MT / 8];
+    const double* krow0 = nullptr;
+    const double* krow1 = nullptr;
+    auto load_kf = [&](int mt) {
+#pragma unroll
+      for (int nb = 0; nb < MT / 8; ++nb) {
+        const int col = mt * MT + 8 * nb + 2 * t;
+        double2 a, b;
+        a.x = a.y = b.x = b.y = 0.0;
+        if (col < p.m) {       // ldk is even: the pair is in bounds; a column == m carries coefficient 0
+          a = __ldg(reinterpret_cast<const double2*>(krow0 + col));
+          b = __ldg(reinterpret_cast<const double2*>(krow1 + col));
+        }
+        kf[0][nb] = a; kf[1][nb] = b;
+      }
+    };
+    if (FROM_K) {
+      const int64_t ra = min(row0 + r0 + g, p.n - 1), rb = min(row0 + r0 + g + 8, p.n - 1);   // masked later
+      krow0 = p.Kin + ra * p.ldk;
+      krow1 = p.Kin + rb * p.ldk;
+      load_kf(0);
+    }
+
     for (int mt = 0; mt < p.mtiles; ++mt) {
       const double* zt = zbuf + (size_t)zs * L::TILE;
       mbar_wait(&zfull[zs], zph);
       double s[2][MT / 8][2];
-      dist_gemm<DP>(s, xr0, xr1, zt, hx0, hx1, g, t);
-      // W = exp(-r^2/2) * coef, zero where the clipped r^2 is zero (GPy's _inv_dist)
       const double* cf = zt + MT * S + MT;
+      if (FROM_K) {
+        // W = Kfu * coef from the stored entries; an entry equal to the kernel variance is
+        // exp(0): a pair whose clipped r^2 is zero, which GPy's _inv_dist drops
 #pragma unroll
-      for (int nb = 0; nb < MT / 8; ++nb) {
-        const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
+        for (int nb = 0; nb < MT / 8; ++nb) {
+          const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
+          const double2 k0 = kf[0][nb], k1 = kf[1][nb];
+          const double w00 = k0.x != p.sf2 ? k0.x * c.x : 0.0, w01 = k0.y != p.sf2 ? k0.y * c.y : 0.0;
+          const double w10 = k1.x != p.sf2 ? k1.x * c.x : 0.0, w11 = k1.y != p.sf2 ? k1.y * c.y : 0.0;
+          s[0][nb][0] = w00; s[0][nb][1] = w01; s[1][nb][0] = w10; s[1][nb][1] = w11;
+          rs0 += w00 + w01; rs1 += w10 + w11;
+        }
+        if (mt + 1 < p.mtiles) load_kf(mt + 1);       // in flight during the contraction below
+      } else {
+        dist_gemm<DP>(s, xr0, xr1, zt, hx0, hx1, g, t);
+        // W = exp(-r^2/2) * coef, zero where the clipped r^2 is zero (GPy's _inv_dist)
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const double e0 = s[mb][nb][0], e1 = s[mb][nb][1];
-          const double w0 = e0 < 0.0 ? exp(e0) * c.x : 0.0;
-          const double w1 = e1 < 0.0 ? exp(e1) * c.y : 0.0;
-          s[mb][nb][0] = w0; s[mb][nb][1] = w1;
-          if (mb == 0) rs0 += w0 + w1; else rs1 += w0 + w1;
+        for (int nb = 0; nb < MT / 8; ++nb) {
+          const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const double e0 = s[mb][nb][0], e1 = s[mb][nb][1];
+            const double w0 = e0 < 0.0 ? exp(e0) * c.x : 0.0;
+            const double w1 = e1 < 0.0 ? exp(e1) * c.y : 0.0;
+            s[mb][nb][0] = w0; s[mb][nb][1] = w1;
+            if (mb == 0) rs0 += w0 + w1; else rs1 += w0 + w1;
+          }
         }
       }
       // acc += W * (Z / l^2): the accumulator columns {2t, 2t+1} of block nb become k-slices whose
@@ -283,6 +365,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
     }
 
     // G = acc - rowsum(W) * x / l^2, staged over this warp's own X rows
+    if (FROM_K) mbar_wait(&xfull[xs], xph);
     rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
     rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
     const bool v0 = row0 + r0 + g < p.n, v1 = row0 + r0 + g + 8 < p.n;
@@ -475,6 +558,16 @@ static cudaError_t launch_grad_gram_t(const PipeParams& p, int grid, cudaStream_
   return cudaGetLastError();
 }
 
+template <int DP, int NS>
+static cudaError_t launch_grad_gram_cached_t(const PipeParams& p, int grid, cudaStream_t st) {
+  using L = Smem<DP, 1, NS>;
+  auto kern = grad_gram_kernel<DP, true, 1, NS, true>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p); count_launch();
+  return cudaGetLastError();
+}
+
 template <int DP, int XS, int NS>
 static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) {
   using L = Smem<DP, XS, NS>;
@@ -518,6 +611,31 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
   }
   if (e != cudaSuccess) return e;
   if (C != nullptr && dp <= 64) {
+    reduce_gram_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(Cpart, grid, dp, d, C); count_launch();
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+cudaError_t launch_grad_gram_cached(const double* X, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
+                                    const double* pack, int m, double* G, double* C, double* Cpart, int sms,
+                                    cudaStream_t st) {
+  PipeParams p{};
+  p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
+  p.ntiles = (n + BM - 1) / BM; p.G = G; p.Cpart = C ? Cpart : nullptr; p.m = m;
+  p.Kin = Kin; p.ldk = ldk; p.sf2 = sf2;
+  const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+  const int dp = padded_dim(d);
+  cudaError_t e;
+  switch (dp) {
+    case 16: e = launch_grad_gram_cached_t<16, 4>(p, grid, st); break;
+    case 32: e = launch_grad_gram_cached_t<32, 4>(p, grid, st); break;
+    case 48: e = launch_grad_gram_cached_t<48, 4>(p, grid, st); break;
+    case 64: e = launch_grad_gram_cached_t<64, 4>(p, grid, st); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e != cudaSuccess) return e;
+  if (C != nullptr) {
     reduce_gram_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(Cpart, grid, dp, d, C); count_launch();
     e = cudaGetLastError();
   }

@@ -117,6 +117,38 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
   }
 }
 
+// count[0] += number of non-finite entries (NaN or +-Inf): sklearn's check_X_y / check_array scan
+// (edrgp/gp_model/base.py:87,105) as one HBM-speed pass on the device.
+__global__ void __launch_bounds__(256) count_nonfinite_kernel(const double* __restrict__ X, int64_t total,
+                                                              unsigned int* __restrict__ count) {
+  unsigned int bad = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) {
+    const int64_t pairs = total >> 1;
+    const double2* X2 = reinterpret_cast<const double2*>(X);
+    for (int64_t j = i; j < pairs; j += stride) {
+      const double2 v = X2[j];
+      bad += !isfinite(v.x);
+      bad += !isfinite(v.y);
+    }
+    if ((total & 1) && i == 0) bad += !isfinite(X[total - 1]);
+  } else {
+    for (int64_t j = i; j < total; j += stride) bad += !isfinite(X[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
+cudaError_t launch_count_nonfinite(const double* X, int64_t total, unsigned int* count, int sms, cudaStream_t st) {
+  int64_t blocks = (total / 2 + 255) / 256;
+  if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+  if (blocks < 1) blocks = 1;
+  count_nonfinite_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, total, count); count_launch();
+  return cudaGetLastError();
+}
+
 size_t col_moments_workspace_bytes(int d, int sms) { return (size_t)sms * 4 * 2 * d * sizeof(double); }
 
 cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,

@@ -29,12 +29,24 @@ class _BaseGP(BaseEstimator):
         ``'optimize_restarts'`` or ``'fixed'``) with ``messages=False, max_iters=1000`` defaults
         (edrgp/gp_model/base.py:46-70)."""
         X, y = self._check_data(X, y)
-        self.n_features_ = X.shape[1]
-        kernel = self._make_kernel()
-        self.estimator_ = self._get_model(X, y, kernel)
-        opt_kws.setdefault('messages', False)
-        opt_kws.setdefault('max_iters', 1000)
-        getattr(self.estimator_, self.method)(**opt_kws)
+        previous = {k: getattr(self, k) for k in ('n_features_', 'estimator_') if hasattr(self, k)}
+        try:
+            self.n_features_ = X.shape[1]
+            kernel = self._make_kernel()
+            model = self._get_model(X, y, kernel)
+            opt_kws.setdefault('messages', False)
+            opt_kws.setdefault('max_iters', 1000)
+            getattr(model, self.method)(**opt_kws)
+            model._check_pd()          # deferred input / positive-definiteness checks surface here
+        except Exception:
+            # a failed fit leaves the estimator as it was (the reference validates before it builds)
+            for k in ('n_features_', 'estimator_'):
+                if k in previous:
+                    setattr(self, k, previous[k])
+                elif hasattr(self, k):
+                    delattr(self, k)
+            raise
+        self.estimator_ = model
         return self
 
     def _check_data(self, X, y):
@@ -148,8 +160,20 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         kw = dict(kernel=kernel, Z=self.Z, num_inducing=self.num_inducing, X_variance=self.X_variance,
                   mean_function=self.mean_function, normalizer=self.normalizer, chunk_rows=self.chunk_rows,
                   noise_var=self.noise_var)
+        from . import ops as _ops
+
+        def raise_if_nonfinite(Xc, yc):
+            bad = _ops.count_nonfinite(Xc, yc)          # enqueued now, read at the first host sync
+
+            def check():
+                if int(bad.cpu()[0]) != 0:
+                    if int(_ops.count_nonfinite(Xc).cpu()[0]) != 0:
+                        raise ValueError("Input X contains NaN or infinity.")
+                    raise ValueError("Input y contains NaN or infinity.")
+            return check
+
         if isinstance(X, torch.Tensor):
-            return _model.SparseGPRegression(X, y, **kw)
+            return _model.SparseGPRegression(X, y, pre_sync_check=raise_if_nonfinite(X, y), **kw)
         # Host rows: copy them block by block on a side stream while the statistics pass already
         # works on the blocks that have arrived; the non-finite scan (sklearn's check_X_y) runs on the
         # device once the last block is in, before the first host read-back.
@@ -184,10 +208,7 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
         def check():
             loader(0, n)
-            if not bool(torch.isfinite(Xd).all()):
-                raise ValueError("Input X contains NaN or infinity.")
-            if not bool(torch.isfinite(yd).all()):
-                raise ValueError("Input y contains NaN or infinity.")
+            raise_if_nonfinite(Xd, yd)()
 
         Xd.record_stream(copy_stream)
         return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check, **kw)
@@ -202,11 +223,7 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                 raise ValueError("X must be (n, d) and y (n,)")
             Xd = X.to(device='cuda', dtype=torch.float64)
             yd = y.to(device='cuda', dtype=torch.float64).reshape(-1, 1)
-            if not bool(torch.isfinite(Xd).all()):
-                raise ValueError("Input X contains NaN or infinity.")
-            if not bool(torch.isfinite(yd).all()):
-                raise ValueError("Input y contains NaN or infinity.")
-            return Xd, yd
+            return Xd, yd                    # the non-finite scan runs on the device (see _get_model)
         X = np.asarray(X)
         y = np.asarray(y)
         if X.ndim != 2:

@@ -217,8 +217,9 @@ class SparseGPRegression(object):
             need = self.n_local * ldk * 8
             budget = self.cache_bytes
             if budget is None:
-                free, _ = torch.cuda.mem_get_info(self.device)
-                budget = int(0.5 * free)
+                # (cudaMemGetInfo costs ~25 ms per call on this driver: use the allocator's counters)
+                total = torch.cuda.get_device_properties(self.device).total_memory
+                budget = int(0.5 * max(0, total - torch.cuda.memory_allocated(self.device)))
             if need <= budget:
                 self._Kcache = torch.empty(self.n_local, ldk, dtype=F64, device=self.device)
         if getattr(self, '_Kbuf', None) is None or self._Kbuf.shape[1] != ldk:
@@ -239,7 +240,8 @@ class SparseGPRegression(object):
         self._Z_dev = torch.as_tensor(Zp, device=dev)
         beta = 1.0 / max(float(self.noise_variance), CONST_JITTER)
         need_grad = self._need_grad
-        ldk = self._kbuffers(need_grad)
+        # the stored Kfu blocks are reused by the gradient passes when the whole matrix fits
+        ldk = self._kbuffers(True)
 
         self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
         P = torch.empty(m, m, dtype=F64, device=dev)
@@ -255,12 +257,40 @@ class SparseGPRegression(object):
         if self.n_local == 0:
             P.zero_(); byy.zero_()
         dist.allreduce_sum_(P, byy)
+        self._stats = (P, byy)
+        self._beta = beta
+        self._solve = None
+        self._log_marginal_likelihood = None
+        self._woodbury_inv = None
+        self._info_dev = None
+        self._alpha_is_direct = not need_grad
+        if need_grad:
+            trA, data_fit = self._full_chain()
+            self._gradients(P, self._solve, beta, sf2, ell[:d], trA, data_fit, float(byy[m]), ldk)
+        else:
+            # Fixed hyper-parameters: the posterior weights need ONE Cholesky.  With Lm = chol(Kuu) and
+            # LB = chol(I + beta Lm^-1 P Lm^-T) of GPy's chain, Lm LB is the Cholesky factor of
+            # S = Kuu + beta P, so alpha = Lm^-T LB^-T LB^-1 Lm^-1 beta b = S^-1 beta b.  The bound, the
+            # Woodbury inverse and the gradients run the full chain on demand (_ensure_full).
+            S = ops.kmm(self._pack, sf2, CONST_JITTER)
+            S.add_(P, alpha=beta)
+            S, info = ops.potrf(S)
+            v = byy[:m] * beta
+            ops.trsm(S, v, False)
+            ops.trsm(S, v, True)
+            self.alpha = v                                       # GPy posterior.woodbury_vector (m,)
+            self._info_dev = info
+            self.kernel_launches += 40
+
+    def _full_chain(self):
+        """GPy's VarDTC Cholesky chain from the reduced statistics: Lm, LB, alpha, bound."""
+        m = self.num_inducing
+        P, byy = self._stats
+        beta, sf2 = self._beta, float(self.kern.variance)
         Kmm = ops.kmm(self._pack, sf2, CONST_JITTER)
         res = ops.solve(Kmm, P, byy[:m].contiguous(), beta)
         self.kernel_launches += 8
-        if getattr(self, '_pre_sync_check', None) is not None:
-            check, self._pre_sync_check = self._pre_sync_check, None
-            check()
+        self._run_pre_sync_check()
         info = res.info.cpu().tolist()
         if info[0] != 0 or info[1] != 0:
             raise np.linalg.LinAlgError("not positive definite: chol(Kuu) info=%d, chol(I + A) info=%d" % tuple(info))
@@ -272,11 +302,27 @@ class SparseGPRegression(object):
                  - 0.5 * (beta * n * sf2 - trA) - sumlogLB + 0.5 * data_fit)
         self._log_marginal_likelihood = np.array([[bound]])
         self._solve = res
-        self._beta = beta
-        self.alpha = res.alpha                                   # GPy posterior.woodbury_vector (m,)
-        self._woodbury_inv = None
-        if need_grad:
-            self._gradients(P, res, beta, sf2, ell[:d], trA, data_fit, yy, ldk)
+        if not self._alpha_is_direct:           # keep one alpha per hyper-parameter set: results stay bit-stable
+            self.alpha = res.alpha
+        self._info_dev = None
+        return trA, data_fit
+
+    def _ensure_full(self):
+        if self._solve is None:
+            self._full_chain()
+
+    def _run_pre_sync_check(self):
+        if getattr(self, '_pre_sync_check', None) is not None:
+            check, self._pre_sync_check = self._pre_sync_check, None
+            check()
+
+    def _check_pd(self):
+        """Deferred failure check of the sync-free fixed path (called before results reach the host)."""
+        self._run_pre_sync_check()
+        if getattr(self, '_info_dev', None) is not None:
+            info, self._info_dev = int(self._info_dev.cpu()[0]), None
+            if info != 0:
+                raise np.linalg.LinAlgError("not positive definite: chol(Kuu + beta P) info=%d" % info)
 
     def _gradients(self, P, res, beta, sf2, ell, trA, data_fit, yy, ldk):
         dev = self.device
@@ -343,6 +389,7 @@ class SparseGPRegression(object):
 
     def log_likelihood(self):
         """The VFE bound as a (1, 1) array, like GPy (edrgp/tests/test_edr.py:49-50)."""
+        self._ensure_full()
         return self._log_marginal_likelihood
 
     # -------------------------------------------------------------------------------------------
@@ -407,7 +454,6 @@ class SparseGPRegression(object):
             self._need_grad = False
         self._set_optimizer_array(x_opt)
         self.optimization_runs.append((f_opt, x_opt, info))
-        self._Kcache = None
         return self
 
     def optimize_restarts(self, num_restarts=10, robust=False, verbose=False, **kwargs):
@@ -474,13 +520,21 @@ class SparseGPRegression(object):
         together with whatever else they need).  ``X=None`` uses the training rows.
         """
         Xd = self.X if X is None else ops.pad_even(_as_device(X, self.device))
-        pack = self._grad_pack(self._grad_scale(scale_by_normalizer))
+        scale = self._grad_scale(scale_by_normalizer)
         d = self.input_dim
         if Xd.shape[0] == 0:
             G = torch.empty(0, d, dtype=F64, device=self.device) if want_G else None
             return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
         fused = self.d_even <= 64
-        G, C = ops.grad_gram(Xd, pack, want_G=want_G or (want_C and not fused), want_C=want_C and fused, G_out=G_out)
+        if X is None and fused and getattr(self, '_Kcache', None) is not None:
+            # training rows with their cross-covariance already in HBM: no Kuf recompute, no exp
+            pack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale)
+            G, C = ops.grad_gram_cached(Xd, self._Kcache, pack, float(self.kern.variance), want_G=want_G,
+                                        want_C=want_C, G_out=G_out)
+        else:
+            pack = self._grad_pack(scale)
+            G, C = ops.grad_gram(Xd, pack, want_G=want_G or (want_C and not fused), want_C=want_C and fused,
+                                 G_out=G_out)
         self.kernel_launches += 3
         if want_C and not fused:
             C = ops.syrk(G)
@@ -490,6 +544,7 @@ class SparseGPRegression(object):
                 G = G[:, :d].contiguous()
             if C is not None:
                 C = C[:d, :d].contiguous()
+        self._check_pd()
         return (G if want_G else None), C
 
     def predictive_gradients(self, Xnew, scale_by_normalizer=True):
@@ -503,6 +558,7 @@ class SparseGPRegression(object):
     def woodbury_inv(self):
         """GPy posterior.woodbury_inv = Lm^-T (I - (I + A)^-1) Lm^-1, (m, m) on the device."""
         if self._woodbury_inv is None:
+            self._ensure_full()
             m = self.num_inducing
             eye = torch.eye(m, dtype=F64, device=self.device)
             Bi = eye - _backsub_both_sides(self._solve.LB, eye, 'left')
@@ -512,6 +568,7 @@ class SparseGPRegression(object):
     def predict(self, Xnew, want_variance=True):
         """``GP.predict``: (mean (n, 1), variance (n, 1)) with the likelihood noise added and the
         target normalisation undone."""
+        self._check_pd()
         Xd = ops.pad_even(_as_device(Xnew, self.device))
         n = Xd.shape[0]
         m = self.num_inducing
@@ -544,6 +601,7 @@ class SparseGPRegression(object):
     # persistence: plain arrays (edrgp/gp_model/base.py:224-257 pickles the GPy model)
     # -------------------------------------------------------------------------------------------
     def state_dict(self):
+        self._ensure_full()
         st = {'Z': self.Z.copy(), 'variance': self.kern.variance, 'lengthscale': self.kern.lengthscale.copy(),
               'ARD': self.kern.ARD, 'noise_variance': self.noise_variance, 'input_dim': self.input_dim,
               'alpha': self.alpha.cpu().numpy(), 'num_data': self.num_data,
@@ -590,10 +648,14 @@ class FittedSparseGP(SparseGPRegression):
         sr.LB = torch.as_tensor(np.asarray(state['LB'], dtype=np.float64), device=self.device)
         self._solve = sr
         self._woodbury_inv = None
+        self._alpha_is_direct = True
         self.X = None
 
     def parameters_changed(self):
         raise RuntimeError("a restored model has no training rows; refit to change hyper-parameters")
+
+    def _ensure_full(self):
+        pass
 
     def gradient_gram(self, X=None, **kw):
         if X is None:

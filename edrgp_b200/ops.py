@@ -139,6 +139,34 @@ def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
     return G, C
 
 
+def grad_gram_cached(X, K, pack, sf2, want_G=True, want_C=True, G_out=None):
+    """``grad_gram`` from a stored cross-covariance block K (n, ldk) (entries sf2 exp(-r^2/2), as
+    written by ``kuf``); ``pack`` carries coef = alpha * scale (without sf2).  d <= 64."""
+    lib = _lib.load()
+    d_user = X.shape[1]
+    X = pad_even(X)
+    _need_cuda(X, K)
+    n, d = X.shape
+    if K.shape[0] != n:
+        raise ValueError("K and X row counts differ")
+    G = None
+    if want_G:
+        G = G_out if (G_out is not None and d == d_user) else torch.empty(n, d, dtype=F64, device=X.device)
+    C = ws = None
+    if want_C:
+        C = torch.empty(d, d, dtype=F64, device=X.device)
+        ws = torch.empty(lib.edrgp_grad_gram_workspace_bytes(d) // 8, dtype=F64, device=X.device)
+    with _Timed('grad_gram_cached'):
+        _lib.check(lib.edrgp_grad_gram_cached(_ptr(X), n, d, _ptr(K), K.shape[1], float(sf2), _ptr(pack.buf), pack.m,
+                                              _ptr(G), _ptr(C), _ptr(ws), _stream()), 'edrgp_grad_gram_cached')
+    if d != d_user:
+        if G is not None:
+            G = G[:, :d_user].contiguous()
+        if C is not None:
+            C = C[:d_user, :d_user].contiguous()
+    return G, C
+
+
 def syrk(A, k=None, out=None, accumulate=False):
     """C (+)= A[:, :k]^T A[:, :k] for a tall (n, lda) tensor (lda even)."""
     lib = _lib.load()
@@ -229,6 +257,18 @@ def solve(Kmm, P, b, beta):
     return out
 
 
+def potrf(A):
+    """In-place lower Cholesky of a symmetric (m, m) tensor; returns (A, info) with info a device int32
+    (0, or 1 + index of the first non-positive pivot)."""
+    lib = _lib.load()
+    _need_cuda(A)
+    m = A.shape[0]
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    with _Timed('solve'):
+        _lib.check(lib.edrgp_potrf(_ptr(A), m, A.shape[1], _ptr(info), _stream()), 'edrgp_potrf')
+    return A, info
+
+
 def trsm(L, B, trans=False):
     """In-place triangular solve with a lower factor: L X = B (trans=False) or L^T X = B."""
     lib = _lib.load()
@@ -295,6 +335,22 @@ def weights(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, want_r
                                  float(c_km), _ptr(T), 0 if T is None else T.shape[1], _ptr(rowsum), _ptr(colsum),
                                  int(bool(accumulate)), _ptr(ws), _stream()), 'edrgp_weights')
     return rowsum
+
+
+def count_nonfinite(*tensors):
+    """Device int32 tensor holding the number of NaN / Inf entries over all given tensors."""
+    lib = _lib.load()
+    count = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == F64):
+            raise ValueError("expected CUDA float64 tensors")
+        t = t if t.is_contiguous() else t.contiguous()
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int32, device=t.device)
+        _lib.check(lib.edrgp_count_nonfinite(_ptr(t), t.numel(), _ptr(count), _stream()), 'edrgp_count_nonfinite')
+    return count
 
 
 def standardize(X, mean, scale, out=None):

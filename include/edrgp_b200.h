@@ -88,6 +88,15 @@ size_t edrgp_grad_gram_workspace_bytes(int d);
 int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m,
                     double* G, double* C, void* workspace, void* stream);
 
+/* The same gradients and Gram matrix from a STORED cross-covariance block (the one edrgp_kuf wrote
+ * for the statistics pass: Kfu (n, ldk), entries sf2 exp(-r^2/2)) instead of recomputing it: only
+ * the W Z contraction, the row sums and G^T G remain.  `pack` must have been built with coef = alpha
+ * and coef_scale = scale (the entries already carry sf2); entries exactly equal to sf2 are the
+ * pairs with clipped r^2 == 0 that GPy's _inv_dist drops.  Requires d <= 64.  Same workspace. */
+int edrgp_grad_gram_cached(const double* X, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
+                            const double* pack, int m, double* G, double* C, void* workspace,
+                            void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2 / K5  tall-skinny reductions on the FP64 tensor pipe.  All matrices row-major, leading
  * dimensions even, base pointers 16-byte aligned; results are deterministic (fixed-order split-K
@@ -150,6 +159,12 @@ size_t edrgp_solve_workspace_bytes(int m);
 int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* LB,
                 double* alpha, double* c, double* scalars, int* info, void* workspace, void* stream);
 
+/* Lower Cholesky factor in place (GPy jitchol -> LAPACK dpotrf): A (m, ld) row-major, the strict
+ * upper triangle is left untouched; info[0] = 0 or 1 + index of the first non-positive pivot.
+ * With A = Kuu + beta P its factor LS = Lm LB gives the posterior weights directly,
+ * alpha = LS^-T LS^-1 (beta b): the fixed-hyper-parameter sweep needs nothing else of the chain. */
+int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream);
+
 /* lower-triangular solves with a factor from edrgp_solve: trans = 0: L X = B, 1: L^T X = B;
  * B (m, nrhs) row-major, overwritten.  (GPy dtrtrs.) */
 int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream);
@@ -173,6 +188,9 @@ int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void
  *  edrgp_project:     out (n, k) = X (n, d) V^T, V (k, d) row-major: EDR.transform
  *      (edrgp/edr.py:261-289, edrgp/base.py:462).
  * ------------------------------------------------------------------------------------------- */
+ /* edrgp_count_nonfinite: count[0] += #(NaN or Inf entries) of a dense buffer of `total` doubles:
+ *      the non-finite scan of sklearn's check_X_y / check_array (edrgp/gp_model/base.py:87,105). */
+int edrgp_count_nonfinite(const double* X, int64_t total, unsigned int* count, void* stream);
 size_t edrgp_col_moments_workspace_bytes(int d);
 int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
                       double* out, int accumulate, void* workspace, void* stream);

@@ -111,3 +111,31 @@ def test_full_size_linearity_property():
     assert float(err) < 1e-12
     Cref = G12.T @ G12
     assert float((C12 - Cref).abs().max() / Cref.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("n,d,m", SHAPES)
+def test_cached_kfu_gradients_match_recompute_and_oracle(n, d, m):
+    """The gradient kernel fed from the stored Kfu block (statistics pass) instead of recomputing it."""
+    from edrgp_b200 import ops
+    w = op.make_workload(max(n, m), d, m, seed=n + d + 2)
+    X = w['X'][:n].copy()
+    if n > m:
+        X[:3] = w['Z'][:3]                  # a few coincident pairs: entries equal to the variance are dropped
+    rng = np.random.RandomState(3)
+    alpha = rng.standard_normal(m)
+    sf2, scale = 1.3, 0.7
+    plain = ops.InducingPack(_dev(w['Z']), _dev(w['ell']))
+    K, _ = ops.kuf(_dev(X), plain, sf2)
+    ldk = m + (m & 1)
+    Kbuf = torch.zeros(n, ldk, dtype=torch.float64, device='cuda')
+    Kbuf[:, :m] = K
+    cpack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']), _dev(alpha), scale)
+    G, C = ops.grad_gram_cached(_dev(X), Kbuf, cpack, sf2)
+    rpack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']), _dev(alpha), sf2 * scale)
+    G2, C2 = ops.grad_gram(_dev(X), rpack)
+    Gref = op.gradients_faithful(X, w['Z'], w['ell'], sf2, alpha, scale)
+    assert _relerr(G.cpu().numpy(), Gref) < 1e-11
+    assert _relerr(C.cpu().numpy(), Gref.T.dot(Gref)) < 1e-11
+    assert float((G - G2).abs().max()) <= 1e-13 * float(G2.abs().max())
+    _, C3 = ops.grad_gram_cached(_dev(X), Kbuf, cpack, sf2, want_G=False)
+    assert torch.equal(C, C3)
