@@ -195,6 +195,7 @@ def run_ours(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ['NCCL_DEBUG'] = 'WARN'        # keep NCCL's version banner off stdout: ONE JSON line
         tdist.init_process_group('nccl', device_id=dev)
     n, d, m = args.n, args.d, args.m
     lo, hi = edist.shard_bounds(n, rank, world)
@@ -402,7 +403,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=N_TOTAL)

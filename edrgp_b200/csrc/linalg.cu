@@ -513,7 +513,160 @@ __global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* Ag, int d, do
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi for d <= 128: the fast path of edrgp_eigh.
+// The working matrix W = C V and the accumulated rotations V sit in shared memory, column-major.
+// One warp owns one column pair per step: its lanes hold the two W columns and the two V columns in
+// registers, the three inner products |a|^2, |b|^2, a.b are warp-shuffle reductions, every lane
+// derives the rotation for itself and applies it -- one __syncthreads per round-robin step instead of
+// the three phases of the two-sided kernel.  At convergence the columns of W are orthogonal, i.e. V
+// diagonalises C^2 and hence the symmetric positive semi-definite C; eigenvalues are the Rayleigh
+// quotients v^T C v against the untouched input.
+// ---------------------------------------------------------------------------------------------
+// Cheap FP64 reciprocal / reciprocal square root: FP32 hardware estimate + two Newton steps (rel. error
+// ~1e-15).  All 32 lanes of a warp derive the same rotation, so the IEEE divide / sqrt sequences
+// (~40 FP64 instructions each) were the throughput bound of the solver; the rotation ANGLE only
+// steers convergence -- what must be exact is c^2 + s^2 = 1, which c = rsqrt(1 + t^2), s = t c gives.
+__device__ __forceinline__ double fast_rsqrt(double x) {      // 1e-30 < x < 1e30
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) {        // 1e-30 < |x| < 1e30
+  double r = (double)__frcp_rn((float)x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
+constexpr int EIG_MAXD = 128;
+constexpr int EIG_RPL = EIG_MAXD / 32;      // rows per lane
+
+__global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __restrict__ C, int d,
+                                                               double* __restrict__ evals, double* __restrict__ comps,
+                                                               int max_sweeps, int* __restrict__ sweeps_out) {
+  extern __shared__ double sh[];
+  double* W = sh;                       // [d][d] column-major: W[c * d + r]
+  double* V = sh + (size_t)d * d;
+  __shared__ int rotated;
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int dd = d + (d & 1), np = dd / 2;
+  for (int i = tid; i < d * d; i += nt) {
+    const int c = i / d, r = i - c * d;
+    W[i] = C[(int64_t)r * d + c];
+    V[i] = r == c ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int step = 0; step < dd - 1; ++step) {
+      for (int k = warp; k < np; k += nwarps) {
+        const int a0 = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
+        const int b0 = (step + dd - 1 - k) % (dd - 1);
+        const int p = min(a0, b0), q = max(a0, b0);
+        if (q >= d) continue;                       // the bye of an odd dimension
+        double wa[EIG_RPL], wb[EIG_RPL];
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+        for (int e = 0; e < EIG_RPL; ++e) {
+          const int r = lane + 32 * e;
+          wa[e] = r < d ? W[p * d + r] : 0.0;
+          wb[e] = r < d ? W[q * d + r] : 0.0;
+          alpha = fma(wa[e], wa[e], alpha); beta = fma(wb[e], wb[e], beta); gamma = fma(wa[e], wb[e], gamma);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+          beta += __shfl_xor_sync(0xffffffffu, beta, o);
+          gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+        }
+        if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) continue;   // warp-uniform
+        double tt;
+        const double ag = fabs(gamma), diff = beta - alpha;
+        if (ag > 1e-30 && ag < 1e30 && fabs(diff) < 1e15 * ag) {
+          const double zeta = diff * fast_rcp(2.0 * gamma);
+          const double w = fma(zeta, zeta, 1.0);                    // < 1e30
+          const double den = fabs(zeta) + w * fast_rsqrt(w);       // |zeta| + sqrt(1 + zeta^2) >= 1
+          tt = (zeta >= 0.0 ? 1.0 : -1.0) * fast_rcp(den);
+        } else {                                                    // out of the estimates' range: IEEE path
+          const double zeta = diff / (2.0 * gamma);
+          tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        }
+        const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
+        if (lane == 0) rotated = 1;
+#pragma unroll
+        for (int e = 0; e < EIG_RPL; ++e) {
+          const int r = lane + 32 * e;
+          if (r < d) {
+            W[p * d + r] = c * wa[e] - s * wb[e];
+            W[q * d + r] = s * wa[e] + c * wb[e];
+            const double va = V[p * d + r], vb = V[q * d + r];
+            V[p * d + r] = c * va - s * vb;
+            V[q * d + r] = s * va + c * vb;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!rotated) break;
+    __syncthreads();
+  }
+  if (tid == 0 && sweeps_out) *sweeps_out = sweep;
+  // eigenvalues: Rayleigh quotients against the input (one warp per vector), kept in W's first column slots
+  double* lam = W;                      // reuse: [d]
+  __syncthreads();
+  double mine[ (EIG_MAXD + 31) / 32 ];
+  int cnt = 0;
+  for (int i = warp; i < d; i += nwarps, ++cnt) {
+    double acc = 0.0;
+    for (int r = lane; r < d; r += 32) {
+      double cv = 0.0;
+      for (int k = 0; k < d; ++k) cv = fma(C[(int64_t)r * d + k], V[i * d + k], cv);
+      acc = fma(V[i * d + r], cv, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mine[cnt] = acc;
+  }
+  __syncthreads();                      // every warp is done reading W before it is reused
+  cnt = 0;
+  for (int i = warp; i < d; i += nwarps, ++cnt)
+    if (lane == 0) lam[i] = mine[cnt];
+  __syncthreads();
+  // sort descending by rank counting, write components as rows with a fixed sign
+  for (int i = tid; i < d; i += nt) {
+    const double li = lam[i];
+    int rank = 0;
+    for (int j = 0; j < d; ++j) {
+      const double lj = lam[j];
+      rank += (lj > li) || (lj == li && j < i);
+    }
+    evals[rank] = li;
+    double best = 0.0;
+    for (int r = 0; r < d; ++r) {
+      const double v = V[i * d + r];
+      if (fabs(v) > fabs(best)) best = v;
+    }
+    const double sgn = best < 0.0 ? -1.0 : 1.0;
+    for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[i * d + r];
+  }
+}
+
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
+  if (d <= 117) {       // two d x d matrices in shared memory
+    const size_t smem1 = (size_t)2 * d * d * sizeof(double);
+    if (smem1 > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      if (e != cudaSuccess) return e;
+    }
+    jacobi_onesided_kernel<<<1, 1024, smem1, st>>>(A, d, evals, comps, 60, sweeps); count_launch();
+    return cudaGetLastError();
+  }
+
   const int dd = d + (d & 1), np = dd / 2;
   size_t smem = (size_t)(3 * np + (np & 1)) * sizeof(double);
   const size_t mats = (size_t)2 * d * d * sizeof(double);

@@ -6,11 +6,26 @@ Per fixed-hyper-parameter sweep exactly two all-reduces run on the data path:
 {P (m x m), b (m), y^T y, n} after the statistics pass and {C (d x d)} after the gradient pass
 (plus 2d / 2 doubles for the scaler / target normaliser).  Everything else is rank-local.
 """
+import contextlib
+
 import torch
+
+_LOCAL_ONLY = False
+
+
+@contextlib.contextmanager
+def local_only():
+    """Treat this process as a single-rank job inside the block (reference runs in multi-rank tests)."""
+    global _LOCAL_ONLY
+    prev, _LOCAL_ONLY = _LOCAL_ONLY, True
+    try:
+        yield
+    finally:
+        _LOCAL_ONLY = prev
 
 
 def is_distributed():
-    return torch.distributed.is_available() and torch.distributed.is_initialized() \
+    return (not _LOCAL_ONLY) and torch.distributed.is_available() and torch.distributed.is_initialized() \
         and torch.distributed.get_world_size() > 1
 
 
