@@ -23,16 +23,17 @@ SIGNATURES = {
     'edrgp_fp64_probe': (_int, [_c_dp, _int, ctypes.POINTER(ctypes.c_double), _c_dp]),
     'edrgp_pack_bytes': (_sz, [_int, _int]),
     'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
-    'edrgp_kuf': (_int, [_c_dp, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_kuf': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
     'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
-    'edrgp_grad_gram_cached': (_int, [_c_dp, _i64, _int, _c_dp, _i64, _dbl, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_grad_gram_cached': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _dbl, _c_dp, _int, _c_dp, _i64, _c_dp,
+                                      _c_dp, _c_dp]),
     'edrgp_syrk_workspace_bytes': (_sz, [_i64, _int]),
     'edrgp_syrk': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
     'edrgp_inducing_stats': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _c_dp, _i64, _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_gemm_tn_workspace_bytes': (_sz, [_i64, _int, _int]),
     'edrgp_gemm_tn': (_int, [_c_dp, _i64, _int, _c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
-    'edrgp_kmm': (_int, [_c_dp, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _c_dp]),
+    'edrgp_kmm': (_int, [_c_dp, _i64, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _int, _int, _c_dp]),
     'edrgp_solve_workspace_bytes': (_sz, [_int]),
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_potrf': (_int, [_c_dp, _int, _i64, _c_dp, _c_dp]),

@@ -71,15 +71,17 @@ static int check_x(const char* who, const double* X, int64_t n, int d, const dou
   return EDRGP_OK;
 }
 
-int edrgp_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu, int64_t ldk,
-              const double* y, double* b, double* mu, void* stream) {
+int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
+              int64_t ldk, int multiply, const double* y, double* b, double* mu, void* stream) {
   int rc = check_x("kuf", X, n, d, pack, m);
   if (rc) return rc;
+  if (ldx < d || (ldx & 1)) return fail(EDRGP_ERR_ARG, "kuf: ldx must be even and >= d");
+  if (multiply && !Kfu) return fail(EDRGP_ERR_ARG, "kuf: multiply needs the Kfu buffer");
   if (Kfu && (ldk < m || (ldk & 1) || !aligned16(Kfu))) return fail(EDRGP_ERR_ARG, "kuf: ldk must be even, >= m; Kfu 16-byte aligned");
   if ((y == nullptr) != (b == nullptr)) return fail(EDRGP_ERR_ARG, "kuf: y and b go together");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kuf: no CUDA device");
-  cudaError_t e = edrgp::launch_kuf(X, n, d, pack, m, sf2, Kfu, ldk, y, b, mu, sms, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_kuf(X, ldx, n, d, pack, m, sf2, Kfu, ldk, multiply, y, b, mu, sms, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf");
 }
 
@@ -104,10 +106,13 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_gram");
 }
 
-int edrgp_grad_gram_cached(const double* X, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
-                            const double* pack, int m, double* G, double* C, void* workspace, void* stream) {
+int edrgp_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
+                            const double* pack, int m, double* G, int64_t ldg, double* C, void* workspace,
+                            void* stream) {
   int rc = check_x("grad_gram_cached", X, n, d, pack, m);
   if (rc) return rc;
+  if (ldx < d || (ldx & 1)) return fail(EDRGP_ERR_ARG, "grad_gram_cached: ldx must be even and >= d");
+  if (G && (ldg < d || (ldg & 1))) return fail(EDRGP_ERR_ARG, "grad_gram_cached: ldg must be even and >= d");
   if (!Kfu || ldk < m || (ldk & 1) || !aligned16(Kfu))
     return fail(EDRGP_ERR_ARG, "grad_gram_cached: Kfu must be 16-byte aligned with an even leading dimension >= m");
   if (G && !aligned16(G)) return fail(EDRGP_ERR_ARG, "grad_gram_cached: G must be 16-byte aligned");
@@ -116,8 +121,8 @@ int edrgp_grad_gram_cached(const double* X, int64_t n, int d, const double* Kfu,
     return fail(EDRGP_ERR_UNSUPPORTED, "grad_gram_cached: needs d <= 64; use edrgp_grad_gram");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "grad_gram_cached: no CUDA device");
-  cudaError_t e = edrgp::launch_grad_gram_cached(X, n, d, Kfu, ldk, sf2, pack, m, G, C, (double*)workspace, sms,
-                                                 (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_grad_gram_cached(X, ldx, n, d, Kfu, ldk, sf2, pack, m, G, ldg, C, (double*)workspace,
+                                                 sms, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_gram_cached");
 }
 
@@ -194,16 +199,18 @@ int edrgp_weights(const double* Kfu, int64_t n, int m, int64_t ldk, const double
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "weights");
 }
 
-int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, double jitter, double* Kmm,
-              int64_t ldk, void* stream) {
+int edrgp_kmm(const double* Zp, int64_t ldz, const double* pack, int m, int d, double sf2, double jitter,
+              double* Kmm, int64_t ldk, int multiply, int finish, void* stream) {
   int rc = check_x("kmm", Zp, m, d, pack, m);
   if (rc) return rc;
+  if (ldz < d || (ldz & 1)) return fail(EDRGP_ERR_ARG, "kmm: ldz must be even and >= d");
   if (!Kmm || ldk < m || (ldk & 1) || !aligned16(Kmm))
     return fail(EDRGP_ERR_ARG, "kmm: Kmm must be 16-byte aligned with an even leading dimension >= m");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kmm: no CUDA device");
-  cudaError_t e = edrgp::launch_kuf(Zp, m, d, pack, m, sf2, Kmm, ldk, nullptr, nullptr, nullptr, sms, (cudaStream_t)stream);
-  if (e == cudaSuccess) e = edrgp::launch_kmm_fix(Kmm, m, ldk, sf2, jitter, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_kuf(Zp, ldz, m, d, pack, m, sf2, Kmm, ldk, multiply, nullptr, nullptr, nullptr, sms,
+                                    (cudaStream_t)stream);
+  if (e == cudaSuccess && finish) e = edrgp::launch_kmm_fix(Kmm, m, ldk, sf2, jitter, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kmm");
 }
 

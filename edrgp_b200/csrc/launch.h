@@ -13,11 +13,12 @@ cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, 
 bool grad_gram_fused(int d);
 cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pack, int m, double* G, double* C,
                              double* Cpart, int sms, cudaStream_t st);
-cudaError_t launch_grad_gram_cached(const double* X, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
-                                    const double* pack, int m, double* G, double* C, double* Cpart, int sms,
-                                    cudaStream_t st);
-cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
-                       int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st);
+cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int d, const double* Kin, int64_t ldk,
+                                    double sf2, const double* pack, int m, double* G, int64_t ldg, double* C,
+                                    double* Cpart, int sms, cudaStream_t st);
+cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
+                       double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
+                       cudaStream_t st);
 
 // C (+)= A^T B (sym: B = A, upper tiles mirrored; optional y: bout[0..ka) (+)= A^T y, bout[ka] (+)= y^T y)
 size_t gemm_tn_workspace_bytes(int64_t n, int ka, int kb, int sym, int sms);

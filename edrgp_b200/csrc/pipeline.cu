@@ -96,6 +96,9 @@ struct PipeParams {
   double* b;
   double* mu;       // kuf only: mu_i = sum_j K_ij coef_j (posterior mean when coef = alpha)
   const double* Kin;   // cached-Kfu gradient kernel: stored entries (n, ldk), read instead of recomputed
+  int64_t ldx;         // leading dimension of X (>= d): a feature block of a wider matrix can be streamed
+  int64_t ldg;         // leading dimension of G
+  int mul;             // kuf: multiply the entries already in Kfu by this block's factor (feature-chunked d > 128)
 };
 
 // Producer warp: streams the X row tiles and the inducing tiles of every row tile of this CTA.
@@ -114,7 +117,7 @@ __device__ __forceinline__ void producer_loop(const PipeParams& p, double* xbuf,
     __syncwarp();
     double* dst = xbuf + (size_t)xs * BM * L::S;
     for (int r = lane; r < rows; r += 32)
-      bulk_g2s(dst + (size_t)r * L::S, p.X + (row0 + r) * p.d, row_bytes, &xfull[xs]);
+      bulk_g2s(dst + (size_t)r * L::S, p.X + (row0 + r) * p.ldx, row_bytes, &xfull[xs]);
     if (++xs == XS) { xs = 0; xph ^= 1; }
   };
   int64_t tile = blockIdx.x;
@@ -164,7 +167,7 @@ __device__ __forceinline__ void producer_loop_cached(const PipeParams& p, double
         if (lane == 0) mbar_arrive_expect_tx(&xfull[0], (uint32_t)rows * row_bytes);
         __syncwarp();
         for (int r = lane; r < rows; r += 32)
-          bulk_g2s(xbuf + (size_t)r * L::S, p.X + (row0 + r) * p.d, row_bytes, &xfull[0]);
+          bulk_g2s(xbuf + (size_t)r * L::S, p.X + (row0 + r) * p.ldx, row_bytes, &xfull[0]);
         xph ^= 1;
       }
     }
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
         const int r = i / half, c2 = i - r * half;
         const int64_t row = row0 + r0 + r;
         if (row < p.n)
-          *reinterpret_cast<double2*>(p.G + row * p.d + 2 * c2) = *reinterpret_cast<const double2*>(xw + r * S + 2 * c2);
+          *reinterpret_cast<double2*>(p.G + row * p.ldg + 2 * c2) = *reinterpret_cast<const double2*>(xw + r * S + 2 * c2);
       }
     }
     if (FUSE_GRAM) {
@@ -500,8 +503,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         // entries are stored without the pack coefficient; only the row sums mu carry it
-        const double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)), k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0));
-        const double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)), k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0));
+        double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)), k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0));
+        double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)), k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0));
+        if (p.mul && j < p.m) {
+          // feature-chunked evaluation: exp(-r^2/2) factorises over blocks of features
+          if (v0) { const double2 o = *reinterpret_cast<const double2*>(p.Kfu + ra * p.ldk + j); k00 *= o.x; k01 *= o.y; }
+          if (v1) { const double2 o = *reinterpret_cast<const double2*>(p.Kfu + rb * p.ldk + j); k10 *= o.x; k11 *= o.y; }
+        }
         mu0 += fma(k00, c.x, k01 * c.y); mu1 += fma(k10, c.x, k11 * c.y);
         if (p.Kfu != nullptr) {
           // ldk even (host guarantees) and j even -> 16-byte stores
@@ -595,6 +603,7 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
   PipeParams p{};
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
   p.ntiles = (n + BM - 1) / BM; p.G = G; p.Cpart = C ? Cpart : nullptr; p.m = m;
+  p.ldx = d; p.ldg = d;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
   const int dp = padded_dim(d);
   cudaError_t e;
@@ -617,13 +626,13 @@ cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pa
   return e;
 }
 
-cudaError_t launch_grad_gram_cached(const double* X, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
-                                    const double* pack, int m, double* G, double* C, double* Cpart, int sms,
-                                    cudaStream_t st) {
+cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int d, const double* Kin, int64_t ldk,
+                                    double sf2, const double* pack, int m, double* G, int64_t ldg, double* C,
+                                    double* Cpart, int sms, cudaStream_t st) {
   PipeParams p{};
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
   p.ntiles = (n + BM - 1) / BM; p.G = G; p.Cpart = C ? Cpart : nullptr; p.m = m;
-  p.Kin = Kin; p.ldk = ldk; p.sf2 = sf2;
+  p.Kin = Kin; p.ldk = ldk; p.sf2 = sf2; p.ldx = ldx; p.ldg = ldg;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
   const int dp = padded_dim(d);
   cudaError_t e;
@@ -642,9 +651,11 @@ cudaError_t launch_grad_gram_cached(const double* X, int64_t n, int d, const dou
   return e;
 }
 
-cudaError_t launch_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
-                       int64_t ldk, const double* y, double* b, double* mu, int sms, cudaStream_t st) {
+cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
+                       double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
+                       cudaStream_t st) {
   PipeParams p{};
+  p.ldx = ldx; p.ldg = d; p.mul = mul;
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
   p.ntiles = (n + BM - 1) / BM; p.sf2 = sf2; p.Kfu = Kfu; p.ldk = ldk; p.m = m; p.y = y; p.b = b; p.mu = mu;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);

@@ -525,20 +525,47 @@ class SparseGPRegression(object):
         if Xd.shape[0] == 0:
             G = torch.empty(0, d, dtype=F64, device=self.device) if want_G else None
             return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
-        fused = self.d_even <= 64
-        if X is None and fused and getattr(self, '_Kcache', None) is not None:
+        use_cache = X is None and getattr(self, '_Kcache', None) is not None
+        sf2 = float(self.kern.variance)
+        if use_cache and self.d_even <= 64:
             # training rows with their cross-covariance already in HBM: no Kuf recompute, no exp
-            pack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale)
-            G, C = ops.grad_gram_cached(Xd, self._Kcache, pack, float(self.kern.variance), want_G=want_G,
-                                        want_C=want_C, G_out=G_out)
-        else:
+            pack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale, block=64)
+            G, C = ops.grad_gram_cached(Xd, self._Kcache, pack, sf2, want_G=want_G, want_C=want_C, G_out=G_out)
+            self.kernel_launches += 3
+        elif not use_cache and self.d_even <= 128:
+            fused = self.d_even <= 64
             pack = self._grad_pack(scale)
             G, C = ops.grad_gram(Xd, pack, want_G=want_G or (want_C and not fused), want_C=want_C and fused,
                                  G_out=G_out)
-        self.kernel_launches += 3
-        if want_C and not fused:
-            C = ops.syrk(G)
-            self.kernel_launches += 2
+            self.kernel_launches += 3
+            if want_C and not fused:
+                C = ops.syrk(G)
+                self.kernel_launches += 2
+        else:
+            # any width: row blocks of the stored (or freshly written) Kfu feed the cached-gradient
+            # kernel one 64-feature block at a time; the Gram matrix accumulates on the DMMA reduction
+            gpack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale, block=64)
+            kpack = None if use_cache else ops.InducingPack(self._Z_dev, self._ell_dev)
+            nrow = Xd.shape[0]
+            rows = min(self.chunk_rows, nrow)
+            ldk = self.num_inducing + (self.num_inducing & 1)
+            Kb = None if use_cache else torch.empty(rows, ldk, dtype=F64, device=self.device)
+            G = (G_out if (G_out is not None and G_out.shape[1] == self.d_even) else
+                 torch.empty(nrow, self.d_even, dtype=F64, device=self.device)) if want_G else None
+            Gb = None if want_G else torch.empty(rows, self.d_even, dtype=F64, device=self.device)
+            C = torch.zeros(self.d_even, self.d_even, dtype=F64, device=self.device) if want_C else None
+            for i, s0 in enumerate(range(0, nrow, rows)):
+                e0 = min(nrow, s0 + rows)
+                if use_cache:
+                    Kc = self._Kcache[s0:e0]
+                else:
+                    Kc = Kb[:e0 - s0]
+                    ops.kuf(Xd[s0:e0], kpack, sf2, out=Kc)
+                Gc = G[s0:e0] if want_G else Gb[:e0 - s0]
+                ops.grad_gram_cached(Xd[s0:e0], Kc, gpack, sf2, want_G=True, want_C=False, G_out=Gc)
+                if want_C:
+                    ops.syrk(Gc, out=C, accumulate=i > 0)
+                self.kernel_launches += 6
         if self.d_even != d:
             if G is not None:
                 G = G[:, :d].contiguous()
@@ -546,6 +573,8 @@ class SparseGPRegression(object):
                 C = C[:d, :d].contiguous()
         self._check_pd()
         return (G if want_G else None), C
+
+
 
     def predictive_gradients(self, Xnew, scale_by_normalizer=True):
         """``GP.predictive_gradients``: (mean Jacobian (n, d, 1), None).  edr-gp keeps only

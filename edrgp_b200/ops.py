@@ -68,10 +68,14 @@ def pad_even(X):
 
 
 class InducingPack(object):
-    """Device-resident tiled copy of (Z / l^2, -|z/l|^2 / 2, coef): see edrgp_pack_inducing."""
+    """Device-resident tiled copy of (Z / l^2, -|z/l|^2 / 2, coef): see edrgp_pack_inducing.
 
-    def __init__(self, Z, ell, coef=None, coef_scale=1.0):
-        lib = _lib.load()
+    ``block`` features per kernel call (128 for the cross-covariance kernels, 64 for the cached
+    gradient kernel): a wider Z is packed as several feature blocks, each with its own buffer;
+    exp(-r^2/2) factorises over the blocks and the gradient of a feature only needs its own block.
+    """
+
+    def __init__(self, Z, ell, coef=None, coef_scale=1.0, block=128):
         _need_cuda(Z, ell, coef)
         self.m, d = Z.shape
         if d % 2:
@@ -79,34 +83,55 @@ class InducingPack(object):
             ell = torch.cat([ell, torch.ones(1, dtype=F64, device=ell.device)])
         self.d = Z.shape[1]
         self.Z, self.ell = Z, ell
-        nbytes = lib.edrgp_pack_bytes(self.m, self.d)
-        self.buf = torch.empty(nbytes // 8, dtype=F64, device=Z.device)
+        self.block = int(block)
+        self.blocks = []                      # (first feature, width, Z block, ell block, buffer)
+        lib = _lib.load()
+        for c0 in range(0, self.d, self.block):
+            dc = min(self.block, self.d - c0)
+            if self.d <= self.block:
+                Zb, eb = Z, ell
+            else:
+                Zb, eb = Z[:, c0:c0 + dc].contiguous(), ell[c0:c0 + dc].contiguous()
+            buf = torch.empty(lib.edrgp_pack_bytes(self.m, dc) // 8, dtype=F64, device=Z.device)
+            self.blocks.append((c0, dc, Zb, eb, buf))
+        self.buf = self.blocks[0][4]
         self.set_coef(coef, coef_scale)
 
     def set_coef(self, coef, coef_scale=1.0):
         lib = _lib.load()
         _need_cuda(coef)
-        _lib.check(lib.edrgp_pack_inducing(_ptr(self.Z), _ptr(self.ell), _ptr(coef), float(coef_scale),
-                                           self.m, self.d, _ptr(self.buf), _stream()), 'edrgp_pack_inducing')
+        for c0, dc, Zb, eb, buf in self.blocks:
+            _lib.check(lib.edrgp_pack_inducing(_ptr(Zb), _ptr(eb), _ptr(coef), float(coef_scale), self.m, dc,
+                                               _ptr(buf), _stream()), 'edrgp_pack_inducing')
         return self
 
 
 def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
     """Kfu (n, m) and, if y is given, b = Kfu^T y.  want_mu: returns (K, b, mu) with
-    mu = Kfu @ coef (the coefficients stored in the pack)."""
+    mu = Kfu @ coef (the coefficients stored in the pack).  Any feature count: more than 128
+    features are evaluated block by block into the same buffer (multiply mode)."""
     lib = _lib.load()
     X = pad_even(X)
     _need_cuda(X, y)
-    n = X.shape[0]
+    n, ldx = X.shape
+    if ldx != pack.d:
+        raise ValueError("X has %d features, the pack %d" % (ldx, pack.d))
     K = None
     ldk = pack.m + (pack.m & 1)
-    if want_K:
+    nblk = len(pack.blocks)
+    if want_K or nblk > 1:
         K = out if out is not None else torch.empty(n, ldk, dtype=F64, device=X.device)
     b = torch.zeros(pack.m, dtype=F64, device=X.device) if y is not None else None
     mu = torch.empty(n, dtype=F64, device=X.device) if want_mu else None
     with _Timed('kuf'):
-        _lib.check(lib.edrgp_kuf(_ptr(X), n, X.shape[1], _ptr(pack.buf), pack.m, float(sf2), _ptr(K), ldk,
-                                 _ptr(y), _ptr(b), _ptr(mu), _stream()), 'edrgp_kuf')
+        for i, (c0, dc, _, _, buf) in enumerate(pack.blocks):
+            last = i == nblk - 1
+            _lib.check(lib.edrgp_kuf(X.data_ptr() + 8 * c0, ldx, n, dc, _ptr(buf), pack.m,
+                                     float(sf2) if last else 1.0, _ptr(K), ldk, int(i > 0),
+                                     _ptr(y) if last else 0, _ptr(b) if last else 0, _ptr(mu) if last else 0,
+                                     _stream()), 'edrgp_kuf')
+    if not want_K:
+        K = None
     if K is not None and ldk != pack.m:
         K = K[:, :pack.m]
     if want_mu:
@@ -141,7 +166,9 @@ def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
 
 def grad_gram_cached(X, K, pack, sf2, want_G=True, want_C=True, G_out=None):
     """``grad_gram`` from a stored cross-covariance block K (n, ldk) (entries sf2 exp(-r^2/2), as
-    written by ``kuf``); ``pack`` carries coef = alpha * scale (without sf2).  d <= 64."""
+    written by ``kuf``); ``pack`` carries coef = alpha * scale (without sf2) in feature blocks of at
+    most 64.  One block: G and C come from the fused kernel.  Several blocks (d > 64): every block
+    writes its columns of G and C = G^T G runs on the symmetric reduction."""
     lib = _lib.load()
     d_user = X.shape[1]
     X = pad_even(X)
@@ -149,22 +176,29 @@ def grad_gram_cached(X, K, pack, sf2, want_G=True, want_C=True, G_out=None):
     n, d = X.shape
     if K.shape[0] != n:
         raise ValueError("K and X row counts differ")
+    if d != pack.d or max(dc for _, dc, _, _, _ in pack.blocks) > 64:
+        raise ValueError("the pack must hold the same features in blocks of at most 64")
+    single = len(pack.blocks) == 1
     G = None
-    if want_G:
+    if want_G or not single:
         G = G_out if (G_out is not None and d == d_user) else torch.empty(n, d, dtype=F64, device=X.device)
     C = ws = None
-    if want_C:
+    if want_C and single:
         C = torch.empty(d, d, dtype=F64, device=X.device)
         ws = torch.empty(lib.edrgp_grad_gram_workspace_bytes(d) // 8, dtype=F64, device=X.device)
     with _Timed('grad_gram_cached'):
-        _lib.check(lib.edrgp_grad_gram_cached(_ptr(X), n, d, _ptr(K), K.shape[1], float(sf2), _ptr(pack.buf), pack.m,
-                                              _ptr(G), _ptr(C), _ptr(ws), _stream()), 'edrgp_grad_gram_cached')
+        for c0, dc, _, _, buf in pack.blocks:
+            _lib.check(lib.edrgp_grad_gram_cached(X.data_ptr() + 8 * c0, d, n, dc, _ptr(K), K.shape[1], float(sf2),
+                                                  _ptr(buf), pack.m, 0 if G is None else G.data_ptr() + 8 * c0, d,
+                                                  _ptr(C), _ptr(ws), _stream()), 'edrgp_grad_gram_cached')
+    if want_C and not single:
+        C = syrk(G)
     if d != d_user:
         if G is not None:
             G = G[:, :d_user].contiguous()
         if C is not None:
             C = C[:d_user, :d_user].contiguous()
-    return G, C
+    return (G if want_G else None), C
 
 
 def syrk(A, k=None, out=None, accumulate=False):
@@ -227,8 +261,12 @@ def kmm(pack, sf2, jitter=1e-8):
     m = pack.m
     ldk = m + (m & 1)
     K = torch.empty(m, ldk, dtype=F64, device=pack.buf.device)
-    _lib.check(lib.edrgp_kmm(_ptr(pack.Z), _ptr(pack.buf), m, pack.d, float(sf2), float(jitter), _ptr(K), ldk,
-                             _stream()), 'edrgp_kmm')
+    nblk = len(pack.blocks)
+    for i, (c0, dc, _, _, buf) in enumerate(pack.blocks):
+        # the variance rides on the last block: its call also finishes the diagonal with sf2 + jitter
+        _lib.check(lib.edrgp_kmm(pack.Z.data_ptr() + 8 * c0, pack.d, _ptr(buf), m, dc,
+                                 float(sf2) if i == nblk - 1 else 1.0, float(jitter), _ptr(K), ldk, int(i > 0),
+                                 int(i == nblk - 1), _stream()), 'edrgp_kmm')
     return K if ldk == m else K[:, :m].contiguous()
 
 

@@ -69,9 +69,15 @@ int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, 
  * route is edrgp_inducing_stats) and writes mu_i = sum_j Kfu_ij coef_j (mu may be NULL): with
  * coef = alpha in the pack this is the posterior mean K(x, Z) alpha of GPy Posterior._raw_predict
  * (edrgp/gp_model/base.py:187).  The stored entries never carry the pack coefficient.
+ * X is (n, ldx) with ldx even, >= d: only the first d columns from the pointer are used, so a block
+ * of features of a wider matrix can be passed (d <= 128 per call).  multiply != 0 multiplies the
+ * entries already in Kfu by this call's factor: exp(-r^2/2) factorises over feature blocks, which is
+ * how d > 128 is evaluated (every block but the first with multiply = 1; the variance sf2, y, b
+ * and mu only on the last block, the others with sf2 = 1).
  * ------------------------------------------------------------------------------------------- */
-int edrgp_kuf(const double* X, int64_t n, int d, const double* pack, int m, double sf2,
-              double* Kfu, int64_t ldk, const double* y, double* b, double* mu, void* stream);
+int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
+              double* Kfu, int64_t ldk, int multiply, const double* y, double* b, double* mu,
+              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1+K4+K5 fused  posterior-mean gradients and their outer product.
@@ -92,10 +98,13 @@ int edrgp_grad_gram(const double* X, int64_t n, int d, const double* pack, int m
  * for the statistics pass: Kfu (n, ldk), entries sf2 exp(-r^2/2)) instead of recomputing it: only
  * the W Z contraction, the row sums and G^T G remain.  `pack` must have been built with coef = alpha
  * and coef_scale = scale (the entries already carry sf2); entries exactly equal to sf2 are the
- * pairs with clipped r^2 == 0 that GPy's _inv_dist drops.  Requires d <= 64.  Same workspace. */
-int edrgp_grad_gram_cached(const double* X, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
-                            const double* pack, int m, double* G, double* C, void* workspace,
-                            void* stream);
+ * pairs with clipped r^2 == 0 that GPy's _inv_dist drops.  Requires d <= 64 per call: X (n, ldx) and
+ * G (n, ldg) may be feature blocks of wider matrices (the gradient of feature q only needs the full
+ * Kfu and column q of X and Z), which is how d > 64 is covered block by block; C is then the
+ * block's own d x d Gram matrix (use edrgp_syrk on the assembled G for the full one).  Same workspace. */
+int edrgp_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk,
+                            double sf2, const double* pack, int m, double* G, int64_t ldg, double* C,
+                            void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2 / K5  tall-skinny reductions on the FP64 tensor pipe.  All matrices row-major, leading
@@ -139,10 +148,12 @@ int edrgp_weights(const double* Kfu, int64_t n, int m, int64_t ldk, const double
  * Kuu = K(Z, Z) with the diagonal forced to sf2 + jitter (GPy Stationary._unscaled_dist zeroes the
  * diagonal distance; VarDTC adds const_jitter = 1e-8).  Zp is the (m, d) inducing matrix with d
  * even (as stored by the host pack), `pack` built with coef = NULL.  Kmm is (m, ldk) row-major
- * with ldk even and >= m (rows are written with 16-byte stores).
+ * with ldk even and >= m (rows are written with 16-byte stores).  Zp is (m, ldz); like edrgp_kuf it
+ * can be called per feature block (multiply), with finish != 0 on the last block only (diagonal,
+ * jitter and symmetrisation).
  * ------------------------------------------------------------------------------------------- */
-int edrgp_kmm(const double* Zp, const double* pack, int m, int d, double sf2, double jitter,
-              double* Kmm, int64_t ldk, void* stream);
+int edrgp_kmm(const double* Zp, int64_t ldz, const double* pack, int m, int d, double sf2, double jitter,
+              double* Kmm, int64_t ldk, int multiply, int finish, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  the m x m solve chain of GPy VarDTC.inference, driven by the n-reduced statistics

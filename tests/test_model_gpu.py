@@ -168,3 +168,42 @@ def test_transformer_matches_svd():
 def S2_all(G):
     s = np.linalg.svd(G, compute_uv=False) ** 2
     return s / s.sum()
+
+
+@pytest.mark.parametrize("n,d,m", [(1500, 512, 96),      # BASELINE config 4 shape (d=512, m=1024) at reduced n, m
+                                   (1200, 128, 160),     # BASELINE config 5 shape (d=128, m=2048) at reduced n, m
+                                   (900, 200, 70),       # ragged feature blocks: 128 + 72 and 64 + 64 + 64 + 8
+                                   (700, 97, 33)])       # odd d between 64 and 128
+def test_wide_inputs_feature_blocked(n, d, m):
+    """d > 64 / d > 128: the cross-covariance is evaluated as a product over feature blocks and the
+    gradients block by block from the stored Kfu; everything must still match the oracle."""
+    w = op.make_workload(n, d, m, seed=d, k_true=2)
+    ref = _oracle_model(w, True)
+    mod = _device_model(w, True, chunk_rows=1024)
+    ll, ll_ref = mod.log_likelihood(), ref.log_likelihood()
+    assert abs(ll[0, 0] - ll_ref[0, 0]) < 1e-9 * abs(ll_ref[0, 0])
+    # training-row gradients (stored Kfu) and their Gram matrix
+    G, C = mod.gradient_gram(want_G=True, want_C=True)
+    G_ref = ref.predictive_gradients(w['X'])[0][:, :, 0]
+    assert G.shape == (n, d) and C.shape == (d, d)
+    assert _relerr(G.cpu().numpy(), G_ref) < 1e-8
+    assert _relerr(C.cpu().numpy(), G_ref.T.dot(G_ref)) < 1e-8
+    _, C2 = mod.gradient_gram(want_G=False, want_C=True)
+    assert _relerr(C2.cpu().numpy(), G_ref.T.dot(G_ref)) < 1e-8
+    # new rows (no stored Kfu)
+    Xnew = np.random.RandomState(2).standard_normal((257, d))
+    assert _relerr(mod.predictive_gradients(Xnew)[0], ref.predictive_gradients(Xnew)[0]) < 1e-8
+    mu, var = mod.predict(Xnew)
+    mu_ref, var_ref = ref.predict(Xnew)
+    assert _relerr(mu, mu_ref) < 1e-8 and _relerr(var, var_ref) < 1e-8
+    # hyper-parameter gradients through the same blocks
+    mod._need_grad = True
+    mod.parameters_changed()
+    mod._need_grad = False
+    assert _relerr(mod.grad_lengthscale, ref.grad_lengthscale) < 1e-7
+    assert _relerr(mod.grad_Z, ref.grad_Z) < 1e-7
+    # EDR directions from the Gram matrix
+    import edrgp_b200 as eb
+    tr = eb.GramEighTransformer(n_components=2).fit_gram(C, n)
+    cref, _, _ = op.edr_from_gram(G_ref.T.dot(G_ref), 2)
+    assert op.principal_angle(tr.components_, cref) < 1e-6
