@@ -38,6 +38,7 @@ SIGNATURES = {
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_potrf': (_int, [_c_dp, _int, _i64, _c_dp, _c_dp]),
     'edrgp_trsm': (_int, [_c_dp, _int, _c_dp, _int, _int, _c_dp]),
+    'edrgp_eigh_workspace_bytes': (_sz, [_int]),
     'edrgp_eigh': (_int, [_c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_count_nonfinite': (_int, [_c_dp, _i64, _c_dp, _c_dp]),
     'edrgp_col_moments_workspace_bytes': (_sz, [_int]),

@@ -237,6 +237,8 @@ int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* str
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "trsm");
 }
 
+size_t edrgp_eigh_workspace_bytes(int d) { return d > 0 ? edrgp::eigh_workspace_doubles(d) * sizeof(double) : 0; }
+
 int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace, void* stream) {
   if (!C || !evals || !comps || !workspace || d <= 0) return fail(EDRGP_ERR_ARG, "eigh: bad argument");
   cudaError_t e = edrgp::launch_eigh(C, d, (double*)workspace, evals, comps, sweeps, (cudaStream_t)stream);

@@ -69,6 +69,31 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- exp(x) for x <= 0 -------------------------------------------------------------------------
+// x = n ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^(n >> 6) * T[n & 63] * (1 + r + r^2/2 + ... + r^5/120),
+// T[j] = 2^(j/64) from a 64-entry shared-memory table (exp_table_init).  About 10 FP64 instructions
+// against ~20 for libm's exp: the FP64 pipe is shared with the DMMA contraction, so each one counts.
+// Truncation error r^6/720 < 4e-17; results below the normal range (x < -708) flush to zero.
+__device__ __forceinline__ void exp_table_init(double* tab, int tid) {
+  if (tid < 64) tab[tid] = exp2((double)tid * (1.0 / 64.0));
+}
+__device__ __forceinline__ double exp_neg(double x, const double* tab) {
+  const double t = fma(x, 92.33248261689366, 6755399441055744.0);       // x * 64/ln2 + 1.5 * 2^52
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -0x1.62e42fee00000p-7, x);                          // ln2/64, high part (31 bits)
+  r = fma(nf, -0x1.a39ef35793c76p-39, r);                               //         low part
+  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = p * r;
+  const double tj = tab[n & 63];
+  const double v = fma(tj, p, tj);
+  const int hi = __double2hiint(v) + ((n >> 6) << 20);
+  return x < -708.0 ? 0.0 : __hiloint2double(hi, __double2loint(v));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

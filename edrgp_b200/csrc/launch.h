@@ -32,6 +32,7 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* Bmat,
                          double* alpha, double* cvec, double* scalars, int* info, double* workspace,
                          cudaStream_t st);
+size_t eigh_workspace_doubles(int d);
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st);
 
 size_t col_moments_workspace_bytes(int d, int sms);

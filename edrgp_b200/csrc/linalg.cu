@@ -410,118 +410,7 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 }
 
 // ---------------------------------------------------------------------------------------------
-// Symmetric eigensolver: cyclic two-sided Jacobi with round-robin pair ordering, one CTA.
-// A (d x d, destroyed) and V (d x d) live in global memory (L2-resident at these sizes).
-// Output: evals sorted descending, comps[k][:] = k-th eigenvector (rows), sign fixed so that the
-// largest-magnitude entry of every row is positive.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) jacobi_eigh_kernel(double* Ag, int d, double* Vg,
-                                                           double* __restrict__ evals, double* __restrict__ comps,
-                                                           int max_sweeps, int* __restrict__ sweeps_out, int use_smem) {
-  extern __shared__ double sh[];
-  const int dd = d + (d & 1);          // players in the round-robin (one bye if d is odd)
-  const int np = dd / 2;
-  double* cs_c = sh;                   // [np]
-  double* cs_s = sh + np;              // [np]
-  int* pp = reinterpret_cast<int*>(sh + 2 * np);   // [np]
-  int* qq = pp + np;                   // [np]
-  // the matrix and the accumulated rotations live in shared memory when they fit (every step is a
-  // chain of dependent reads: ~30 cycles there against ~700 through L2)
-  double* A = use_smem ? sh + 3 * np + (np & 1) : Ag;
-  double* V = use_smem ? A + (size_t)d * d : Vg;
-  __shared__ int rotated;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (use_smem)
-    for (int i = tid; i < d * d; i += nt) A[i] = Ag[i];
-  for (int i = tid; i < d * d; i += nt) V[i] = ((i / d) == (i % d)) ? 1.0 : 0.0;
-  __syncthreads();
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    if (tid == 0) rotated = 0;
-    __syncthreads();
-    for (int step = 0; step < dd - 1; ++step) {
-      // round-robin pairing: player dd-1 fixed, the others rotate
-      for (int k = tid; k < np; k += nt) {
-        int a = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
-        int b = (step + dd - 1 - k) % (dd - 1);
-        int p = min(a, b), q = max(a, b);
-        double c = 1.0, s = 0.0;
-        if (q < d) {
-          const double apq = A[(int64_t)p * d + q];
-          const double app = A[(int64_t)p * d + p], aqq = A[(int64_t)q * d + q];
-          if (fabs(apq) > 1e-300 && fabs(apq) > 2.220446049250313e-16 * 1e-2 * sqrt(fabs(app * aqq))) {
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + tt * tt);
-            s = tt * c;
-            rotated = 1;
-          }
-        } else {
-          p = -1;
-        }
-        cs_c[k] = c; cs_s[k] = s; pp[k] = p; qq[k] = q;
-      }
-      __syncthreads();
-      // rows: A <- J^T A
-      for (int i = tid; i < np * d; i += nt) {
-        const int k = i / d, j = i - k * d;
-        const int p = pp[k], q = qq[k];
-        const double c = cs_c[k], s = cs_s[k];
-        if (p >= 0 && s != 0.0) {
-          const double x = A[(int64_t)p * d + j], y = A[(int64_t)q * d + j];
-          A[(int64_t)p * d + j] = c * x - s * y;
-          A[(int64_t)q * d + j] = s * x + c * y;
-        }
-      }
-      __syncthreads();
-      // columns: A <- A J,  V <- V J
-      for (int i = tid; i < np * d; i += nt) {
-        const int k = i % np, r = i / np;
-        const int p = pp[k], q = qq[k];
-        const double c = cs_c[k], s = cs_s[k];
-        if (p >= 0 && s != 0.0) {
-          double x = A[(int64_t)r * d + p], y = A[(int64_t)r * d + q];
-          A[(int64_t)r * d + p] = c * x - s * y;
-          A[(int64_t)r * d + q] = s * x + c * y;
-          x = V[(int64_t)r * d + p]; y = V[(int64_t)r * d + q];
-          V[(int64_t)r * d + p] = c * x - s * y;
-          V[(int64_t)r * d + q] = s * x + c * y;
-        }
-      }
-      __syncthreads();
-    }
-    if (!rotated) break;
-    __syncthreads();
-  }
-  if (tid == 0 && sweeps_out) *sweeps_out = sweep;
-  // sort descending by rank counting, write components as rows with a fixed sign
-  for (int i = tid; i < d; i += nt) {
-    const double li = A[(int64_t)i * d + i];
-    int rank = 0;
-    for (int j = 0; j < d; ++j) {
-      const double lj = A[(int64_t)j * d + j];
-      rank += (lj > li) || (lj == li && j < i);
-    }
-    evals[rank] = li;
-    double best = 0.0;
-    for (int r = 0; r < d; ++r) {
-      const double v = V[(int64_t)r * d + i];
-      if (fabs(v) > fabs(best)) best = v;
-    }
-    const double sgn = best < 0.0 ? -1.0 : 1.0;
-    for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[(int64_t)r * d + i];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One-sided (Hestenes) Jacobi for d <= 128: the fast path of edrgp_eigh.
-// The working matrix W = C V and the accumulated rotations V sit in shared memory, column-major.
-// One warp owns one column pair per step: its lanes hold the two W columns and the two V columns in
-// registers, the three inner products |a|^2, |b|^2, a.b are warp-shuffle reductions, every lane
-// derives the rotation for itself and applies it -- one __syncthreads per round-robin step instead of
-// the three phases of the two-sided kernel.  At convergence the columns of W are orthogonal, i.e. V
-// diagonalises C^2 and hence the symmetric positive semi-definite C; eigenvalues are the Rayleigh
-// quotients v^T C v against the untouched input.
+// Symmetric eigensolver (positive semi-definite input): one-sided cyclic Jacobi.
 // ---------------------------------------------------------------------------------------------
 // Cheap FP64 reciprocal / reciprocal square root: FP32 hardware estimate + two Newton steps (rel. error
 // ~1e-15).  All 32 lanes of a warp derive the same rotation, so the IEEE divide / sqrt sequences
@@ -656,6 +545,131 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-sided Jacobi for large d (> 117): the same algorithm with W = C V and V in global memory
+// (column-major, L2-resident) and ONE KERNEL PER ROUND-ROBIN STEP, a warp per column pair, so that
+// all SMs work on the d/2 independent pairs of a step.  The host reads the "rotated" flag once per
+// sweep (the only place where this library synchronises the stream).
+// ---------------------------------------------------------------------------------------------
+__global__ void eig_init_kernel(const double* __restrict__ C, int d, double* __restrict__ W, double* __restrict__ V) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)d * d) return;
+  const int c = (int)(i / d), r = (int)(i - (int64_t)c * d);
+  W[i] = C[(int64_t)r * d + c];
+  V[i] = r == c ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(256) eig_step_kernel(double* __restrict__ W, double* __restrict__ V, int d, int step,
+                                                       int* __restrict__ rotated) {
+  const int dd = d + (d & 1), np = dd / 2;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= np) return;
+  const int a0 = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
+  const int b0 = (step + dd - 1 - k) % (dd - 1);
+  const int p = min(a0, b0), q = max(a0, b0);
+  if (q >= d) return;
+  double* wa = W + (int64_t)p * d;
+  double* wb = W + (int64_t)q * d;
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+  for (int r = lane; r < d; r += 32) {
+    const double x = wa[r], y = wb[r];
+    alpha = fma(x, x, alpha); beta = fma(y, y, beta); gamma = fma(x, y, gamma);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+    beta += __shfl_xor_sync(0xffffffffu, beta, o);
+    gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+  }
+  if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) return;
+  const double zeta = (beta - alpha) / (2.0 * gamma);
+  const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
+  if (lane == 0) *rotated = 1;
+  double* va = V + (int64_t)p * d;
+  double* vb = V + (int64_t)q * d;
+  for (int r = lane; r < d; r += 32) {
+    const double x = wa[r], y = wb[r];
+    wa[r] = c * x - s * y; wb[r] = s * x + c * y;
+    const double u = va[r], v = vb[r];
+    va[r] = c * u - s * v; vb[r] = s * u + c * v;
+  }
+}
+
+// lam[i] = v_i^T C v_i (one warp per vector)
+__global__ void __launch_bounds__(256) eig_rayleigh_kernel(const double* __restrict__ C, const double* __restrict__ V,
+                                                           int d, double* __restrict__ lam) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= d) return;
+  const double* v = V + (int64_t)i * d;
+  double acc = 0.0;
+  for (int r = lane; r < d; r += 32) {
+    double cv = 0.0;
+    for (int k = 0; k < d; ++k) cv = fma(C[(int64_t)r * d + k], v[k], cv);
+    acc = fma(v[r], cv, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) lam[i] = acc;
+}
+
+__global__ void eig_finish_kernel(const double* __restrict__ lam, const double* __restrict__ V, int d,
+                                  double* __restrict__ evals, double* __restrict__ comps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  const double li = lam[i];
+  int rank = 0;
+  for (int j = 0; j < d; ++j) {
+    const double lj = lam[j];
+    rank += (lj > li) || (lj == li && j < i);
+  }
+  evals[rank] = li;
+  double best = 0.0;
+  for (int r = 0; r < d; ++r) {
+    const double v = V[(int64_t)i * d + r];
+    if (fabs(v) > fabs(best)) best = v;
+  }
+  const double sgn = best < 0.0 ? -1.0 : 1.0;
+  for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[(int64_t)i * d + r];
+}
+
+size_t eigh_workspace_doubles(int d) { return d <= 117 ? (size_t)d * d : (size_t)2 * d * d + d + 2; }
+
+static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double* evals, double* comps, int* sweeps,
+                                     cudaStream_t st) {
+  double* W = ws;
+  double* V = ws + (size_t)d * d;
+  double* lam = V + (size_t)d * d;
+  int* flag = reinterpret_cast<int*>(lam + d);
+  const int dd = d + (d & 1), np = dd / 2;
+  eig_init_kernel<<<(unsigned)(((int64_t)d * d + 255) / 256), 256, 0, st>>>(C, d, W, V); count_launch();
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    for (int step = 0; step < dd - 1; ++step) {
+      eig_step_kernel<<<(np + 7) / 8, 256, 0, st>>>(W, V, d, step, flag); count_launch();
+    }
+    int rotated = 0;
+    e = cudaMemcpyAsync(&rotated, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    if (!rotated) break;
+  }
+  if (sweeps) {
+    cudaError_t e = cudaMemcpyAsync(sweeps, &sweep, sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);       // `sweep` lives on this stack frame
+    if (e != cudaSuccess) return e;
+  }
+  eig_rayleigh_kernel<<<(d + 7) / 8, 256, 0, st>>>(C, V, d, lam); count_launch();
+  eig_finish_kernel<<<(d + 127) / 128, 128, 0, st>>>(lam, V, d, evals, comps); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
   if (d <= 117) {       // two d x d matrices in shared memory
     const size_t smem1 = (size_t)2 * d * d * sizeof(double);
@@ -666,18 +680,7 @@ cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comp
     jacobi_onesided_kernel<<<1, 1024, smem1, st>>>(A, d, evals, comps, 60, sweeps); count_launch();
     return cudaGetLastError();
   }
-
-  const int dd = d + (d & 1), np = dd / 2;
-  size_t smem = (size_t)(3 * np + (np & 1)) * sizeof(double);
-  const size_t mats = (size_t)2 * d * d * sizeof(double);
-  const int use_smem = smem + mats <= 220 * 1024;
-  if (use_smem) smem += mats;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  jacobi_eigh_kernel<<<1, 1024, smem, st>>>(A, d, V, evals, comps, 60, sweeps, use_smem); count_launch();
-  return cudaGetLastError();
+  return launch_eigh_large(A, d, V, evals, comps, sweeps, st);
 }
 
 }  // namespace edrgp

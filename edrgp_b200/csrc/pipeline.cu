@@ -74,7 +74,8 @@ struct Smem {
   static constexpr size_t z_off = x_off + (size_t)XS * BM * S * 8;
   static constexpr size_t il2_off = z_off + (size_t)NS * TILE * 8;
   static constexpr size_t hx_off = il2_off + (size_t)DP * 8;
-  static constexpr size_t bar_off = hx_off + (size_t)BM * 8;
+  static constexpr size_t tab_off = hx_off + (size_t)BM * 8;             // exp table, 64 doubles
+  static constexpr size_t bar_off = tab_off + 64 * 8;
   static constexpr size_t bytes = bar_off + (size_t)(2 * XS + 2 * NS) * 8;
 };
 
@@ -222,6 +223,33 @@ __device__ __forceinline__ void dist_gemm(double (&s)[2][MT / 8][2], const doubl
   }
 }
 
+// The same contraction in pieces (accumulator start, then one 16-feature group at a time), so that a
+// caller can interleave it with independent work at source level.
+__device__ __forceinline__ void dist_gemm_init(double (&s)[2][MT / 8][2], const double* hz, double hx0, double hx1, int t) {
+#pragma unroll
+  for (int nb = 0; nb < MT / 8; ++nb) {
+    const double2 h = *reinterpret_cast<const double2*>(hz + 8 * nb + 2 * t);
+    s[0][nb][0] = hx0 + h.x; s[0][nb][1] = hx0 + h.y;
+    s[1][nb][0] = hx1 + h.x; s[1][nb][1] = hx1 + h.y;
+  }
+}
+template <int DP>
+__device__ __forceinline__ void dist_gemm_group(double (&s)[2][MT / 8][2], const double* x0, const double* x1,
+                                                const double* zg, int kg) {
+  constexpr int S = row_stride(DP);
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    const int col = kg * 16 + 2 * sl;
+    const double a0 = x0[col], a1 = x1[col];
+#pragma unroll
+    for (int nb = 0; nb < MT / 8; ++nb) {
+      const double b = zg[nb * 8 * S + col];
+      dmma(s[0][nb][0], s[0][nb][1], a0, b);
+      dmma(s[1][nb][0], s[1][nb][1], a1, b);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // K1+K4+K5 fused
 // -------------------------------------------------------------------------------------------------
@@ -237,6 +265,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
   double* zbuf = reinterpret_cast<double*>(smem_raw + L::z_off);
   double* il2s = reinterpret_cast<double*>(smem_raw + L::il2_off);
   double* hxs = reinterpret_cast<double*>(smem_raw + L::hx_off);
+  double* etab = reinterpret_cast<double*>(smem_raw + L::tab_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::bar_off);
   uint64_t* xfull = bars;
   uint64_t* xempty = bars + XS;
@@ -250,6 +279,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
     mbar_fence_init();
   }
   for (int i = tid; i < DP; i += blockDim.x) il2s[i] = p.pack[i];
+  exp_table_init(etab, tid);
   // padding columns of the X buffers must be finite zeros (bulk copies fill only d columns)
   for (int i = tid; i < XS * BM * S; i += blockDim.x) xbuf[i] = 0.0;
   fence_proxy_async();
@@ -339,8 +369,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
             const double e0 = s[mb][nb][0], e1 = s[mb][nb][1];
-            const double w0 = e0 < 0.0 ? exp(e0) * c.x : 0.0;
-            const double w1 = e1 < 0.0 ? exp(e1) * c.y : 0.0;
+            const double w0 = e0 < 0.0 ? exp_neg(e0, etab) * c.x : 0.0;
+            const double w1 = e1 < 0.0 ? exp_neg(e1, etab) * c.y : 0.0;
             s[mb][nb][0] = w0; s[mb][nb][1] = w1;
             if (mb == 0) rs0 += w0 + w1; else rs1 += w0 + w1;
           }
@@ -447,7 +477,12 @@ __global__ void reduce_gram_kernel(const double* __restrict__ Cpart, int nparts,
 // -------------------------------------------------------------------------------------------------
 // K1 (+ b = Kuf y): cross-covariance tiles written to HBM
 // -------------------------------------------------------------------------------------------------
-template <int DP, int XS, int NS>
+// SIMPLE: entries are stored, nothing is multiplied in and no Kfu^T y is accumulated -- the statistics
+// pass.  Its tile loop is software pipelined: the exp + store of inducing tile t is interleaved, at
+// source level and branch-free, with the distance contraction of tile t + 1, so that the DMMA pipe
+// is fed while the FP64 exponentials of the previous tile retire (both warps of a sub-partition
+// otherwise reach their exp phase together behind the shared tile barrier: 57 % pipe use, ncu r01).
+template <int DP, int XS, int NS, bool SIMPLE>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipeParams p) {
   using L = Smem<DP, XS, NS>;
   constexpr int S = L::S;
@@ -456,6 +491,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
   double* zbuf = reinterpret_cast<double*>(smem_raw + L::z_off);
   double* il2s = reinterpret_cast<double*>(smem_raw + L::il2_off);
   double* hxs = reinterpret_cast<double*>(smem_raw + L::hx_off);
+  double* etab = reinterpret_cast<double*>(smem_raw + L::tab_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::bar_off);
   uint64_t* xfull = bars;
   uint64_t* xempty = bars + XS;
@@ -469,6 +505,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
     mbar_fence_init();
   }
   for (int i = tid; i < DP; i += blockDim.x) il2s[i] = p.pack[i];
+  exp_table_init(etab, tid);
   for (int i = tid; i < XS * BM * S; i += blockDim.x) xbuf[i] = 0.0;
   fence_proxy_async();
   __syncthreads();
@@ -492,7 +529,63 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
     double y0 = 0.0, y1 = 0.0;
     if (p.y != nullptr) { if (v0) y0 = p.y[ra]; if (v1) y1 = p.y[rb]; }
     double mu0 = 0.0, mu1 = 0.0;
-    for (int mt = 0; mt < p.mtiles; ++mt) {
+    if (SIMPLE) {
+      const int cperm = (t & 1) + 8 * (t >> 1);
+      const double* x0 = xw + g * S + cperm;
+      const double* x1 = xw + (g + 8) * S + cperm;
+      double* k0p = p.Kfu + ra * p.ldk + 2 * t;
+      double* k1p = p.Kfu + rb * p.ldk + 2 * t;
+      // finish one inducing tile: K = sf2 exp(min(s, 0)), row sums, predicated 16-byte stores
+      auto finish = [&](double (&sc)[2][MT / 8][2], int nb, int mt, const double* cf) {
+        const int j = mt * MT + 8 * nb + 2 * t;
+        const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
+        double2 o0, o1;
+        o0.x = p.sf2 * exp_neg(fmin(sc[0][nb][0], 0.0), etab); o0.y = p.sf2 * exp_neg(fmin(sc[0][nb][1], 0.0), etab);
+        o1.x = p.sf2 * exp_neg(fmin(sc[1][nb][0], 0.0), etab); o1.y = p.sf2 * exp_neg(fmin(sc[1][nb][1], 0.0), etab);
+        mu0 += fma(o0.x, c.x, o0.y * c.y); mu1 += fma(o1.x, c.x, o1.y * c.y);
+        // ldk is even, so a pair starting at an even j < m is in bounds (a column == m is padding)
+        if (v0 && j < p.m) *reinterpret_cast<double2*>(k0p + mt * MT + 8 * nb) = o0;
+        if (v1 && j < p.m) *reinterpret_cast<double2*>(k1p + mt * MT + 8 * nb) = o1;
+      };
+      double sa[2][MT / 8][2], sb[2][MT / 8][2];
+      const double* zt = zbuf + (size_t)zs * L::TILE;
+      mbar_wait(&zfull[zs], zph);
+      dist_gemm_init(sa, zt + MT * S, hx0, hx1, t);
+#pragma unroll
+      for (int kg = 0; kg < DP / 16; ++kg) dist_gemm_group<DP>(sa, x0, x1, zt + g * S + cperm, kg);
+      for (int mt = 0; mt + 1 < p.mtiles; ++mt) {
+        const double* cf = zt + MT * S + MT;
+        const int zs_cur = zs;
+        if (++zs == NS) { zs = 0; zph ^= 1; }
+        const double* zn = zbuf + (size_t)zs * L::TILE;
+        mbar_wait(&zfull[zs], zph);
+        dist_gemm_init(sb, zn + MT * S, hx0, hx1, t);
+        // DP / 16 contraction groups of the next tile against MT / 8 = 4 finishing steps of this one
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int kg = q * (DP / 16) / 4; kg < (q + 1) * (DP / 16) / 4; ++kg)
+            dist_gemm_group<DP>(sb, x0, x1, zn + g * S + cperm, kg);
+          finish(sa, q, mt, cf);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&zempty[zs_cur]);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < MT / 8; ++nb) { sa[mb][nb][0] = sb[mb][nb][0]; sa[mb][nb][1] = sb[mb][nb][1]; }
+        zt = zn;
+      }
+      {
+        const double* cf = zt + MT * S + MT;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) finish(sa, q, p.mtiles - 1, cf);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&zempty[zs]);
+        if (++zs == NS) { zs = 0; zph ^= 1; }
+      }
+    }
+    for (int mt = 0; !SIMPLE && mt < p.mtiles; ++mt) {
       const double* zt = zbuf + (size_t)zs * L::TILE;
       mbar_wait(&zfull[zs], zph);
       double s[2][MT / 8][2];
@@ -503,8 +596,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         // entries are stored without the pack coefficient; only the row sums mu carry it
-        double k00 = p.sf2 * exp(fmin(s[0][nb][0], 0.0)), k01 = p.sf2 * exp(fmin(s[0][nb][1], 0.0));
-        double k10 = p.sf2 * exp(fmin(s[1][nb][0], 0.0)), k11 = p.sf2 * exp(fmin(s[1][nb][1], 0.0));
+        double k00 = p.sf2 * exp_neg(fmin(s[0][nb][0], 0.0), etab), k01 = p.sf2 * exp_neg(fmin(s[0][nb][1], 0.0), etab);
+        double k10 = p.sf2 * exp_neg(fmin(s[1][nb][0], 0.0), etab), k11 = p.sf2 * exp_neg(fmin(s[1][nb][1], 0.0), etab);
         if (p.mul && j < p.m) {
           // feature-chunked evaluation: exp(-r^2/2) factorises over blocks of features
           if (v0) { const double2 o = *reinterpret_cast<const double2*>(p.Kfu + ra * p.ldk + j); k00 *= o.x; k01 *= o.y; }
@@ -576,14 +669,21 @@ static cudaError_t launch_grad_gram_cached_t(const PipeParams& p, int grid, cuda
   return cudaGetLastError();
 }
 
-template <int DP, int XS, int NS>
-static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) {
+template <int DP, int XS, int NS, bool SIMPLE>
+static cudaError_t launch_kuf_s(const PipeParams& p, int grid, cudaStream_t st) {
   using L = Smem<DP, XS, NS>;
-  auto kern = kuf_kernel<DP, XS, NS>;
+  auto kern = kuf_kernel<DP, XS, NS, SIMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
   kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p); count_launch();
   return cudaGetLastError();
+}
+
+template <int DP, int XS, int NS>
+static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) {
+  // the pipelined variant needs DP / 16 divisible by 4 (64, 128) to split the next tile's contraction
+  const bool simple = p.Kfu != nullptr && !p.mul && p.b == nullptr && (DP % 64 == 0);
+  return simple ? launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(p, grid, st) : launch_kuf_s<DP, XS, NS, false>(p, grid, st);
 }
 
 cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,

@@ -323,10 +323,10 @@ def eigh(C):
     lib = _lib.load()
     _need_cuda(C)
     d = C.shape[0]
-    A = C.clone()
+    A = C.contiguous()
     evals = torch.empty(d, dtype=F64, device=C.device)
     comps = torch.empty(d, d, dtype=F64, device=C.device)
-    ws = torch.empty(d * d, dtype=F64, device=C.device)
+    ws = torch.empty(max(1, lib.edrgp_eigh_workspace_bytes(d) // 8), dtype=F64, device=C.device)
     with _Timed('eigh'):
         _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
     return evals, comps

@@ -181,11 +181,16 @@ int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream);
 int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * K6  symmetric eigendecomposition of the d x d EDR matrix C = G^T G (cyclic Jacobi).
+ * K6  symmetric eigendecomposition of the d x d positive semi-definite EDR matrix C = G^T G
+ * (one-sided cyclic Jacobi on W = C V; eigenvalues as Rayleigh quotients).
  * Replaces np.linalg.svd(G) in SVDTransformer.fit (edrgp/utils.py:140): comps rows are the right
- * singular vectors of G, evals = S^2, descending.  C is destroyed.  workspace: d*d doubles.
- * sweeps (device int, may be NULL) receives the number of Jacobi sweeps used.
+ * singular vectors of G, evals = S^2, descending.  C is left intact.
+ * workspace: edrgp_eigh_workspace_bytes(d).  sweeps (device int, may be NULL) receives the number of
+ * Jacobi sweeps used.  d <= 117 runs as one CTA in shared memory and only enqueues; larger d runs
+ * one kernel per round-robin step over all SMs and SYNCHRONISES the stream once per sweep to read
+ * the convergence flag (the one exception to "enqueue only").
  * ------------------------------------------------------------------------------------------- */
+size_t edrgp_eigh_workspace_bytes(int d);
 int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace,
                void* stream);
 

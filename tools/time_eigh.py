@@ -11,7 +11,7 @@ for name, C in (('dominant', G.T @ G), ('flat', torch.randn(500, d, dtype=torch.
     if name == 'flat':
         C = C @ C.T
     A = C.clone(); ev = torch.empty(d, dtype=torch.float64, device='cuda'); cp = torch.empty(d, d, dtype=torch.float64, device='cuda')
-    ws = torch.empty(d * d, dtype=torch.float64, device='cuda'); sw = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ws = torch.empty(lib.edrgp_eigh_workspace_bytes(d) // 8 + 8, dtype=torch.float64, device="cuda"); sw = torch.zeros(1, dtype=torch.int32, device='cuda')
     st = torch.cuda.current_stream().cuda_stream
     best = 1e9
     for _ in range(5):
