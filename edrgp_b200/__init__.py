@@ -8,6 +8,6 @@ there is no CPU fallback.
 __version__ = '0.1.0'
 
 from .gp_model import SparseGaussianProcessRegressor          # noqa: F401
-from .transformer import GramEighTransformer                  # noqa: F401
+from .transformer import GramEighTransformer, DevicePCA       # noqa: F401
 from .edr import EffectiveDimensionalityReduction, EDR        # noqa: F401
 from .utils import discrepancy, subspace_variance_ratio_from_gram   # noqa: F401

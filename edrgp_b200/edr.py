@@ -155,13 +155,17 @@ class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):
         self._reverse_scaling_ = np.diag(1 / scaler.scale_)
         Xs = ops.standardize(Xd, mean, scale) if n_local else Xd
         if self.preprocessor is not None:
-            if dist.is_distributed():
-                raise NotImplementedError("a host preprocessor needs all rows in one process")
             self.preprocessor_ = clone(self.preprocessor)
-            Xp = self.preprocessor_.fit_transform(Xs.cpu().numpy())
+            if hasattr(self.preprocessor_, 'fit_transform_device'):
+                # device preprocessor (DevicePCA): rows stay in HBM, moments reduced over ranks
+                Xs = self.preprocessor_.fit_transform_device(Xs)
+            else:
+                if dist.is_distributed():
+                    raise NotImplementedError("a host preprocessor needs all rows in one process; use DevicePCA")
+                Xp = self.preprocessor_.fit_transform(Xs.cpu().numpy())
+                Xs = torch.as_tensor(np.ascontiguousarray(Xp, dtype=np.float64), device=Xd.device)
             self._check_transformer(self.preprocessor_)
             self._preprocessing_ = self.preprocessor_.components_
-            Xs = torch.as_tensor(np.ascontiguousarray(Xp, dtype=np.float64), device=Xd.device)
         return Xs
 
     def _preprocessing_transform(self, X):

@@ -83,3 +83,87 @@ class GramEighTransformer(BaseEstimator, TransformerMixin):
             V = torch.as_tensor(np.ascontiguousarray(self.components_), device=X.device)
             return ops.project(X.contiguous(), V)
         return np.asarray(X).dot(self.components_.T)
+
+
+class DevicePCA(BaseEstimator, TransformerMixin):
+    """PCA preprocessor on the device: drop-in for ``sklearn.decomposition.PCA``
+    as edr-gp uses it in front of the estimator (``preprocessor=PCA(n_components=...)``,
+    ``edrgp/edr.py:169-174``; examples/chain_PCA-EDRGP.ipynb).
+
+    The column means and the centred Gram matrix X_c^T X_c are reduced on the device (column-moment
+    and DMMA symmetric-reduction kernels, summed over ranks), the d x d eigenproblem runs on the Jacobi
+    kernel and the rows are projected by ``edrgp_project``: X never visits the host.  Attributes follow
+    sklearn: ``components_`` (k, d) with the largest-magnitude entry of each row positive, ``mean_``,
+    ``explained_variance_`` (ddof = 1), ``explained_variance_ratio_``, ``singular_values_``.
+    """
+
+    def __init__(self, n_components=None):
+        self.n_components = n_components
+
+    def _fit_device(self, Xd):
+        n_local, d = Xd.shape
+        cnt = torch.tensor([float(n_local)], dtype=F64, device=Xd.device)
+        s1 = ops.col_moments(Xd)[0].clone() if n_local else torch.zeros(d, dtype=F64, device=Xd.device)
+        dist.allreduce_sum_(s1, cnt)
+        n = float(cnt[0])
+        mean = s1 / n
+        ones = torch.ones(d, dtype=F64, device=Xd.device)
+        Xc = ops.standardize(Xd, mean, ones) if n_local else Xd
+        if n_local:
+            C = ops.syrk(ops.pad_even(Xc))[:d, :d].contiguous()
+        else:
+            C = torch.zeros(d, d, dtype=F64, device=Xd.device)
+        dist.allreduce_sum_(C)
+        evals, comps = ops.eigh(C)
+        lam = np.clip(evals.cpu().numpy(), 0.0, np.inf)
+        comps = comps.cpu().numpy()
+        nc = self.n_components
+        if nc is None:
+            k = min(d, int(n))
+        elif isinstance(nc, (int, np.integer)) and 0 < nc <= d:
+            k = int(nc)
+        elif isinstance(nc, float) and 0 < nc < 1:
+            ratio = lam / lam.sum()
+            k = int(np.searchsorted(np.cumsum(ratio), nc, side='right')) + 1
+            k = min(k, d)
+        else:
+            raise ValueError("n_components=%r is not supported" % (nc,))
+        self.mean_ = mean.cpu().numpy()
+        self.n_samples_ = int(round(n))
+        self.n_features_in_ = d
+        self.components_ = comps[:k]
+        self.explained_variance_ = lam[:k] / max(n - 1.0, 1.0)
+        self.explained_variance_ratio_ = lam[:k] / lam.sum() if lam.sum() > 0 else np.zeros(k)
+        self.singular_values_ = np.sqrt(lam[:k])
+        self.n_components_ = k
+        return Xc
+
+    def fit_transform_device(self, Xd):
+        """Fit on this rank's device rows and return their projection (device tensor, (n_local, k))."""
+        Xc = self._fit_device(Xd.contiguous())
+        if Xc.shape[0] == 0:
+            return torch.empty(0, self.n_components_, dtype=F64, device=Xd.device)
+        return ops.project(Xc, torch.as_tensor(np.ascontiguousarray(self.components_), device=Xd.device))
+
+    def fit(self, X, y=None):
+        self._fit_device(_rows_to_device(X))
+        return self
+
+    def fit_transform(self, X, y=None):
+        out = self.fit_transform_device(_rows_to_device(X))
+        return out if isinstance(X, torch.Tensor) else out.cpu().numpy()
+
+    def transform(self, X):
+        if isinstance(X, torch.Tensor):
+            mean = torch.as_tensor(self.mean_, device=X.device)
+            Xc = ops.standardize(X.to(dtype=F64).contiguous(), mean, torch.ones_like(mean))
+            return ops.project(Xc, torch.as_tensor(np.ascontiguousarray(self.components_), device=X.device))
+        return (np.asarray(X) - self.mean_).dot(self.components_.T)
+
+
+def _rows_to_device(X):
+    if isinstance(X, torch.Tensor):
+        Xd = X.to(dtype=F64)
+        return (Xd if Xd.is_cuda else Xd.cuda()).contiguous()
+    X = check_array(X, dtype=np.float64)
+    return torch.as_tensor(np.ascontiguousarray(X), device='cuda')

@@ -142,3 +142,36 @@ def test_get_estimator_gradients_and_importances():
     assert g.shape == (30, 6) and np.all(np.isfinite(g))
     assert edr.feature_importances_.shape == (2, 6)
     assert edr.inverse_transform(edr.transform(X[:5])).shape == (5, 6)
+
+
+def test_device_pca_matches_sklearn_and_chains():
+    """the PCA preprocessor on the device (examples/chain_PCA-EDRGP.ipynb): same
+    components / variances as sklearn's PCA, and the chained EDR fit equals the host-PCA chain."""
+    from sklearn.decomposition import PCA
+    import edrgp_b200 as eb
+    rng = np.random.RandomState(4)
+    X = rng.standard_normal((3000, 9)).dot(rng.standard_normal((9, 9))) + rng.standard_normal(9) * 3
+    ref = PCA(n_components=4, svd_solver='full').fit(X)
+    dev = eb.DevicePCA(n_components=4)
+    Xt = dev.fit_transform(X)
+    assert np.allclose(dev.explained_variance_, ref.explained_variance_, rtol=1e-10)
+    assert np.allclose(dev.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-10)
+    assert np.allclose(dev.mean_, ref.mean_, rtol=1e-12, atol=1e-12)
+    for a, b in zip(dev.components_, ref.components_):
+        assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-9
+    assert np.allclose(np.abs(Xt), np.abs(ref.transform(X)), rtol=1e-8, atol=1e-9)
+    assert np.allclose(dev.transform(X[:7]), Xt[:7], rtol=1e-10, atol=1e-10)
+
+    X2, y = _two_d(seed=1)
+    Xw = np.hstack([X2, 1e-3 * rng.standard_normal((X2.shape[0], 2))])
+
+    def make(pre):
+        return eb.EffectiveDimensionalityReduction(
+            eb.SparseGaussianProcessRegressor('RBF', {'ARD': True}, num_inducing=40),
+            eb.GramEighTransformer(), n_components=1, normalize=True, preprocessor=pre)
+    np.random.seed(0)
+    a = make(PCA(n_components=2, svd_solver='full')).fit(Xw, y, max_iters=0)
+    np.random.seed(0)
+    b = make(eb.DevicePCA(n_components=2)).fit(Xw, y, max_iters=0)
+    assert a.components_.shape == b.components_.shape == (1, 4)
+    assert op.principal_angle(a.components_, b.components_) < 1e-6
