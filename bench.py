@@ -340,6 +340,17 @@ def run_ours(args):
                "sample": "%d rows of the same generator, one sweep after one warm-up (%.1f s); oracle/pipeline.py "
                          "chunked NumPy/OpenBLAS on all host threads" % (rows, sec)}
 
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of a launch of the
+    # same size (524288 rows); null when the launch size differs or the capture is absent
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
+            tr = json.load(f)['gemm_tn_kernel']
+        if abs(rows_per_launch_syrk - tr['rows']) < 0.1 * tr['rows'] and (d, m) == (D, M):
+            traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+    except (OSError, ValueError, KeyError):
+        pass
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -357,7 +368,10 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (P = Kfu^T Kfu, b, yy; symmetric DMMA reduction)",
                      "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
-                     "traffic": None,
+                     "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 524288-row launch (ncu --set full, "
+                                     "profiles/r01_ncu_top_kernels_final.txt); algorithmic bytes per launch = 2.15 GB (the Kfu "
+                                     "block once): each column slab is read by several tiles, L2 absorbs about half of the re-reads",
                      "achieved_executed": syrk_tf_exec, "frac_executed": syrk_tf_exec / peak if peak else None,
                      "peak_live": peak_live, "peak_recorded": peak_recorded,
                      "peak_source": "measured FP64 DMMA (mma.sync m8n8k4 f64) peak of this pool's B200: the larger of "

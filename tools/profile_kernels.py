@@ -1,5 +1,6 @@
-"""Runs the three n-scale kernels of the sweep once each after a warm-up, at one 512k-row block of the
-headline shape (d=64, m=512), for ncu captures:  kuf_kernel, gemm_tn_kernel, grad_gram_kernel."""
+"""Runs the n-scale kernels of the sweep once each after a warm-up, at one 524288-row block of the
+headline shape (d=64, m=512), for ncu captures: kuf_kernel (pipelined), gemm_tn_kernel (symmetric),
+grad_gram_kernel (cached-Kfu variant and the fused recompute variant)."""
 import sys
 import torch
 sys.path.insert(0, '.')
@@ -13,11 +14,12 @@ Z = X[:m].contiguous()
 ell = (d ** 0.5) * (1 + 0.5 * torch.rand(d, dtype=torch.float64, device='cuda', generator=g))
 alpha = torch.randn(m, dtype=torch.float64, device='cuda', generator=g)
 pack = ops.InducingPack(Z, ell)
-gpack = ops.InducingPack(Z, ell, alpha, 1.0)
+cpack = ops.InducingPack(Z, ell, alpha, 1.0, block=64)
 K = torch.empty(n, m, dtype=torch.float64, device='cuda')
 for it in range(2):
     ops.kuf(X, pack, 1.0, out=K)
     P, byy = ops.inducing_stats(K, y, m)
-    G, C = ops.grad_gram(X, gpack, want_G=False)
+    G, C = ops.grad_gram_cached(X, K, cpack, 1.0, want_G=False)
+    G2, C2 = ops.grad_gram(X, cpack, want_G=False)
 torch.cuda.synchronize()
-print("ok", float(P[0, 0]), float(C[0, 0]))
+print("ok", float(P[0, 0]), float(C[0, 0]), float(C2[0, 0]))
