@@ -13,6 +13,26 @@ namespace edrgp {
 
 constexpr int NBK = 32;
 
+// Cheap FP64 reciprocal / reciprocal square root: FP32 hardware estimate + two Newton steps (relative
+// error ~2e-16, i.e. the last bit).  The IEEE divide / sqrt sequences (~40 dependent FP64 instructions
+// each) sit on the critical path of the one-warp Cholesky steps and of the Jacobi rotations (where the
+// ANGLE only steers convergence -- what must be exact is c^2 + s^2 = 1, which c = rsqrt(1 + t^2),
+// s = t c gives).
+__device__ __forceinline__ double fast_rsqrt(double x) {      // 1e-30 < x < 1e30
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) {        // 1e-30 < |x| < 1e30
+  double r = (double)__frcp_rn((float)x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // generic strided small GEMM:  C[i][j] = beta C[i][j] + alpha sum_k A(i,k) B(k,j)
 //   A(i,k) = A[i*sai + k*sak],  B(k,j) = B[k*sbk + j*sbj],  C row-major with ldc.
@@ -82,8 +102,11 @@ __device__ __forceinline__ void potf2_regs(double (&a)[NBK], int lane, int nb, i
     if (j < nb && !(djj > 0.0)) {
       if (info != nullptr && lane == 0) atomicCAS(info, 0, k0 + j + 1);
     }
-    const double ljj = sqrt(djj);
-    const double lij = lane == j ? ljj : a[j] / ljj;
+    // pivot through the cheap reciprocal square root when it is in the estimate's range
+    const bool fast = djj > 1e-30 && djj < 1e30;
+    const double inv = fast ? fast_rsqrt(djj) : 1.0 / sqrt(djj);
+    const double ljj = fast ? djj * inv : sqrt(djj);
+    const double lij = lane == j ? ljj : a[j] * inv;
     if (lane >= j) a[j] = lij;
 #pragma unroll
     for (int c = j + 1; c < NBK; ++c) {
@@ -130,12 +153,13 @@ __global__ void __launch_bounds__(32) potrf_step_kernel(double* __restrict__ A, 
     double x[NBK];
 #pragma unroll
     for (int c = 0; c < NBK; ++c) x[c] = X[lane][c];
+    const double dinv = 1.0 / S[lane][lane];          // lane c holds 1 / L11[c][c]
 #pragma unroll
     for (int c = 0; c < NBK; ++c) {
       double v = x[c];
 #pragma unroll
       for (int q = 0; q < c; ++q) v = fma(-x[q], S[c][q], v);
-      x[c] = v / S[c][c];
+      x[c] = v * __shfl_sync(0xffffffffu, dinv, c);
     }
 #pragma unroll
     for (int c = 0; c < NBK; ++c) X[lane][c] = x[c];
@@ -412,68 +436,60 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 // ---------------------------------------------------------------------------------------------
 // Symmetric eigensolver (positive semi-definite input): one-sided cyclic Jacobi.
 // ---------------------------------------------------------------------------------------------
-// Cheap FP64 reciprocal / reciprocal square root: FP32 hardware estimate + two Newton steps (rel. error
-// ~1e-15).  All 32 lanes of a warp derive the same rotation, so the IEEE divide / sqrt sequences
-// (~40 FP64 instructions each) were the throughput bound of the solver; the rotation ANGLE only
-// steers convergence -- what must be exact is c^2 + s^2 = 1, which c = rsqrt(1 + t^2), s = t c gives.
-__device__ __forceinline__ double fast_rsqrt(double x) {      // 1e-30 < x < 1e30
-  double y = (double)rsqrtf((float)x);
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
-}
-__device__ __forceinline__ double fast_rcp(double x) {        // 1e-30 < |x| < 1e30
-  double r = (double)__frcp_rn((float)x);
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
-}
+constexpr int EIG_R = 8;                    // rows per lane
 
-constexpr int EIG_MAXD = 128;
-constexpr int EIG_RPL = EIG_MAXD / 32;      // rows per lane
-
-__global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __restrict__ C, int d,
+// L lanes per column pair (32 / L pairs per warp): d <= 8 L.  Fewer, fuller warps than one warp per
+// pair: the rotation parameters are derived once per warp instruction for 32 / L pairs at a time,
+// which is what the solver's time goes into (issue slots of the FP64 sequences), and the block-wide
+// barrier per step spans fewer warps.
+template <int L>
+__global__ void __launch_bounds__(L == 16 ? 1024 : 256) jacobi_onesided_kernel(const double* __restrict__ C, int d,
                                                                double* __restrict__ evals, double* __restrict__ comps,
                                                                int max_sweeps, int* __restrict__ sweeps_out) {
   extern __shared__ double sh[];
-  double* W = sh;                       // [d][d] column-major: W[c * d + r]
-  double* V = sh + (size_t)d * d;
+  const int ds = d + 1 + ((d + 1) & 1);       // column stride: breaks the power-of-two bank pattern
+  double* W = sh;                             // [d][ds] column-major: W[c * ds + r]
+  double* V = sh + (size_t)d * ds;
   __shared__ int rotated;
-  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x;
   const int dd = d + (d & 1), np = dd / 2;
   for (int i = tid; i < d * d; i += nt) {
     const int c = i / d, r = i - c * d;
-    W[i] = C[(int64_t)r * d + c];
-    V[i] = r == c ? 1.0 : 0.0;
+    W[c * ds + r] = C[(int64_t)r * d + c];
+    V[c * ds + r] = r == c ? 1.0 : 0.0;
   }
   __syncthreads();
+  const int k = tid / L, l = tid % L;         // pair slot and lane within the pair group
+  const bool active = k < np;
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     if (tid == 0) rotated = 0;
     __syncthreads();
     for (int step = 0; step < dd - 1; ++step) {
-      for (int k = warp; k < np; k += nwarps) {
+      int p = 0, q = d;
+      if (active) {
         const int a0 = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
         const int b0 = (step + dd - 1 - k) % (dd - 1);
-        const int p = min(a0, b0), q = max(a0, b0);
-        if (q >= d) continue;                       // the bye of an odd dimension
-        double wa[EIG_RPL], wb[EIG_RPL];
-        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        p = min(a0, b0); q = max(a0, b0);
+      }
+      const bool live = active && q < d;      // q == d: the bye of an odd dimension / idle slot
+      double wa[EIG_R], wb[EIG_R];
+      double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
-        for (int e = 0; e < EIG_RPL; ++e) {
-          const int r = lane + 32 * e;
-          wa[e] = r < d ? W[p * d + r] : 0.0;
-          wb[e] = r < d ? W[q * d + r] : 0.0;
-          alpha = fma(wa[e], wa[e], alpha); beta = fma(wb[e], wb[e], beta); gamma = fma(wa[e], wb[e], gamma);
-        }
+      for (int e = 0; e < EIG_R; ++e) {
+        const int r = l + L * e;
+        const bool ok = live && r < d;
+        wa[e] = ok ? W[p * ds + r] : 0.0;
+        wb[e] = ok ? W[q * ds + r] : 0.0;
+        alpha = fma(wa[e], wa[e], alpha); beta = fma(wb[e], wb[e], beta); gamma = fma(wa[e], wb[e], gamma);
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-          beta += __shfl_xor_sync(0xffffffffu, beta, o);
-          gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
-        }
-        if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) continue;   // warp-uniform
+      for (int o = L / 2; o > 0; o >>= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+      }
+      if (live && gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
         double tt;
         const double ag = fabs(gamma), diff = beta - alpha;
         if (ag > 1e-30 && ag < 1e30 && fabs(diff) < 1e15 * ag) {
@@ -486,16 +502,16 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __r
           tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         }
         const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
-        if (lane == 0) rotated = 1;
+        if (l == 0) rotated = 1;
 #pragma unroll
-        for (int e = 0; e < EIG_RPL; ++e) {
-          const int r = lane + 32 * e;
+        for (int e = 0; e < EIG_R; ++e) {
+          const int r = l + L * e;
           if (r < d) {
-            W[p * d + r] = c * wa[e] - s * wb[e];
-            W[q * d + r] = s * wa[e] + c * wb[e];
-            const double va = V[p * d + r], vb = V[q * d + r];
-            V[p * d + r] = c * va - s * vb;
-            V[q * d + r] = s * va + c * vb;
+            W[p * ds + r] = c * wa[e] - s * wb[e];
+            W[q * ds + r] = s * wa[e] + c * wb[e];
+            const double va = V[p * ds + r], vb = V[q * ds + r];
+            V[p * ds + r] = c * va - s * vb;
+            V[q * ds + r] = s * va + c * vb;
           }
         }
       }
@@ -505,25 +521,26 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __r
     __syncthreads();
   }
   if (tid == 0 && sweeps_out) *sweeps_out = sweep;
-  // eigenvalues: Rayleigh quotients against the input (one warp per vector), kept in W's first column slots
-  double* lam = W;                      // reuse: [d]
+  // eigenvalues: Rayleigh quotients v^T C v against the input, one warp per vector
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  double* lam = W;                      // reused once every warp is done with W
   __syncthreads();
-  double mine[ (EIG_MAXD + 31) / 32 ];
+  double mine[8];
   int cnt = 0;
-  for (int i = warp; i < d; i += nwarps, ++cnt) {
+  for (int i = warp; i < d && cnt < 8; i += nwarps, ++cnt) {
     double acc = 0.0;
     for (int r = lane; r < d; r += 32) {
       double cv = 0.0;
-      for (int k = 0; k < d; ++k) cv = fma(C[(int64_t)r * d + k], V[i * d + k], cv);
-      acc = fma(V[i * d + r], cv, acc);
+      for (int kk = 0; kk < d; ++kk) cv = fma(C[(int64_t)r * d + kk], V[i * ds + kk], cv);
+      acc = fma(V[i * ds + r], cv, acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     mine[cnt] = acc;
   }
-  __syncthreads();                      // every warp is done reading W before it is reused
+  __syncthreads();
   cnt = 0;
-  for (int i = warp; i < d; i += nwarps, ++cnt)
+  for (int i = warp; i < d && cnt < 8; i += nwarps, ++cnt)
     if (lane == 0) lam[i] = mine[cnt];
   __syncthreads();
   // sort descending by rank counting, write components as rows with a fixed sign
@@ -537,12 +554,28 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(const double* __r
     evals[rank] = li;
     double best = 0.0;
     for (int r = 0; r < d; ++r) {
-      const double v = V[i * d + r];
+      const double v = V[i * ds + r];
       if (fabs(v) > fabs(best)) best = v;
     }
     const double sgn = best < 0.0 ? -1.0 : 1.0;
-    for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[i * d + r];
+    for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[i * ds + r];
   }
+}
+
+template <int L>
+static cudaError_t launch_jacobi_small(const double* C, int d, double* evals, double* comps, int* sweeps, cudaStream_t st) {
+  const int ds = d + 1 + ((d + 1) & 1);
+  const size_t smem = (size_t)2 * d * ds * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int np = (d + 1) / 2;
+  int threads = ((np * L + 31) / 32) * 32;
+  if (threads < 128) threads = 128;            // at least 4 warps for the Rayleigh / output phase (<= 8 vectors per warp needs d <= 8 * warps)
+  while ((threads / 32) * 8 < d) threads += 32;
+  jacobi_onesided_kernel<L><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps); count_launch();
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -635,7 +668,7 @@ __global__ void eig_finish_kernel(const double* __restrict__ lam, const double* 
   for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[(int64_t)i * d + r];
 }
 
-size_t eigh_workspace_doubles(int d) { return d <= 117 ? (size_t)d * d : (size_t)2 * d * d + d + 2; }
+size_t eigh_workspace_doubles(int d) { return d <= 116 ? (size_t)d * d : (size_t)2 * d * d + d + 2; }
 
 static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double* evals, double* comps, int* sweeps,
                                      cudaStream_t st) {
@@ -671,14 +704,10 @@ static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double*
 }
 
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
-  if (d <= 117) {       // two d x d matrices in shared memory
-    const size_t smem1 = (size_t)2 * d * d * sizeof(double);
-    if (smem1 > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-      if (e != cudaSuccess) return e;
-    }
-    jacobi_onesided_kernel<<<1, 1024, smem1, st>>>(A, d, evals, comps, 60, sweeps); count_launch();
-    return cudaGetLastError();
+  if (d <= 116) {       // two d x (d + 2) matrices in shared memory
+    if (d <= 32) return launch_jacobi_small<4>(A, d, evals, comps, sweeps, st);
+    if (d <= 64) return launch_jacobi_small<8>(A, d, evals, comps, sweeps, st);
+    return launch_jacobi_small<16>(A, d, evals, comps, sweeps, st);
   }
   return launch_eigh_large(A, d, V, evals, comps, sweeps, st);
 }

@@ -162,18 +162,19 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                   noise_var=self.noise_var)
         from . import ops as _ops
 
-        def raise_if_nonfinite(Xc, yc):
+        def nonfinite_check(Xc, yc):
+            """(device count of NaN / Inf entries, raiser): the model reads the count together with its
+            other deferred scalars in one transfer and calls the raiser if it is non-zero."""
             bad = _ops.count_nonfinite(Xc, yc)          # enqueued now, read at the first host sync
 
-            def check():
-                if int(bad.cpu()[0]) != 0:
-                    if int(_ops.count_nonfinite(Xc).cpu()[0]) != 0:
-                        raise ValueError("Input X contains NaN or infinity.")
-                    raise ValueError("Input y contains NaN or infinity.")
-            return check
+            def on_bad():
+                if int(_ops.count_nonfinite(Xc).cpu()[0]) != 0:
+                    raise ValueError("Input X contains NaN or infinity.")
+                raise ValueError("Input y contains NaN or infinity.")
+            return bad, on_bad
 
         if isinstance(X, torch.Tensor):
-            return _model.SparseGPRegression(X, y, pre_sync_check=raise_if_nonfinite(X, y), **kw)
+            return _model.SparseGPRegression(X, y, pre_sync_check=lambda: nonfinite_check(X, y), **kw)
         # Host rows: copy them block by block on a side stream while the statistics pass already
         # works on the blocks that have arrived; the non-finite scan (sklearn's check_X_y) runs on the
         # device once the last block is in, before the first host read-back.
@@ -208,7 +209,7 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
         def check():
             loader(0, n)
-            raise_if_nonfinite(Xd, yd)()
+            return nonfinite_check(Xd, yd)
 
         Xd.record_stream(copy_stream)
         return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check, **kw)

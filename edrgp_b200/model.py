@@ -71,23 +71,47 @@ class RBF(object):
 
 
 class Standardize(object):
-    """``GPy.util.normalizer.Standardize`` with the moments reduced on the device / across ranks."""
+    """``GPy.util.normalizer.Standardize`` with the moments reduced on the device / across ranks.
+    Nothing is read back while the model is being built: ``mean`` / ``std`` are fetched on first use."""
 
-    def scale_by_device(self, y_dev, n_total):
+    def scale_by_device(self, y_dev, cnt_dev):
+        """cnt_dev: 1-element device tensor holding this rank's row count; it is summed over ranks
+        in the same collective as the first moment (and left holding the global count)."""
         s1, _ = ops.col_moments(y_dev)
         s1 = s1.clone()
-        dist.allreduce_sum_(s1)
-        mean = s1 / n_total
+        dist.allreduce_sum_(s1, cnt_dev)
+        mean = s1 / cnt_dev
         _, s2 = ops.col_moments(y_dev, shift=mean)
         s2 = s2.clone()
         dist.allreduce_sum_(s2)
-        self.mean = float(mean[0])
-        self.std = float(torch.sqrt(s2 / n_total)[0])
+        self._mean_dev, self._std_dev = mean, torch.sqrt(s2 / cnt_dev)
+        self._mean = self._std = None
+
+    def _fetch(self):
+        if self._mean is None:
+            v = torch.cat([self._mean_dev, self._std_dev]).cpu()
+            self._mean, self._std = float(v[0]), float(v[1])
+
+    @property
+    def mean(self):
+        self._fetch()
+        return self._mean
+
+    @mean.setter
+    def mean(self, v):
+        self._mean = float(v)
+
+    @property
+    def std(self):
+        self._fetch()
+        return self._std
+
+    @std.setter
+    def std(self, v):
+        self._std = float(v)
 
     def normalize_device(self, y_dev):
-        dev = y_dev.device
-        return ops.standardize(y_dev, torch.tensor([self.mean], dtype=F64, device=dev),
-                               torch.tensor([self.std], dtype=F64, device=dev))
+        return ops.standardize(y_dev, self._mean_dev, self._std_dev)
 
     def inverse_mean(self, X):
         return (X * self.std) + self.mean
@@ -134,9 +158,21 @@ class SparseGPRegression(object):
         Yd = _as_device(Y, self.device).reshape(-1)
         if Yd.shape[0] != self.n_local:
             raise ValueError("X and Y row counts differ")
-        cnt = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
-        dist.allreduce_sum_(cnt)
-        self.num_data = int(round(float(cnt[0])))
+        # global row count: reduced together with the normaliser's first moment, read back lazily
+        self._cnt_dev = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
+        self._num_data = None if dist.is_distributed() else self.n_local
+        if normalizer is True:
+            self.normalizer = Standardize()
+        elif normalizer is False or normalizer is None:
+            self.normalizer = None
+        else:
+            self.normalizer = normalizer
+        if self.normalizer is not None:
+            self.normalizer.scale_by_device(Yd, self._cnt_dev)
+            self.Y_normalized = self.normalizer.normalize_device(Yd)
+        else:
+            dist.allreduce_sum_(self._cnt_dev)
+            self.Y_normalized = Yd
         self.kern = RBF(self.input_dim) if kernel is None else kernel
         if self.kern.input_dim != self.input_dim:
             raise ValueError("kernel input_dim does not match X")
@@ -154,17 +190,6 @@ class SparseGPRegression(object):
         self.num_inducing = Zh.shape[0]
         self.noise_variance = float(noise_var)                     # GPy likelihoods.Gaussian() default: 1.0
 
-        if normalizer is True:
-            self.normalizer = Standardize()
-        elif normalizer is False or normalizer is None:
-            self.normalizer = None
-        else:
-            self.normalizer = normalizer
-        if self.normalizer is not None:
-            self.normalizer.scale_by_device(Yd, self.num_data)
-            self.Y_normalized = self.normalizer.normalize_device(Yd)
-        else:
-            self.Y_normalized = Yd
         self.chunk_rows = int(max(1024, min(chunk_rows, max(self.n_local, 1))))
         self.chunk_rows += self.chunk_rows & 1                    # even chunks keep y slices 16-byte aligned
         self.cache_bytes = cache_bytes
@@ -180,6 +205,16 @@ class SparseGPRegression(object):
         self._pre_sync_check = pre_sync_check
         self.parameters_changed()
         self._row_loader = None
+
+    @property
+    def num_data(self):
+        if self._num_data is None:
+            self._num_data = int(round(float(self._cnt_dev.cpu()[0])))
+        return self._num_data
+
+    @num_data.setter
+    def num_data(self, v):
+        self._num_data = int(v)
 
     # -------------------------------------------------------------------------------------------
     # inducing inputs: GPy takes ``X[np.random.permutation(n)[:m]]``; with sharded rows every rank
@@ -312,17 +347,35 @@ class SparseGPRegression(object):
             self._full_chain()
 
     def _run_pre_sync_check(self):
-        if getattr(self, '_pre_sync_check', None) is not None:
-            check, self._pre_sync_check = self._pre_sync_check, None
-            check()
+        """Host-row loader flush + deferred input validation; returns after at most ONE read-back that
+        also brings the row count and the normaliser moments to the host."""
+        check, self._pre_sync_check = getattr(self, '_pre_sync_check', None), None
+        bad, on_bad = check() if check is not None else (None, None)
+        norm = self.normalizer if isinstance(getattr(self, 'normalizer', None), Standardize) else None
+        need_norm = norm is not None and norm._mean is None
+        need_cnt = self._num_data is None
+        info = getattr(self, '_info_dev', None)
+        if bad is None and info is None and not need_norm and not need_cnt:
+            return 0
+        parts = [bad.to(F64) if bad is not None else torch.zeros(1, dtype=F64, device=self.device),
+                 info.to(F64) if info is not None else torch.zeros(1, dtype=F64, device=self.device),
+                 self._cnt_dev]
+        if need_norm:
+            parts += [norm._mean_dev, norm._std_dev]
+        v = torch.cat(parts).cpu()
+        self._info_dev = None
+        self._num_data = int(round(float(v[2])))
+        if need_norm:
+            norm._mean, norm._std = float(v[3]), float(v[4])
+        if float(v[0]) != 0.0:
+            on_bad()
+        return int(v[1])
 
     def _check_pd(self):
         """Deferred failure check of the sync-free fixed path (called before results reach the host)."""
-        self._run_pre_sync_check()
-        if getattr(self, '_info_dev', None) is not None:
-            info, self._info_dev = int(self._info_dev.cpu()[0]), None
-            if info != 0:
-                raise np.linalg.LinAlgError("not positive definite: chol(Kuu + beta P) info=%d" % info)
+        info = self._run_pre_sync_check()
+        if info != 0:
+            raise np.linalg.LinAlgError("not positive definite: chol(Kuu + beta P) info=%d" % info)
 
     def _gradients(self, P, res, beta, sf2, ell, trA, data_fit, yy, ldk):
         dev = self.device

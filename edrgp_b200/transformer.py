@@ -57,8 +57,11 @@ class GramEighTransformer(BaseEstimator, TransformerMixin):
             C = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64), device='cuda')
         d = C.shape[0]
         evals, comps = ops.eigh(C)
-        S2 = np.clip(evals.cpu().numpy(), 0.0, np.inf)
-        comps = comps.cpu().numpy()
+        # one read-back for eigenvalues, eigenvectors and the Gram matrix itself
+        host = torch.cat([evals, comps.reshape(-1), C.reshape(-1)]).cpu().numpy()
+        S2 = np.clip(host[:d], 0.0, np.inf)
+        comps = host[d:d + d * d].reshape(d, d)
+        gram = host[d + d * d:].reshape(d, d)
         total = S2.sum()
         ratio = S2 / total if total > 0 else np.zeros_like(S2)
         nc = self.n_components
@@ -71,7 +74,7 @@ class GramEighTransformer(BaseEstimator, TransformerMixin):
             k = int(np.sum(np.cumsum(ratio) < nc, dtype=int)) + 1
         if n_samples is not None:
             k = min(int(n_samples), k)
-        self.gram_ = C.cpu().numpy()
+        self.gram_ = gram
         self.components_ = comps[:k, :]
         self.subspace_variance_ = S2[:k]
         self.subspace_variance_ratio_ = ratio[:k]

@@ -186,7 +186,7 @@ int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* str
  * Replaces np.linalg.svd(G) in SVDTransformer.fit (edrgp/utils.py:140): comps rows are the right
  * singular vectors of G, evals = S^2, descending.  C is left intact.
  * workspace: edrgp_eigh_workspace_bytes(d).  sweeps (device int, may be NULL) receives the number of
- * Jacobi sweeps used.  d <= 117 runs as one CTA in shared memory and only enqueues; larger d runs
+ * Jacobi sweeps used.  d <= 116 runs as one CTA in shared memory and only enqueues; larger d runs
  * one kernel per round-robin step over all SMs and SYNCHRONISES the stream once per sweep to read
  * the convergence flag (the one exception to "enqueue only").
  * ------------------------------------------------------------------------------------------- */
