@@ -35,6 +35,7 @@ struct GemmTnParams {
   int ka, kb;
   int64_t lda, ldb;
   int sym;         // B == A, only tiles ti <= tj
+  int bn;          // B-side tile width: 128, or 64 in general mode when kb <= 64
   int nta, ntb;    // tiles per edge
   int ntiles;      // general mode: nta * ntb; symmetric mode: off-diagonal tiles ntb (ntb - 1) / 2
   int ksplit;      // row splits of the general / off-diagonal tiles
@@ -118,6 +119,58 @@ __device__ __forceinline__ void diag_consumer(const GemmTnParams& p, const doubl
   }
 }
 
+// Consumer of a full tile: 128 rows of C x BN = 16 NJ columns (BN = 128, or 64 for a narrow B such as
+// the (n, d <= 64) data rows of T^T X, which would leave half of a 128-wide tile empty).
+template <int NJ>
+__device__ __forceinline__ void full_consumer(const GemmTnParams& p, const double* sm, uint64_t* full, uint64_t* empty,
+                                              int nchunks, int ti, int tj, int split) {
+  constexpr int BN = 16 * NJ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;          // warp tile: rows 32*wm.., cols (BN/2)*wn..
+  double acc[4][NJ][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  int stage = 0, ph = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const double* As = sm + (size_t)stage * STAGE_DOUBLES;
+    const double* Bs = As + KC * SS;
+    mbar_wait(&full[stage], ph);
+#pragma unroll
+    for (int ks = 0; ks < KC / 4; ++ks) {
+      const double* ar = As + (4 * ks + t) * SS + 32 * wm + g;
+      const double* br = Bs + (4 * ks + t) * SS + (BN / 2) * wn + g;
+      double a[4], b[NJ];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = ar[8 * i];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) b[j] = br[8 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == SST) { stage = 0; ph ^= 1; }
+  }
+  double* out = p.part + (size_t)split * p.ka * p.kb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ti * TB + 32 * wm + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int cidx = tj * BN + (BN / 2) * wn + 8 * j + 2 * t;
+      if (r < p.ka && cidx < p.kb) {
+        out[(size_t)r * p.kb + cidx] = acc[i][j][0];
+        if (cidx + 1 < p.kb) out[(size_t)r * p.kb + cidx + 1] = acc[i][j][1];
+      }
+    }
+  }
+}
+
 // Operand staging is done by a dedicated producer warp with TMA bulk copies (one 1 KB row slice
 // per lane and operand, SASS UBLKCP) completing on an mbarrier full/empty ring: the 8 compute warps
 // issue nothing but LDS + DMMA in the main loop.  (With cp.async issued by the compute warps the
@@ -169,7 +222,7 @@ __global__ void __launch_bounds__((GT_WARPS + 1) * 32, 1) gemm_tn_kernel(const G
     // ------------------------------ producer ------------------------------
     // 16-byte granules: an odd column count is rounded up (the leading dimensions are even, so the
     // extra column is in bounds; it only feeds output rows / columns that are never written)
-    const int acols = min(TB, p.ka - ti * TB), bcols = min(TB, p.kb - tj * TB);
+    const int acols = min(TB, p.ka - ti * TB), bcols = min(p.bn, p.kb - tj * p.bn);
     const uint32_t abytes = (uint32_t)((acols + 1) & ~1) * 8u, bbytes = diag ? 0u : (uint32_t)((bcols + 1) & ~1) * 8u;
     double yy = 0.0;
     int stage = 0, ph = 0;
@@ -196,7 +249,7 @@ __global__ void __launch_bounds__((GT_WARPS + 1) * 32, 1) gemm_tn_kernel(const G
       __syncwarp();
       if (ok) {
         bulk_g2s(base + lane * SS, p.A + row * p.lda + (int64_t)ti * TB, abytes, &full[stage]);
-        if (!diag) bulk_g2s(base + KC * SS + lane * SS, p.B + row * p.ldb + (int64_t)tj * TB, bbytes, &full[stage]);
+        if (!diag) bulk_g2s(base + KC * SS + lane * SS, p.B + row * p.ldb + (int64_t)tj * p.bn, bbytes, &full[stage]);
       } else {
         // ragged last chunk: rows past the end must read as zeros
         for (int q = 0; q < TB; ++q) { base[lane * SS + q] = 0.0; if (!diag) base[KC * SS + lane * SS + q] = 0.0; }
@@ -226,50 +279,8 @@ __global__ void __launch_bounds__((GT_WARPS + 1) * 32, 1) gemm_tn_kernel(const G
     }
     return;
   }
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;          // warp tile: rows 32*wm.., cols 64*wn..
-  double acc[4][8][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  int stage = 0, ph = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const double* As = sm + (size_t)stage * STAGE_DOUBLES;
-    const double* Bs = As + KC * SS;
-    mbar_wait(&full[stage], ph);
-#pragma unroll
-    for (int ks = 0; ks < KC / 4; ++ks) {
-      const double* ar = As + (4 * ks + t) * SS + 32 * wm + g;
-      const double* br = Bs + (4 * ks + t) * SS + 64 * wn + g;
-      double a[4], b[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = ar[8 * i];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = br[8 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
-    if (++stage == SST) { stage = 0; ph ^= 1; }
-  }
-
-  double* out = p.part + (size_t)split * p.ka * p.kb;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = ti * TB + 32 * wm + 8 * i + g;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int cidx = tj * TB + 64 * wn + 8 * j + 2 * t;
-      if (r < p.ka && cidx < p.kb) {
-        out[(size_t)r * p.kb + cidx] = acc[i][j][0];
-        if (cidx + 1 < p.kb) out[(size_t)r * p.kb + cidx + 1] = acc[i][j][1];
-      }
-    }
-  }
+  if (p.bn == TB) full_consumer<8>(p, sm, full, empty, nchunks, ti, tj, split);
+  else full_consumer<4>(p, sm, full, empty, nchunks, ti, tj, split);
 }
 
 // C (+)= sum over splits of the partials; in symmetric mode only the 8 x 8 blocks on or above the
@@ -342,8 +353,9 @@ static void choose_splits(int ntiles, int ndiag, int sms, int* ko_out, int* kd_o
 }
 
 static void gemm_tn_plan(int64_t n, int ka, int kb, int sym, int sms, GemmTnParams* p) {
+  p->bn = (!sym && kb <= TB / 2) ? TB / 2 : TB;
   p->nta = (ka + TB - 1) / TB;
-  p->ntb = (kb + TB - 1) / TB;
+  p->ntb = (kb + p->bn - 1) / p->bn;
   if (!sym) {
     p->ntiles = p->nta * p->ntb;
     p->ndiag = 0; p->ksplit_diag = 0; p->rows_per_split_diag = KC;

@@ -250,8 +250,9 @@ def gemm_tn(A, B, ka=None, kb=None, out=None, accumulate=False):
         raise ValueError("gemm_tn needs even leading dimensions and matching row counts")
     C = out if out is not None else torch.empty(ka, kb, dtype=F64, device=A.device)
     ws = torch.empty(max(1, lib.edrgp_gemm_tn_workspace_bytes(n, ka, kb) // 8), dtype=F64, device=A.device)
-    _lib.check(lib.edrgp_gemm_tn(_ptr(A), lda, ka, _ptr(B), ldb, kb, n, _ptr(C), kb,
-                                 int(bool(accumulate and out is not None)), _ptr(ws), _stream()), 'edrgp_gemm_tn')
+    with _Timed('gemm_tn'):
+        _lib.check(lib.edrgp_gemm_tn(_ptr(A), lda, ka, _ptr(B), ldb, kb, n, _ptr(C), kb,
+                                     int(bool(accumulate and out is not None)), _ptr(ws), _stream()), 'edrgp_gemm_tn')
     return C
 
 
@@ -343,8 +344,9 @@ def col_moments(X, shift=None, weight=None, out=None, accumulate=False):
     if out is None:
         out = torch.empty(2 * d, dtype=F64, device=X.device)
     ws = torch.empty(lib.edrgp_col_moments_workspace_bytes(d) // 8, dtype=F64, device=X.device)
-    _lib.check(lib.edrgp_col_moments(_ptr(X), n, d, _ptr(shift), _ptr(weight), _ptr(out), acc, _ptr(ws),
-                                     _stream()), 'edrgp_col_moments')
+    with _Timed('col_moments'):
+        _lib.check(lib.edrgp_col_moments(_ptr(X), n, d, _ptr(shift), _ptr(weight), _ptr(out), acc, _ptr(ws),
+                                         _stream()), 'edrgp_col_moments')
     return out[:d], out[d:]
 
 
@@ -369,9 +371,10 @@ def weights(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, want_r
     ws = None
     if want_rowsum or colsum is not None:
         ws = torch.empty(max(1, lib.edrgp_weights_workspace_bytes(n, m) // 8), dtype=F64, device=K.device)
-    _lib.check(lib.edrgp_weights(_ptr(K), n, m, ldk, _ptr(M), M.shape[1], _ptr(y), _ptr(alpha), float(c_ya),
-                                 float(c_km), _ptr(T), 0 if T is None else T.shape[1], _ptr(rowsum), _ptr(colsum),
-                                 int(bool(accumulate)), _ptr(ws), _stream()), 'edrgp_weights')
+    with _Timed('weights'):
+        _lib.check(lib.edrgp_weights(_ptr(K), n, m, ldk, _ptr(M), M.shape[1], _ptr(y), _ptr(alpha), float(c_ya),
+                                     float(c_km), _ptr(T), 0 if T is None else T.shape[1], _ptr(rowsum), _ptr(colsum),
+                                     int(bool(accumulate)), _ptr(ws), _stream()), 'edrgp_weights')
     return rowsum
 
 
