@@ -47,6 +47,7 @@ SIGNATURES = {
     'edrgp_weights': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _c_dp, _c_dp, _dbl, _dbl, _c_dp, _i64, _c_dp,
                              _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_standardize': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_project_dmma': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _c_dp, _i64, _c_dp]),
     'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
 }
 

@@ -280,6 +280,20 @@ int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, con
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "standardize");
 }
 
+int edrgp_project_dmma(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int k, double* out,
+                       int64_t ldo, void* stream) {
+  int rc = check_x("project_dmma", X, n, d, pack, k);
+  if (rc) return rc;
+  if (ldx < d || (ldx & 1)) return fail(EDRGP_ERR_ARG, "project_dmma: ldx must be even and >= d");
+  if (!out || ldo < k || (ldo & 1) || !aligned16(out))
+    return fail(EDRGP_ERR_ARG, "project_dmma: out must be 16-byte aligned with an even leading dimension >= k");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "project_dmma: no CUDA device");
+  cudaError_t e = edrgp::launch_kuf(X, ldx, n, d, pack, k, 1.0, out, ldo, 0, nullptr, nullptr, nullptr, sms,
+                                    (cudaStream_t)stream, 1);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "project_dmma");
+}
+
 int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, double* out, void* stream) {
   if (!X || !V || !out || n <= 0 || d <= 0 || k <= 0) return fail(EDRGP_ERR_ARG, "project: bad argument");
   const int sms = sm_count_cached();

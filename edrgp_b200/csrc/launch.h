@@ -18,7 +18,7 @@ cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int
                                     double* Cpart, int sms, cudaStream_t st);
 cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
                        double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
-                       cudaStream_t st);
+                       cudaStream_t st, int linear = 0);
 
 // C (+)= A^T B (sym: B = A, upper tiles mirrored; optional y: bout[0..ka) (+)= A^T y, bout[ka] (+)= y^T y)
 size_t gemm_tn_workspace_bytes(int64_t n, int ka, int kb, int sym, int sms);

@@ -100,6 +100,7 @@ struct PipeParams {
   int64_t ldx;         // leading dimension of X (>= d): a feature block of a wider matrix can be streamed
   int64_t ldg;         // leading dimension of G
   int mul;             // kuf: multiply the entries already in Kfu by this block's factor (feature-chunked d > 128)
+  int linear;          // kuf: store the plain contraction x . z / l^2 (projection X V^T) instead of the kernel entry
 };
 
 // Producer warp: streams the X row tiles and the inducing tiles of every row tile of this CTA.
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
     mbar_wait(&xfull[xs], xph);
     row_half_norms<DP>(xw, il2s, hxs + r0, lane);
     __syncwarp();
-    const double hx0 = hxs[r0 + g], hx1 = hxs[r0 + g + 8];
+    const double hx0 = p.linear ? 0.0 : hxs[r0 + g], hx1 = p.linear ? 0.0 : hxs[r0 + g + 8];
     const int64_t ra = row0 + r0 + g, rb = ra + 8;
     const bool v0 = ra < p.n, v1 = rb < p.n;
     double y0 = 0.0, y1 = 0.0;
@@ -596,8 +597,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         // entries are stored without the pack coefficient; only the row sums mu carry it
-        double k00 = p.sf2 * exp_neg(fmin(s[0][nb][0], 0.0), etab), k01 = p.sf2 * exp_neg(fmin(s[0][nb][1], 0.0), etab);
-        double k10 = p.sf2 * exp_neg(fmin(s[1][nb][0], 0.0), etab), k11 = p.sf2 * exp_neg(fmin(s[1][nb][1], 0.0), etab);
+        double k00, k01, k10, k11;
+        if (p.linear) {
+          // projection mode: the accumulators started from hz only (hx is zeroed above); take hz back out
+          const double2 h = *reinterpret_cast<const double2*>(zt + MT * S + 8 * nb + 2 * t);
+          k00 = s[0][nb][0] - h.x; k01 = s[0][nb][1] - h.y; k10 = s[1][nb][0] - h.x; k11 = s[1][nb][1] - h.y;
+        } else {
+          k00 = p.sf2 * exp_neg(fmin(s[0][nb][0], 0.0), etab); k01 = p.sf2 * exp_neg(fmin(s[0][nb][1], 0.0), etab);
+          k10 = p.sf2 * exp_neg(fmin(s[1][nb][0], 0.0), etab); k11 = p.sf2 * exp_neg(fmin(s[1][nb][1], 0.0), etab);
+        }
         if (p.mul && j < p.m) {
           // feature-chunked evaluation: exp(-r^2/2) factorises over blocks of features
           if (v0) { const double2 o = *reinterpret_cast<const double2*>(p.Kfu + ra * p.ldk + j); k00 *= o.x; k01 *= o.y; }
@@ -682,7 +690,7 @@ static cudaError_t launch_kuf_s(const PipeParams& p, int grid, cudaStream_t st) 
 template <int DP, int XS, int NS>
 static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) {
   // the pipelined variant needs DP / 16 divisible by 4 (64, 128) to split the next tile's contraction
-  const bool simple = p.Kfu != nullptr && !p.mul && p.b == nullptr && (DP % 64 == 0);
+  const bool simple = p.Kfu != nullptr && !p.mul && !p.linear && p.b == nullptr && (DP % 64 == 0);
   return simple ? launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(p, grid, st) : launch_kuf_s<DP, XS, NS, false>(p, grid, st);
 }
 
@@ -753,9 +761,9 @@ cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int
 
 cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
                        double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
-                       cudaStream_t st) {
+                       cudaStream_t st, int linear) {
   PipeParams p{};
-  p.ldx = ldx; p.ldg = d; p.mul = mul;
+  p.ldx = ldx; p.ldg = d; p.mul = mul; p.linear = linear;
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
   p.ntiles = (n + BM - 1) / BM; p.sf2 = sf2; p.Kfu = Kfu; p.ldk = ldk; p.m = m; p.y = y; p.b = b; p.mu = mu;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);

@@ -33,11 +33,23 @@ F64 = torch.float64
 
 
 def _to_device_rows(X):
+    """Rows on the device.  Host arrays get sklearn's check_array semantics with the O(n d) part on
+    the device: shape / dtype checks here, one copy, the NaN / Inf scan as a device pass."""
     if isinstance(X, torch.Tensor):
         Xd = X.to(dtype=F64)
-        return (Xd if Xd.is_cuda else Xd.cuda()).contiguous()
-    X = check_array(X, dtype=np.float64)
-    return torch.as_tensor(np.ascontiguousarray(X), device='cuda')
+        Xd = (Xd if Xd.is_cuda else Xd.cuda()).contiguous()
+    else:
+        X = np.asarray(X)
+        if X.ndim != 2:
+            raise ValueError("Expected 2D array, got %dD array instead" % X.ndim)
+        if X.shape[0] < 1 or X.shape[1] < 1:
+            raise ValueError("Found array with %d sample(s) and %d feature(s) while a minimum of 1 is required." % X.shape)
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to('cuda', non_blocking=True)
+    if Xd.dim() != 2:
+        raise ValueError("Expected 2D rows")
+    if Xd.numel() and int(ops.count_nonfinite(Xd).cpu()[0]) != 0:
+        raise ValueError("Input X contains NaN or infinity.")
+    return Xd
 
 
 def _to_device_targets(y, n):
@@ -46,12 +58,13 @@ def _to_device_targets(y, n):
         yd = yd if yd.is_cuda else yd.cuda()
     else:
         y = np.asarray(y, dtype=np.float64).reshape(-1)
-        if not np.all(np.isfinite(y)):
-            raise ValueError("Input y contains NaN or infinity.")
-        yd = torch.as_tensor(np.ascontiguousarray(y), device='cuda')
+        yd = torch.from_numpy(np.ascontiguousarray(y)).to('cuda', non_blocking=True)
     if yd.shape[0] != n:
         raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]" % (n, yd.shape[0]))
-    return yd.contiguous()
+    yd = yd.contiguous()
+    if yd.numel() and int(ops.count_nonfinite(yd).cpu()[0]) != 0:
+        raise ValueError("Input y contains NaN or infinity.")
+    return yd
 
 
 class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):

@@ -406,13 +406,24 @@ def standardize(X, mean, scale, out=None):
 
 
 def project(X, V):
-    """X (n, d) @ V^T with V (k, d): EDR.transform."""
+    """X (n, d) @ V^T with V (k, d): EDR.transform.  Few components: one streaming pass (a warp per
+    row); many components (k > 8, d <= 128): the FP64 tensor-pipe contraction of the Kfu kernel."""
     lib = _lib.load()
     _need_cuda(X, V)
     n, d = X.shape
     k = V.shape[0]
+    if k > 8 and d + (d & 1) <= 128 and n > 0:
+        Xe = pad_even(X)
+        pack = InducingPack(V.contiguous(), torch.ones(d, dtype=F64, device=X.device))
+        ldo = k + (k & 1)
+        out = torch.empty(n, ldo, dtype=F64, device=X.device)
+        with _Timed('project'):
+            _lib.check(lib.edrgp_project_dmma(_ptr(Xe), Xe.shape[1], n, Xe.shape[1], _ptr(pack.buf), k, _ptr(out), ldo,
+                                              _stream()), 'edrgp_project_dmma')
+        return out if ldo == k else out[:, :k].contiguous()
     out = torch.empty(n, k, dtype=F64, device=X.device)
-    _lib.check(lib.edrgp_project(_ptr(X), n, d, _ptr(V), k, _ptr(out), _stream()), 'edrgp_project')
+    with _Timed('project'):
+        _lib.check(lib.edrgp_project(_ptr(X), n, d, _ptr(V), k, _ptr(out), _stream()), 'edrgp_project')
     return out
 
 

@@ -207,6 +207,11 @@ int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void
  /* edrgp_count_nonfinite: count[0] += #(NaN or Inf entries) of a dense buffer of `total` doubles:
  *      the non-finite scan of sklearn's check_X_y / check_array (edrgp/gp_model/base.py:87,105). */
 int edrgp_count_nonfinite(const double* X, int64_t total, unsigned int* count, void* stream);
+ /* edrgp_project_dmma: the same projection on the FP64 tensor pipe for many components (k > 8):
+ *      out (n, ldo) = X (n, ldx)[:, :d] V^T with V given as an inducing pack built from V with unit
+ *      lengthscales (edrgp_pack_inducing(V, ones, NULL, 1, k, d, ...)); d <= 128, ldo even. */
+int edrgp_project_dmma(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int k,
+                       double* out, int64_t ldo, void* stream);
 size_t edrgp_col_moments_workspace_bytes(int d);
 int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
                       double* out, int accumulate, void* workspace, void* stream);

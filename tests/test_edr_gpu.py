@@ -175,3 +175,17 @@ def test_device_pca_matches_sklearn_and_chains():
     b = make(eb.DevicePCA(n_components=2)).fit(Xw, y, max_iters=0)
     assert a.components_.shape == b.components_.shape == (1, 4)
     assert op.principal_angle(a.components_, b.components_) < 1e-6
+
+
+def test_edr_rejects_bad_input():
+    X, y, _ = _make(200, 5, 2, seed=9)
+    Xb = X.copy(); Xb[3, 2] = np.nan
+    with pytest.raises(ValueError):
+        _edr(k=2, m=10).fit(Xb, y, max_iters=0)
+    yb = y.copy(); yb[5] = np.inf
+    with pytest.raises(ValueError):
+        _edr(k=2, m=10).fit(X, yb, max_iters=0)
+    with pytest.raises(ValueError):
+        _edr(k=2, m=10).fit(X, y[:-1], max_iters=0)
+    with pytest.raises(ValueError):
+        _edr(k=2, m=10).fit(X[:, 0], y, max_iters=0)

@@ -139,3 +139,16 @@ def test_cached_kfu_gradients_match_recompute_and_oracle(n, d, m):
     assert float((G - G2).abs().max()) <= 1e-13 * float(G2.abs().max())
     _, C3 = ops.grad_gram_cached(_dev(X), Kbuf, cpack, sf2, want_G=False)
     assert torch.equal(C, C3)
+
+
+@pytest.mark.parametrize("n,d,k", [(1000, 10, 3), (5000, 64, 61), (3001, 33, 20), (2000, 128, 128), (777, 200, 40), (64, 8, 9)])
+def test_projection_matches_numpy(n, d, k):
+    """EDR.transform: the streaming kernel (few components / wide inputs) and the tensor-pipe path."""
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(n + k)
+    X = rng.standard_normal((n, d)) * 3.0 + 1.0
+    V = rng.standard_normal((k, d))
+    out = ops.project(_dev(X), _dev(V)).cpu().numpy()
+    ref = X.dot(V.T)
+    assert out.shape == (n, k)
+    assert _relerr(out, ref) < 1e-13
