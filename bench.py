@@ -215,15 +215,18 @@ def run_ours(args):
 
     def make_estimator():
         return eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, SF2, ell, ARD=True), Z=Z, normalizer=True,
-                                                 method='fixed', noise_var=NOISE, chunk_rows=args.chunk_rows)
+                                                 method='fixed', noise_var=NOISE, chunk_rows=args.chunk_rows,
+                                                 deferred_checks=True)
 
     def sweep(Xin, yin):
-        """One fixed-hyper-parameter EDR sweep through the public classes."""
+        """One fixed-hyper-parameter EDR sweep through the public classes.  The input validation and
+        the Cholesky flag are computed on the device inside the sweep and read (and raised) once, after
+        the directions have been read back: no host round trip between the row passes."""
         est = make_estimator().fit(Xin, yin)
-        _, C = est.estimator_.gradient_gram(want_G=False)
-        C = C.clone()
+        _, C = est.estimator_.gradient_gram(want_G=False, check=False)
         edist.allreduce_sum_(C)
         tr = eb.GramEighTransformer(n_components=K_TRUE).fit_gram(C, n)
+        est.estimator_.finish_checks()
         return tr.components_
 
     def barrier():

@@ -6,6 +6,7 @@
 // m <= a few thousand and d <= a few hundred: ~m^3 flops against the ~n m^2 of the statistics
 // pass, so the kernels are written for clarity and determinism (32 x 32 blocks, no atomics), not
 // for the last TFLOP.  All matrices are row-major.
+#include <cstdlib>
 #include "common.cuh"
 #include "launch.h"
 
@@ -436,16 +437,25 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 // ---------------------------------------------------------------------------------------------
 // Symmetric eigensolver (positive semi-definite input): one-sided cyclic Jacobi.
 // ---------------------------------------------------------------------------------------------
-constexpr int EIG_R = 8;                    // rows per lane
+// L lanes per column pair (32 / L pairs per warp), R rows per lane: d <= L R.  The solver is bound by
+// the LATENCY of one round-robin step (shared-memory loads -> three dot products -> lane reduction ->
+// rotation parameters -> column update -> block barrier), not by work: 64 columns give 32 independent
+// pairs per step and ~600 dependent steps.  So the step is kept short: few rows per lane (more warps
+// with shorter chains), the V columns are fetched before the parameters are derived, the pair schedule
+// needs no division, and the rotation comes from two reciprocal square roots (no divide):
+//     h = sqrt(diff^2 + 4 gamma^2), cos 2t = |diff| / h,  c = sqrt((1 + cos 2t) / 2),
+//     s = sign(diff) gamma / (h c)            (|t| <= pi / 4, c^2 + s^2 = 1 to rounding)
+// evaluated on operands scaled by a power of two so that the FP32 seeds stay in range.
+// EDRGP_JACOBI_VARIANT (tuning aid, read once): 0 = default lanes / rows split, 1 = fewer lanes, 2 = a warp per pair
+static int jacobi_variant() {
+  static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : 0; }();
+  return v;
+}
 
-// L lanes per column pair (32 / L pairs per warp): d <= 8 L.  Fewer, fuller warps than one warp per
-// pair: the rotation parameters are derived once per warp instruction for 32 / L pairs at a time,
-// which is what the solver's time goes into (issue slots of the FP64 sequences), and the block-wide
-// barrier per step spans fewer warps.
-template <int L>
-__global__ void __launch_bounds__(L == 16 ? 1024 : 256) jacobi_onesided_kernel(const double* __restrict__ C, int d,
-                                                               double* __restrict__ evals, double* __restrict__ comps,
-                                                               int max_sweeps, int* __restrict__ sweeps_out) {
+template <int L, int R>
+__global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
+    const double* __restrict__ C, int d, double* __restrict__ evals, double* __restrict__ comps, int max_sweeps,
+    int* __restrict__ sweeps_out) {
   extern __shared__ double sh[];
   const int ds = d + 1 + ((d + 1) & 1);       // column stride: breaks the power-of-two bank pattern
   double* W = sh;                             // [d][ds] column-major: W[c * ds + r]
@@ -467,20 +477,37 @@ __global__ void __launch_bounds__(L == 16 ? 1024 : 256) jacobi_onesided_kernel(c
     __syncthreads();
     for (int step = 0; step < dd - 1; ++step) {
       int p = 0, q = d;
-      if (active) {
-        const int a0 = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
-        const int b0 = (step + dd - 1 - k) % (dd - 1);
+      if (active) {                           // round-robin tournament; step, k < dd - 1: one conditional subtract
+        int a0 = step + k, b0 = step + dd - 1 - k;
+        if (a0 >= dd - 1) a0 -= dd - 1;
+        if (b0 >= dd - 1) b0 -= dd - 1;
+        if (k == 0) a0 = dd - 1;
         p = min(a0, b0); q = max(a0, b0);
       }
       const bool live = active && q < d;      // q == d: the bye of an odd dimension / idle slot
-      double wa[EIG_R], wb[EIG_R];
+      double* Wp = W + p * ds + l;
+      double* Wq = W + (live ? q : p) * ds + l;
+      double* Vp = V + p * ds + l;
+      double* Vq = V + (live ? q : p) * ds + l;
+      constexpr bool HOIST = R <= 4;          // V columns fetched ahead of the rotation parameters (register budget)
+      double wa[R], wb[R], va[HOIST ? R : 1], vb[HOIST ? R : 1];
       double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
-      for (int e = 0; e < EIG_R; ++e) {
-        const int r = l + L * e;
-        const bool ok = live && r < d;
-        wa[e] = ok ? W[p * ds + r] : 0.0;
-        wb[e] = ok ? W[q * ds + r] : 0.0;
+      for (int e = 0; e < R; ++e) {
+        const bool ok = live && l + L * e < d;
+        wa[e] = ok ? Wp[L * e] : 0.0;
+        wb[e] = ok ? Wq[L * e] : 0.0;
+      }
+      if (HOIST) {
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          const bool ok = live && l + L * e < d;
+          va[HOIST ? e : 0] = ok ? Vp[L * e] : 0.0;
+          vb[HOIST ? e : 0] = ok ? Vq[L * e] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < R; ++e) {
         alpha = fma(wa[e], wa[e], alpha); beta = fma(wb[e], wb[e], beta); gamma = fma(wa[e], wb[e], gamma);
       }
 #pragma unroll
@@ -490,28 +517,31 @@ __global__ void __launch_bounds__(L == 16 ? 1024 : 256) jacobi_onesided_kernel(c
         gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
       }
       if (live && gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
-        double tt;
-        const double ag = fabs(gamma), diff = beta - alpha;
-        if (ag > 1e-30 && ag < 1e30 && fabs(diff) < 1e15 * ag) {
-          const double zeta = diff * fast_rcp(2.0 * gamma);
-          const double w = fma(zeta, zeta, 1.0);                    // < 1e30
-          const double den = fabs(zeta) + w * fast_rsqrt(w);       // |zeta| + sqrt(1 + zeta^2) >= 1
-          tt = (zeta >= 0.0 ? 1.0 : -1.0) * fast_rcp(den);
-        } else {                                                    // out of the estimates' range: IEEE path
-          const double zeta = diff / (2.0 * gamma);
-          tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c, s;
+        const double sum = alpha + beta;
+        const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
+        if (ex > 64 && ex < 1983) {                                 // 2^-959 < alpha + beta < 2^960
+          const double scale = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex): sum * scale in [1, 2)
+          const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;   // both in [-2, 2]
+          const double ih = fast_rsqrt(fma(dn, dn, gn * gn));       // argument in [~1e-31, 8]
+          const double x = fma(0.5 * fabs(dn), ih, 0.5);            // (1 + cos 2t) / 2 in [0.5, 1]
+          const double r = fast_rsqrt(x);
+          c = x * r;
+          s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
+        } else {                                                    // out of the scaled range: IEEE path
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
         }
-        const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
         if (l == 0) rotated = 1;
 #pragma unroll
-        for (int e = 0; e < EIG_R; ++e) {
-          const int r = l + L * e;
-          if (r < d) {
-            W[p * ds + r] = c * wa[e] - s * wb[e];
-            W[q * ds + r] = s * wa[e] + c * wb[e];
-            const double va = V[p * ds + r], vb = V[q * ds + r];
-            V[p * ds + r] = c * va - s * vb;
-            V[q * ds + r] = s * va + c * vb;
+        for (int e = 0; e < R; ++e) {
+          if (l + L * e < d) {
+            Wp[L * e] = c * wa[e] - s * wb[e];
+            Wq[L * e] = s * wa[e] + c * wb[e];
+            const double x = HOIST ? va[HOIST ? e : 0] : Vp[L * e], y = HOIST ? vb[HOIST ? e : 0] : Vq[L * e];
+            Vp[L * e] = c * x - s * y;
+            Vq[L * e] = s * x + c * y;
           }
         }
       }
@@ -521,60 +551,71 @@ __global__ void __launch_bounds__(L == 16 ? 1024 : 256) jacobi_onesided_kernel(c
     __syncthreads();
   }
   if (tid == 0 && sweeps_out) *sweeps_out = sweep;
-  // eigenvalues: Rayleigh quotients v^T C v against the input, one warp per vector
+  // eigenvalues: Rayleigh quotients v^T C v against the input (C is symmetric: read it by rows so that
+  // the lanes of a warp touch consecutive addresses), one warp per vector, four independent chains
   const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
   double* lam = W;                      // reused once every warp is done with W
   __syncthreads();
-  double mine[8];
-  int cnt = 0;
-  for (int i = warp; i < d && cnt < 8; i += nwarps, ++cnt) {
+  for (int i0 = 0; i0 < d; i0 += nwarps) {
+    const int i = i0 + warp;
     double acc = 0.0;
-    for (int r = lane; r < d; r += 32) {
-      double cv = 0.0;
-      for (int kk = 0; kk < d; ++kk) cv = fma(C[(int64_t)r * d + kk], V[i * ds + kk], cv);
-      acc = fma(V[i * ds + r], cv, acc);
-    }
+    if (i < d) {
+      const double* v = V + i * ds;
+      for (int r = lane; r < d; r += 32) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        int kk = 0;
+        for (; kk + 3 < d; kk += 4) {
+          c0 = fma(C[(int64_t)kk * d + r], v[kk], c0);
+          c1 = fma(C[(int64_t)(kk + 1) * d + r], v[kk + 1], c1);
+          c2 = fma(C[(int64_t)(kk + 2) * d + r], v[kk + 2], c2);
+          c3 = fma(C[(int64_t)(kk + 3) * d + r], v[kk + 3], c3);
+        }
+        for (; kk < d; ++kk) c0 = fma(C[(int64_t)kk * d + r], v[kk], c0);
+        acc = fma(v[r], (c0 + c1) + (c2 + c3), acc);
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    mine[cnt] = acc;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (i < d && lane == 0) lam[i] = acc;
   }
   __syncthreads();
-  cnt = 0;
-  for (int i = warp; i < d && cnt < 8; i += nwarps, ++cnt)
-    if (lane == 0) lam[i] = mine[cnt];
-  __syncthreads();
-  // sort descending by rank counting, write components as rows with a fixed sign
-  for (int i = tid; i < d; i += nt) {
+  // sort descending by rank counting, write components as rows with a fixed sign (the first entry of
+  // largest magnitude is made positive): a warp per vector
+  for (int i = warp; i < d; i += nwarps) {
     const double li = lam[i];
-    int rank = 0;
-    for (int j = 0; j < d; ++j) {
+    int rank = 0, bestj = d;
+    double best = 0.0;
+    for (int j = lane; j < d; j += 32) {
       const double lj = lam[j];
       rank += (lj > li) || (lj == li && j < i);
+      const double v = V[i * ds + j];
+      if (fabs(v) > fabs(best)) { best = v; bestj = j; }
     }
-    evals[rank] = li;
-    double best = 0.0;
-    for (int r = 0; r < d; ++r) {
-      const double v = V[i * ds + r];
-      if (fabs(v) > fabs(best)) best = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rank += __shfl_xor_sync(0xffffffffu, rank, o);
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+      if (fabs(ob) > fabs(best) || (fabs(ob) == fabs(best) && oj < bestj)) { best = ob; bestj = oj; }
     }
     const double sgn = best < 0.0 ? -1.0 : 1.0;
-    for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[i * ds + r];
+    if (lane == 0) evals[rank] = li;
+    for (int r = lane; r < d; r += 32) comps[(int64_t)rank * d + r] = sgn * V[i * ds + r];
   }
 }
 
-template <int L>
+template <int L, int R>
 static cudaError_t launch_jacobi_small(const double* C, int d, double* evals, double* comps, int* sweeps, cudaStream_t st) {
   const int ds = d + 1 + ((d + 1) & 1);
   const size_t smem = (size_t)2 * d * ds * sizeof(double);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel<L, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const int np = (d + 1) / 2;
   int threads = ((np * L + 31) / 32) * 32;
-  if (threads < 128) threads = 128;            // at least 4 warps for the Rayleigh / output phase (<= 8 vectors per warp needs d <= 8 * warps)
-  while ((threads / 32) * 8 < d) threads += 32;
-  jacobi_onesided_kernel<L><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps); count_launch();
+  if (threads < 128) threads = 128;            // at least 4 warps for the Rayleigh / output phase
+  jacobi_onesided_kernel<L, R><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps); count_launch();
   return cudaGetLastError();
 }
 
@@ -705,9 +746,17 @@ static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double*
 
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st) {
   if (d <= 116) {       // two d x (d + 2) matrices in shared memory
-    if (d <= 32) return launch_jacobi_small<4>(A, d, evals, comps, sweeps, st);
-    if (d <= 64) return launch_jacobi_small<8>(A, d, evals, comps, sweeps, st);
-    return launch_jacobi_small<16>(A, d, evals, comps, sweeps, st);
+    // lanes per pair x rows per lane: threads = pairs x lanes (d = 64: 32 x 16 = 512; d = 116: 58 x 16 = 928)
+    const int variant = jacobi_variant();
+    if (d <= 16) return launch_jacobi_small<4, 4>(A, d, evals, comps, sweeps, st);
+    if (d <= 32) return variant == 1 ? launch_jacobi_small<4, 8>(A, d, evals, comps, sweeps, st)
+                                     : launch_jacobi_small<8, 4>(A, d, evals, comps, sweeps, st);
+    if (d <= 64) {
+      if (variant == 1) return launch_jacobi_small<8, 8>(A, d, evals, comps, sweeps, st);
+      if (variant == 2) return launch_jacobi_small<32, 2>(A, d, evals, comps, sweeps, st);
+      return launch_jacobi_small<16, 4>(A, d, evals, comps, sweeps, st);
+    }
+    return launch_jacobi_small<16, 8>(A, d, evals, comps, sweeps, st);
   }
   return launch_eigh_large(A, d, V, evals, comps, sweeps, st);
 }

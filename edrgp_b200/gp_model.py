@@ -37,7 +37,8 @@ class _BaseGP(BaseEstimator):
             opt_kws.setdefault('messages', False)
             opt_kws.setdefault('max_iters', 1000)
             getattr(model, self.method)(**opt_kws)
-            model._check_pd()          # deferred input / positive-definiteness checks surface here
+            if not getattr(self, 'deferred_checks', False):
+                model._check_pd()      # deferred input / positive-definiteness checks surface here
         except Exception:
             # a failed fit leaves the estimator as it was (the reference validates before it builds)
             for k in ('n_features_', 'estimator_'):
@@ -138,11 +139,17 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
     ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time, and
     ``noise_var`` sets the initial Gaussian noise variance (GPy's default 1.0; the dense
     ``GaussianProcessRegressor`` of the reference has the same parameter).
+    ``deferred_checks=True`` keeps ``fit`` from synchronising with the device: the non-finite scan
+    of the input (sklearn's ``check_X_y``) and the positive-definiteness flag of the Cholesky step
+    are still computed, but they are read -- and raise -- at the first host read-back
+    (``predict*``, ``estimator_.gradient_gram(check=True)`` or ``estimator_.finish_checks()``)
+    instead of inside ``fit``.  With row shards of a few hundred thousand points per GPU that one
+    round trip is a visible part of a sweep.
     """
 
     def __init__(self, kernels=None, kernel_options=None, Z=None, num_inducing=10, Y_metadata=None,
                  X_variance=None, normalizer=True, mean_function=None, method='optimize', chunk_rows=262144,
-                 noise_var=1.0):
+                 noise_var=1.0, deferred_checks=False):
         self.kernels = kernels
         self.kernel_options = kernel_options
         self.Z = Z
@@ -154,6 +161,7 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         self.method = method
         self.chunk_rows = chunk_rows
         self.noise_var = noise_var
+        self.deferred_checks = deferred_checks
 
     def _get_model(self, X, y, kernel):
         import torch

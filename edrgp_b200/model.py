@@ -126,6 +126,26 @@ def _as_device(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device, non_blocking=True)
 
 
+_STAGING = {}                 # (device index, doubles) -> [pinned tensor, event of its last copy]
+
+
+def _upload(a, device):
+    """Small host array -> device through a reusable pinned staging buffer, so that the copy is
+    asynchronous (a pageable source makes the driver wait for the stream before it returns)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    key = (torch.device(device).index, a.size)
+    slot = _STAGING.get(key)
+    if slot is None:
+        slot = _STAGING[key] = [torch.empty(a.size, dtype=F64, pin_memory=True), None]
+    if slot[1] is not None:
+        slot[1].synchronize()                      # the previous copy out of this buffer (long done)
+    slot[0].numpy()[:] = a.ravel()
+    out = slot[0].to(device, non_blocking=True).view(a.shape)
+    slot[1] = torch.cuda.Event()
+    slot[1].record()
+    return out
+
+
 def _backsub_both_sides(L, X, transpose='left'):
     """GPy.util.linalg.backsub_both_sides on the device: L^-T X L^-1 ('left') or L^-1 X L^-T."""
     trans = transpose == 'left'
@@ -167,17 +187,16 @@ class SparseGPRegression(object):
             self.normalizer = None
         else:
             self.normalizer = normalizer
-        if self.normalizer is not None:
-            self.normalizer.scale_by_device(Yd, self._cnt_dev)
-            self.Y_normalized = self.normalizer.normalize_device(Yd)
-        else:
-            dist.allreduce_sum_(self._cnt_dev)
-            self.Y_normalized = Yd
+        # the target moments are reduced lazily: right AFTER the first cross-covariance block has been
+        # enqueued (which does not need y), so the device is never idle behind this host-side set-up
+        self._Y_raw = Yd
+        self._Y_normalized = None
         self.kern = RBF(self.input_dim) if kernel is None else kernel
         if self.kern.input_dim != self.input_dim:
             raise ValueError("kernel input_dim does not match X")
 
         if Z is None:
+            self._ensure_y()                         # the draw needs the global row count
             if row_loader is not None:               # the draw gathers arbitrary rows: load them all now
                 row_loader(0, self.n_local)
                 row_loader = None
@@ -206,9 +225,25 @@ class SparseGPRegression(object):
         self.parameters_changed()
         self._row_loader = None
 
+    def _ensure_y(self):
+        """Normalised targets (GPy ``Standardize``) and the global row count, reduced over ranks."""
+        if self._Y_normalized is None:
+            if self.normalizer is not None:
+                self.normalizer.scale_by_device(self._Y_raw, self._cnt_dev)
+                self._Y_normalized = self.normalizer.normalize_device(self._Y_raw)
+            else:
+                dist.allreduce_sum_(self._cnt_dev)
+                self._Y_normalized = self._Y_raw
+        return self._Y_normalized
+
+    @property
+    def Y_normalized(self):
+        return self._ensure_y()
+
     @property
     def num_data(self):
         if self._num_data is None:
+            self._ensure_y()
             self._num_data = int(round(float(self._cnt_dev.cpu()[0])))
         return self._num_data
 
@@ -269,10 +304,10 @@ class SparseGPRegression(object):
         sf2 = float(self.kern.variance)
         ell = np.ones(self.d_even)
         ell[:d] = self.kern.full_lengthscale()
-        self._ell_dev = torch.as_tensor(ell, device=dev)
+        self._ell_dev = _upload(ell, dev)
         Zp = np.zeros((m, self.d_even))
         Zp[:, :d] = self.Z
-        self._Z_dev = torch.as_tensor(Zp, device=dev)
+        self._Z_dev = _upload(Zp, dev)
         beta = 1.0 / max(float(self.noise_variance), CONST_JITTER)
         need_grad = self._need_grad
         # the stored Kfu blocks are reused by the gradient passes when the whole matrix fits
@@ -281,15 +316,16 @@ class SparseGPRegression(object):
         self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
         P = torch.empty(m, m, dtype=F64, device=dev)
         byy = torch.empty(m + 1, dtype=F64, device=dev)
-        y = self.Y_normalized
         for i, (s, e) in enumerate(self._chunks()):
             if self._row_loader is not None:
                 self._row_loader(s, e)
             Kc = self._Kcache[s:e] if self._Kcache is not None else self._Kbuf[:e - s]
             ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
+            y = self._ensure_y()
             ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
             self.kernel_launches += 4
         if self.n_local == 0:
+            self._ensure_y()
             P.zero_(); byy.zero_()
         dist.allreduce_sum_(P, byy)
         self._stats = (P, byy)
@@ -316,6 +352,7 @@ class SparseGPRegression(object):
             self.alpha = v                                       # GPy posterior.woodbury_vector (m,)
             self._info_dev = info
             self.kernel_launches += 40
+            self._enqueue_checks()
 
     def _full_chain(self):
         """GPy's VarDTC Cholesky chain from the reduced statistics: Lm, LB, alpha, bound."""
@@ -346,28 +383,47 @@ class SparseGPRegression(object):
         if self._solve is None:
             self._full_chain()
 
-    def _run_pre_sync_check(self):
-        """Host-row loader flush + deferred input validation; returns after at most ONE read-back that
-        also brings the row count and the normaliser moments to the host."""
+    def _enqueue_checks(self):
+        """Host-row loader flush + deferred input validation, enqueued (nothing is read back): the
+        non-finite count, the Cholesky flag, the row count and the normaliser moments are packed into
+        one small device tensor that ``_run_pre_sync_check`` fetches in ONE transfer."""
         check, self._pre_sync_check = getattr(self, '_pre_sync_check', None), None
         bad, on_bad = check() if check is not None else (None, None)
+        if getattr(self, '_Y_raw', None) is not None:
+            self._ensure_y()
         norm = self.normalizer if isinstance(getattr(self, 'normalizer', None), Standardize) else None
         need_norm = norm is not None and norm._mean is None
-        need_cnt = self._num_data is None
         info = getattr(self, '_info_dev', None)
-        if bad is None and info is None and not need_norm and not need_cnt:
-            return 0
-        parts = [bad.to(F64) if bad is not None else torch.zeros(1, dtype=F64, device=self.device),
-                 info.to(F64) if info is not None else torch.zeros(1, dtype=F64, device=self.device),
-                 self._cnt_dev]
+        self._info_dev = None
+        if bad is None and info is None and not need_norm and self._num_data is not None:
+            return
+        old = getattr(self, '_pending', None)
+        if old is not None:                       # flags of an earlier, still unread evaluation stay armed
+            prev, prev_on_bad, _ = old
+            bad = prev[0:1] if bad is None else bad.to(F64) + prev[0:1]
+            on_bad = on_bad or prev_on_bad
+            info = prev[1:2] if info is None else info            # the latest factorisation's flag wins
+        zero = None
+        if bad is None or info is None:
+            zero = torch.zeros(1, dtype=F64, device=self.device)
+        parts = [bad.to(F64) if bad is not None else zero, info.to(F64) if info is not None else zero, self._cnt_dev]
         if need_norm:
             parts += [norm._mean_dev, norm._std_dev]
-        v = torch.cat(parts).cpu()
-        self._info_dev = None
+        self._pending = (torch.cat(parts), on_bad, norm if need_norm else None)
+
+    def _run_pre_sync_check(self):
+        """Fetch what ``_enqueue_checks`` packed (at most ONE read-back, which also brings the row count
+        and the normaliser moments to the host); returns the Cholesky flag."""
+        self._enqueue_checks()
+        pending, self._pending = getattr(self, '_pending', None), None
+        if pending is None:
+            return 0
+        flat, on_bad, norm = pending
+        v = flat.cpu()
         self._num_data = int(round(float(v[2])))
-        if need_norm:
+        if norm is not None and norm._mean is None:
             norm._mean, norm._std = float(v[3]), float(v[4])
-        if float(v[0]) != 0.0:
+        if float(v[0]) != 0.0 and on_bad is not None:
             on_bad()
         return int(v[1])
 
@@ -376,6 +432,12 @@ class SparseGPRegression(object):
         info = self._run_pre_sync_check()
         if info != 0:
             raise np.linalg.LinAlgError("not positive definite: chol(Kuu + beta P) info=%d" % info)
+
+    def finish_checks(self):
+        """Raise what the deferred checks found (non-finite input: ValueError; Kuu + beta P not
+        positive definite: LinAlgError).  One small read-back the first time, nothing afterwards."""
+        self._check_pd()
+        return self
 
     def _gradients(self, P, res, beta, sf2, ell, trA, data_fit, yy, ldk):
         dev = self.device
@@ -559,18 +621,32 @@ class SparseGPRegression(object):
     # prediction surface
     # -------------------------------------------------------------------------------------------
     def _grad_scale(self, scale_by_normalizer=True):
+        """std(y) of the normaliser (newer GPy scales the Jacobian by it): a float once it has reached
+        the host, otherwise the 1-element device tensor, so that nothing is read back mid-sweep."""
         if self.normalizer is not None and scale_by_normalizer:
-            return float(self.normalizer.std)
+            norm = self.normalizer
+            if isinstance(norm, Standardize) and norm._std is None:
+                return norm._std_dev
+            return float(norm.std)
         return 1.0
 
-    def _grad_pack(self, scale):
-        return ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, float(self.kern.variance) * scale)
+    def _grad_coef(self, scale, factor=1.0):
+        """(coef, coef_scale) for an inducing pack carrying alpha * factor * scale."""
+        if isinstance(scale, torch.Tensor):
+            return self.alpha * scale, float(factor)
+        return self.alpha, float(factor) * scale
 
-    def gradient_gram(self, X=None, want_G=False, want_C=True, scale_by_normalizer=True, G_out=None):
+    def _grad_pack(self, scale):
+        coef, cs = self._grad_coef(scale, float(self.kern.variance))
+        return ops.InducingPack(self._Z_dev, self._ell_dev, coef, cs)
+
+    def gradient_gram(self, X=None, want_G=False, want_C=True, scale_by_normalizer=True, G_out=None, check=True):
         """Posterior-mean gradients of this rank's rows and their Gram matrix, on the device.
 
         Returns ``(G or None, C or None)``; C is NOT reduced across ranks (callers all-reduce it
-        together with whatever else they need).  ``X=None`` uses the training rows.
+        together with whatever else they need).  ``X=None`` uses the training rows.  ``check=False``
+        leaves the deferred input / positive-definiteness checks pending (no host synchronisation
+        here): the caller runs ``finish_checks()`` before it trusts what it read back.
         """
         Xd = self.X if X is None else ops.pad_even(_as_device(X, self.device))
         scale = self._grad_scale(scale_by_normalizer)
@@ -582,7 +658,7 @@ class SparseGPRegression(object):
         sf2 = float(self.kern.variance)
         if use_cache and self.d_even <= 64:
             # training rows with their cross-covariance already in HBM: no Kuf recompute, no exp
-            pack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale, block=64)
+            pack = ops.InducingPack(self._Z_dev, self._ell_dev, *self._grad_coef(scale), block=64)
             G, C = ops.grad_gram_cached(Xd, self._Kcache, pack, sf2, want_G=want_G, want_C=want_C, G_out=G_out)
             self.kernel_launches += 3
         elif not use_cache and self.d_even <= 128:
@@ -597,7 +673,7 @@ class SparseGPRegression(object):
         else:
             # any width: row blocks of the stored (or freshly written) Kfu feed the cached-gradient
             # kernel one 64-feature block at a time; the Gram matrix accumulates on the DMMA reduction
-            gpack = ops.InducingPack(self._Z_dev, self._ell_dev, self.alpha, scale, block=64)
+            gpack = ops.InducingPack(self._Z_dev, self._ell_dev, *self._grad_coef(scale), block=64)
             kpack = None if use_cache else ops.InducingPack(self._Z_dev, self._ell_dev)
             nrow = Xd.shape[0]
             rows = min(self.chunk_rows, nrow)
@@ -624,7 +700,8 @@ class SparseGPRegression(object):
                 G = G[:, :d].contiguous()
             if C is not None:
                 C = C[:d, :d].contiguous()
-        self._check_pd()
+        if check:
+            self._check_pd()
         return (G if want_G else None), C
 
 
