@@ -85,6 +85,34 @@ int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf");
 }
 
+size_t edrgp_pack_tf32_bytes(int m, int d) {
+  if (m <= 0 || d <= 0 || d > 64) return 0;
+  return edrgp::pack_tf32_bytes(m, d);
+}
+
+int edrgp_pack_inducing_tf32(const double* Z, const double* ell, int m, int d, void* pack, void* stream) {
+  if (!Z || !ell || !pack || m <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "pack_inducing_tf32: bad argument");
+  if (d > 64) return fail(EDRGP_ERR_UNSUPPORTED, "pack_inducing_tf32: d=%d > 64 is outside the TF32-split mode", d);
+  if (!aligned16(pack)) return fail(EDRGP_ERR_ARG, "pack_inducing_tf32: pack must be 16-byte aligned");
+  cudaError_t e = edrgp::launch_pack_tf32(Z, ell, m, d, pack, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "pack_inducing_tf32");
+}
+
+int edrgp_kuf_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack, int m,
+                     double sf2, double* Kfu, int64_t ldk, void* stream) {
+  if (!X || !ell || !pack || !Kfu || n <= 0 || d <= 0 || m <= 0) return fail(EDRGP_ERR_ARG, "kuf_tf32x3: bad argument");
+  if (d > 64) return fail(EDRGP_ERR_UNSUPPORTED, "kuf_tf32x3: d=%d > 64 is outside the TF32-split mode", d);
+  if (m > 4096) return fail(EDRGP_ERR_UNSUPPORTED, "kuf_tf32x3: m=%d > 4096", m);
+  if ((d & 1) || ldx < d || (ldx & 1)) return fail(EDRGP_ERR_ARG, "kuf_tf32x3: d and ldx must be even, ldx >= d");
+  if (ldk < m || (ldk & 1)) return fail(EDRGP_ERR_ARG, "kuf_tf32x3: ldk must be even and >= m");
+  if (!(sf2 > 0.0)) return fail(EDRGP_ERR_ARG, "kuf_tf32x3: the kernel variance must be positive");
+  if (!aligned16(X) || !aligned16(pack) || !aligned16(Kfu)) return fail(EDRGP_ERR_ARG, "kuf_tf32x3: X, pack and Kfu must be 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kuf_tf32x3: no CUDA device");
+  cudaError_t e = edrgp::launch_kuf_tf32(X, ldx, n, d, ell, pack, m, sf2, Kfu, ldk, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf_tf32x3");
+}
+
 size_t edrgp_grad_gram_workspace_bytes(int d) {
   const int dp = edrgp::padded_dim(d);
   int sms = sm_count_cached();

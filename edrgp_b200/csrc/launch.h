@@ -48,6 +48,12 @@ cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* 
 cudaError_t launch_project(const double* X, int64_t n, int d, const double* V, int k, double* out, int sms,
                            cudaStream_t st);
 
+// TF32-split cross-covariance (tcgen05): tf32.cu
+size_t pack_tf32_bytes(int m, int d);
+cudaError_t launch_pack_tf32(const double* Z, const double* ell, int m, int d, void* pack, cudaStream_t st);
+cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack, int m,
+                            double sf2, double* K, int64_t ldk, int sms, cudaStream_t st);
+
 cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

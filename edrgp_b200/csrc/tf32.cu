@@ -1,0 +1,448 @@
+// TF32-split ("tf32x3") cross-covariance for B200 (sm_100a): the optional reduced-precision mode of
+// unit K1 (BASELINE north star: kernel entries within 1e-4 relative of the FP64 path).
+//
+//   Kfu[i][j] = sf2 * exp(-0.5 * max(|x_i/l|^2 + |z_j/l|^2 - 2 (x_i/l).(z_j/l), 0))
+//
+// The distance contraction (x/l).(z/l) runs on the 5th-generation tensor cores:
+// tcgen05.mma.kind::tf32 (SASS UTCMMA) with both operands in shared memory and the FP32
+// accumulators in tensor memory.  Each FP64 operand is split into two TF32 values,
+// v = hi + lo (22 significant bits), and three products are accumulated, lo*hi + hi*lo + hi*hi
+// (the dropped lo*lo term is ~2^-22 relative).  The norms are kept outside the contraction in FP64
+// and enter the exponent as two FP32 addends.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      producer : streams the packed inducing chunks (128 points: hi | lo images, already in
+//                          the 128-byte-swizzled K-major layout the MMA reads) with TMA bulk copies
+//   warp 1      MMA      : allocates the 512 TMEM columns; one thread issues the tcgen05.mma sequence
+//                          (M = 128 rows, N = 128 inducing points, K = 8 per instruction) and commits
+//                          to the mbarriers that free the operand buffers / publish the accumulators
+//   warps 2-9   convert  : read the FP64 rows of the X tile (coalesced, one row per warp pass), scale
+//                          by 1/l, split into hi / lo and store them swizzled; row norms -> ring
+//   warps 10-17 epilogue : tcgen05.ld the accumulators (a thread per row, 32 columns per load),
+//                          exponent + ex2.approx + FP32->FP64, 32-byte vector stores of Kfu rows
+// Four accumulator stages of 128 columns let the contraction of chunk j + 1 .. j + 3 run under the
+// epilogue of chunk j: the kernel is bound by the 8 m bytes per point it has to write to HBM.
+#include <cstdint>
+#include <cstdlib>
+#include "common.cuh"
+#include "launch.h"
+
+namespace edrgp {
+
+namespace tf32 {
+
+constexpr int TM = 128;                    // data rows per tile (UMMA M)
+constexpr int TN = 128;                    // inducing points per chunk (UMMA N)
+constexpr int KBLK = 32;                   // TF32 elements per 128-byte swizzled row
+constexpr int BLK_BYTES = TM * 128;        // one operand k-block: 128 rows x 128 B = 16 KB
+constexpr int MAX_KB = 2;                  // d <= 64
+constexpr int ACC_STAGES = 4;              // 4 x 128 = 512 TMEM columns
+constexpr int Z_STAGES = 1;                // inducing chunk buffers (64 KB each at d = 64)
+constexpr int X_STAGES = 2;                // converted X tiles (64 KB each at d = 64)
+constexpr int XN_RING = 8;                 // row-norm ring (tiles): converters run <= 5 tiles ahead of the epilogue
+constexpr int CONV_WARPS = 8;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + CONV_WARPS + EPI_WARPS);
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct Params {
+  const double* X;
+  int64_t ldx;
+  int64_t n;
+  int d;                 // features (even, <= 64)
+  const double* ell;     // lengthscales (d)
+  const uint8_t* pack;   // [cz: mpad floats | chunk images]
+  int m;
+  int nchunks;
+  int kb;                // k-blocks of 32 features
+  int ksteps;            // MMA k-steps of 8 features
+  float l2sf2;           // log2(sf2)
+  double sf2;            // the value stored where r^2 clips at 0 (exactly sf2, as in the FP64 kernel)
+  double* K;
+  int64_t ldk;
+  int64_t ntiles;
+  int debug;             // tuning aid (EDRGP_TF32_DEBUG): 1 = no global stores, 2 = no X conversion after the first tile
+};
+
+__host__ __device__ inline int chunk_bytes(int kb) { return 2 * kb * BLK_BYTES; }
+__host__ __device__ inline int mpad(int m) { return (m + TN - 1) / TN * TN; }
+__host__ __device__ inline size_t cz_bytes(int m) { return ((size_t)mpad(m) * 4 + 1023) / 1024 * 1024; }
+
+// byte offset of element (row r, feature k within the 32-wide block) in a 128-byte-swizzled K-major block
+__host__ __device__ inline uint32_t sw128_offset(int r, int k) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+// v = hi + lo with hi, lo representable in TF32
+__device__ __forceinline__ void split_tf32(double v, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32((float)v);
+  lo = to_tf32((float)(v - (double)__uint_as_float(hi)));
+}
+
+// ---- tcgen05 wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused with swizzle): 1
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, dense
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_v4_f64(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// ---- inducing pack: cz[j] = -0.5 |z_j/l|^2 log2(e) (FP32), then per 128-point chunk the hi and lo images ----
+__global__ void pack_tf32_kernel(const double* __restrict__ Z, const double* __restrict__ ell, int m, int d, int kb,
+                                 uint8_t* __restrict__ pack) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mp = mpad(m);
+  if (warp >= mp) return;
+  const int j = warp;
+  float* cz = reinterpret_cast<float*>(pack);
+  uint8_t* chunk = pack + cz_bytes(m) + (size_t)(j / TN) * chunk_bytes(kb);
+  const int r = j % TN;
+  double zn = 0.0;
+  for (int q = lane; q < kb * KBLK; q += 32) {
+    double zs = 0.0;
+    if (j < m && q < d) zs = Z[(size_t)j * d + q] / ell[q];            // GPy: X2 / lengthscale
+    zn = fma(zs, zs, zn);
+    uint32_t hi, lo;
+    split_tf32(zs, hi, lo);
+    const uint32_t off = (uint32_t)(q / KBLK) * BLK_BYTES + sw128_offset(r, q % KBLK);
+    *reinterpret_cast<uint32_t*>(chunk + off) = hi;
+    *reinterpret_cast<uint32_t*>(chunk + (size_t)kb * BLK_BYTES + off) = lo;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) zn += __shfl_xor_sync(0xffffffffu, zn, o);
+  if (lane == 0) cz[j] = (float)(-0.5 * zn * 1.4426950408889634);
+}
+
+struct __align__(8) Barriers {
+  uint64_t z_full[Z_STAGES], z_empty[Z_STAGES];
+  uint64_t x_full[X_STAGES], x_empty[X_STAGES];
+  uint64_t acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+};
+
+__global__ void __launch_bounds__(THREADS, 1) kuf_tf32_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned carve-up (the swizzle pattern is a function of the absolute shared address)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kb = p.kb;
+  uint8_t* sX = smem;                                        // X_STAGES x [hi kb blocks | lo kb blocks]
+  uint8_t* sZ = sX + X_STAGES * 2 * MAX_KB * BLK_BYTES;      // Z_STAGES x [hi kb blocks | lo kb blocks]
+  float* sCz = reinterpret_cast<float*>(sZ + Z_STAGES * 2 * MAX_KB * BLK_BYTES);     // mpad floats
+  float* sXn = sCz + cz_bytes(p.m) / 4;                      // XN_RING x TM
+  Barriers* bars = reinterpret_cast<Barriers*>(sXn + XN_RING * TM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = p.nchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < Z_STAGES; ++s) { mbar_init(&bars->z_full[s], 1); mbar_init(&bars->z_empty[s], 1); }
+    for (int s = 0; s < X_STAGES; ++s) { mbar_init(&bars->x_full[s], CONV_WARPS); mbar_init(&bars->x_empty[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], EPI_WARPS); }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < mpad(p.m); i += THREADS) sCz[i] = reinterpret_cast<const float*>(p.pack)[i];
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: inducing chunks, re-streamed (L2-resident) for every row tile =====
+    if (lane == 0) {
+      const uint8_t* chunks = p.pack + cz_bytes(p.m);
+      const uint32_t cbytes = (uint32_t)chunk_bytes(kb);
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = it % Z_STAGES;
+          mbar_wait(&bars->z_empty[s], ((it / Z_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars->z_full[s], cbytes);
+          uint8_t* dst = sZ + (size_t)s * 2 * MAX_KB * BLK_BYTES;
+          const uint8_t* src = chunks + (size_t)c * cbytes;
+          for (uint32_t o = 0; o < cbytes; o += BLK_BYTES) bulk_g2s(dst + o, src + o, BLK_BYTES, &bars->z_full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(TM, TN);
+      uint32_t it = 0, tl = 0;
+      for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tl) {
+        const int xs = tl % X_STAGES;
+        const uint32_t xa = smem_u32(sX + (size_t)xs * 2 * MAX_KB * BLK_BYTES);
+        mbar_wait(&bars->x_full[xs], (tl / X_STAGES) & 1);
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int zs = it % Z_STAGES, as = it % ACC_STAGES;
+          mbar_wait(&bars->z_full[zs], (it / Z_STAGES) & 1);
+          mbar_wait(&bars->acc_empty[as], ((it / ACC_STAGES) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t za = smem_u32(sZ + (size_t)zs * 2 * MAX_KB * BLK_BYTES);
+          const uint32_t dcol = tmem_base + (uint32_t)(as * TN);
+          uint32_t acc = 0;
+          // corrections first (lo x hi, hi x lo), the leading product last
+#pragma unroll 1
+          for (int combo = 0; combo < 3; ++combo) {
+            const uint32_t aoff = (combo == 0) ? (uint32_t)kb * BLK_BYTES : 0u;      // X lo | hi | hi
+            const uint32_t boff = (combo == 1) ? (uint32_t)kb * BLK_BYTES : 0u;      // Z hi | lo | hi
+            for (int ks = 0; ks < p.ksteps; ++ks) {
+              const uint32_t koff = (uint32_t)(ks >> 2) * BLK_BYTES + (uint32_t)(ks & 3) * 32;
+              mma_tf32(dcol, smem_desc_sw128(xa + aoff + koff), smem_desc_sw128(za + boff + koff), idesc, acc);
+              acc = 1;
+            }
+          }
+          tc_commit(&bars->z_empty[zs]);            // operand buffer free once these MMAs have read it
+          tc_commit(&bars->acc_full[as]);           // accumulators complete
+        }
+        tc_commit(&bars->x_empty[xs]);              // X tile free
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + CONV_WARPS) {
+    // ===== X converters: FP64 rows -> scaled hi / lo TF32 images, row norms =====
+    const int cw = warp - 2;
+    const int d = p.d;
+    const int q0 = 2 * lane;                                     // this lane's feature pair
+    const bool have = q0 < d;
+    const double il0 = have ? 1.0 / p.ell[q0] : 0.0;
+    const double il1 = (q0 + 1 < d) ? 1.0 / p.ell[q0 + 1] : 0.0;
+    const bool in_k = q0 < kb * KBLK;
+    const uint32_t blk = (uint32_t)(q0 / KBLK) * BLK_BYTES;
+    const int kq = q0 % KBLK;
+    uint32_t tl = 0;
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tl) {
+      const int xs = tl % X_STAGES;
+      uint8_t* sXt = sX + (size_t)xs * 2 * MAX_KB * BLK_BYTES;
+      mbar_wait(&bars->x_empty[xs], ((tl / X_STAGES) & 1) ^ 1);
+      float* xn = sXn + (tl % XN_RING) * TM;
+      if ((p.debug & 2) && tl >= X_STAGES) { __syncwarp(); if (lane == 0) mbar_arrive(&bars->x_full[xs]); continue; }
+      const int64_t row0 = t * TM;
+      constexpr int RB = 8;                                       // rows in flight per warp
+      for (int rb = cw * (TM / CONV_WARPS); rb < (cw + 1) * (TM / CONV_WARPS); rb += RB) {
+        double2 v[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int64_t row = row0 + rb + i;
+          v[i] = make_double2(0.0, 0.0);
+          if (have && row < p.n) v[i] = *reinterpret_cast<const double2*>(p.X + row * p.ldx + q0);
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = rb + i;
+          const double a = v[i].x * il0, b = v[i].y * il1;           // GPy: X / lengthscale
+          double nn = fma(a, a, b * b);
+          uint32_t h0, l0, h1, l1;
+          split_tf32(a, h0, l0);
+          split_tf32(b, h1, l1);
+          if (in_k) {
+            const uint32_t off = blk + sw128_offset(r, kq);
+            *reinterpret_cast<uint2*>(sXt + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(sXt + (size_t)kb * BLK_BYTES + off) = make_uint2(l0, l1);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+          if (lane == 0) xn[r] = (float)(-0.5 * nn * 1.4426950408889634) + p.l2sf2;
+        }
+      }
+      fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_full[xs]);
+    }
+  } else {
+    // ===== epilogue: TMEM -> exponent -> exp2 -> FP64 -> HBM =====
+    const int ew = warp - 2 - CONV_WARPS;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                    // column half of the 128-column stage
+    const int row_in_tile = q * 32 + lane;
+    const bool vec_ok = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 31) == 0);
+    uint32_t it = 0, tl = 0;
+    for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tl) {
+      const int64_t row = t * TM + row_in_tile;
+      float cx = 0.f;
+      bool have_cx = false;
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const int as = it % ACC_STAGES;
+        mbar_wait(&bars->acc_full[as], (it / ACC_STAGES) & 1);
+        tc_fence_after();
+        if (!have_cx) { cx = sXn[(tl % XN_RING) * TM + row_in_tile]; have_cx = true; }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN + half * 64);
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[as]);         // the stage is free: values are in registers
+        const int col0 = c * TN + half * 64;
+        if (p.debug & 1) continue;
+        // A thread holds 32 consecutive columns of ITS row; stored like that, one warp instruction would
+        // touch 32 different 128-byte lines (one 32-byte sector each) and the L1 store path, not HBM,
+        // bounds the kernel.  So the four lanes of a quad first exchange 4-column units (a 4 x 4
+        // transpose by two shuffle butterflies): afterwards lane j of the quad holds, for each of the
+        // quad's four rows, columns [16 h + 4 j, +4) -- and a 32-byte store per lane makes the quad
+        // write one full line of one row.
+        const int quad_row0 = (int)(t * TM) + q * 32 + (lane & ~3);
+        const int jq = lane & 3;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          uint32_t* v = hb ? v1 : v0;
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = fmaf(__uint_as_float(v[i]), LOG2E, cx);      // row term first
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // units j = 0..3 of this h: w[16 h + 4 j + e]
+#pragma unroll
+            for (int bit = 1; bit <= 2; bit <<= 1) {
+              const bool up = (lane & bit) != 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j & bit) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float& lo_u = w[16 * h + 4 * j + e];
+                  float& hi_u = w[16 * h + 4 * (j | bit) + e];
+                  const float send = up ? lo_u : hi_u;
+                  const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                  if (up) lo_u = recv; else hi_u = recv;
+                }
+              }
+            }
+            // now w[16 h + 4 rho + e] = (row quad_row0 + rho, column col0 + 32 hb + 16 h + 4 jq + e)
+            const int cc = hb * 32 + h * 16 + jq * 4;
+            const float4 z4 = *reinterpret_cast<const float4*>(sCz + col0 + cc);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) {
+              const int64_t orow = (int64_t)quad_row0 + rho;
+              double o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float ex = w[16 * h + 4 * rho + e] + zz[e];
+                o[e] = ex >= p.l2sf2 ? p.sf2 : (double)ex2_approx(ex);          // r^2 clipped at 0 (GPy): exactly sf2
+              }
+              if (orow < p.n) {
+                double* out = p.K + orow * p.ldk + col0 + cc;
+                if (vec_ok && col0 + cc + 3 < p.m) {
+                  st_v4_f64(out, o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (col0 + cc + e < p.m) out[e] = o[e];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t smem_bytes(int m) {
+  return 1024 /* alignment slack */ + (size_t)2 * MAX_KB * BLK_BYTES * (X_STAGES + Z_STAGES) + cz_bytes(m) +
+         (size_t)XN_RING * TM * 4 + sizeof(Barriers) + 16;
+}
+
+}  // namespace tf32
+
+size_t pack_tf32_bytes(int m, int d) {
+  const int kb = (d + tf32::KBLK - 1) / tf32::KBLK;
+  return tf32::cz_bytes(m) + (size_t)(tf32::mpad(m) / tf32::TN) * tf32::chunk_bytes(kb);
+}
+
+cudaError_t launch_pack_tf32(const double* Z, const double* ell, int m, int d, void* pack, cudaStream_t st) {
+  const int kb = (d + tf32::KBLK - 1) / tf32::KBLK;
+  const int warps = tf32::mpad(m);
+  tf32::pack_tf32_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(Z, ell, m, d, kb, static_cast<uint8_t*>(pack));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack, int m,
+                            double sf2, double* K, int64_t ldk, int sms, cudaStream_t st) {
+  tf32::Params p{};
+  p.X = X; p.ldx = ldx; p.n = n; p.d = d; p.ell = ell; p.pack = static_cast<const uint8_t*>(pack); p.m = m;
+  p.nchunks = tf32::mpad(m) / tf32::TN;
+  p.kb = (d + tf32::KBLK - 1) / tf32::KBLK;
+  p.ksteps = (d + 7) / 8;
+  p.l2sf2 = (float)log2(sf2);
+  p.sf2 = sf2;
+  p.K = K; p.ldk = ldk;
+  p.ntiles = (n + tf32::TM - 1) / tf32::TM;
+  const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+  { static const int dbg = [] { const char* e = getenv("EDRGP_TF32_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
+  const size_t smem = tf32::smem_bytes(m);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(tf32::kuf_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tf32::kuf_tf32_kernel<<<grid, tf32::THREADS, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace edrgp

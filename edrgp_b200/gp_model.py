@@ -139,6 +139,9 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
     ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time, and
     ``noise_var`` sets the initial Gaussian noise variance (GPy's default 1.0; the dense
     ``GaussianProcessRegressor`` of the reference has the same parameter).
+    ``precision='tf32x3'`` evaluates the training rows' cross-covariance with the TF32-split tcgen05
+    kernel (entries within 1e-4 relative of the FP64 ones; at most 64 features); the default
+    ``'fp64'`` is the reference's arithmetic.
     ``deferred_checks=True`` keeps ``fit`` from synchronising with the device: the non-finite scan
     of the input (sklearn's ``check_X_y``) and the positive-definiteness flag of the Cholesky step
     are still computed, but they are read -- and raise -- at the first host read-back
@@ -149,7 +152,7 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
     def __init__(self, kernels=None, kernel_options=None, Z=None, num_inducing=10, Y_metadata=None,
                  X_variance=None, normalizer=True, mean_function=None, method='optimize', chunk_rows=262144,
-                 noise_var=1.0, deferred_checks=False):
+                 noise_var=1.0, deferred_checks=False, precision='fp64'):
         self.kernels = kernels
         self.kernel_options = kernel_options
         self.Z = Z
@@ -162,12 +165,13 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         self.chunk_rows = chunk_rows
         self.noise_var = noise_var
         self.deferred_checks = deferred_checks
+        self.precision = precision
 
     def _get_model(self, X, y, kernel):
         import torch
         kw = dict(kernel=kernel, Z=self.Z, num_inducing=self.num_inducing, X_variance=self.X_variance,
                   mean_function=self.mean_function, normalizer=self.normalizer, chunk_rows=self.chunk_rows,
-                  noise_var=self.noise_var)
+                  noise_var=self.noise_var, precision=getattr(self, 'precision', 'fp64'))
         from . import ops as _ops
 
         def nonfinite_check(Xc, yc):

@@ -165,14 +165,19 @@ class SparseGPRegression(object):
 
     def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, X_variance=None, mean_function=None,
                  normalizer=None, device=None, chunk_rows=262144, cache_bytes=None, noise_var=1.0,
-                 row_loader=None, pre_sync_check=None, input_dim=None):
+                 row_loader=None, pre_sync_check=None, input_dim=None, precision='fp64'):
         if X_variance is not None or mean_function is not None:
             raise NotImplementedError("uncertain inputs / mean functions are outside the B200 path")
         if not torch.cuda.is_available():
             raise RuntimeError("edrgp_b200 needs a CUDA device (there is no CPU fallback)")
+        if precision not in ('fp64', 'tf32x3'):
+            raise ValueError("precision must be 'fp64' or 'tf32x3'")
+        self.precision = precision
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.X = ops.pad_even(_as_device(X, self.device))          # (n_local, d_even)
         self.n_local, self.d_even = self.X.shape
+        if precision == 'tf32x3' and self.d_even > 64:
+            raise ValueError("precision='tf32x3' covers at most 64 features (got %d)" % X.shape[1])
         # input_dim: X may arrive already padded to an even width (estimator's overlapped loader)
         self.input_dim = X.shape[1] if input_dim is None else int(input_dim)
         Yd = _as_device(Y, self.device).reshape(-1)
@@ -314,13 +319,19 @@ class SparseGPRegression(object):
         ldk = self._kbuffers(True)
 
         self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
+        # TF32-split mode: the training rows' cross-covariance (the n m d contraction) runs on the tcgen05
+        # tensor cores; everything downstream (statistics, solve, gradients, eigh) stays FP64
+        pack32 = ops.InducingPackTF32(self._Z_dev, self._ell_dev) if self.precision == 'tf32x3' else None
         P = torch.empty(m, m, dtype=F64, device=dev)
         byy = torch.empty(m + 1, dtype=F64, device=dev)
         for i, (s, e) in enumerate(self._chunks()):
             if self._row_loader is not None:
                 self._row_loader(s, e)
             Kc = self._Kcache[s:e] if self._Kcache is not None else self._Kbuf[:e - s]
-            ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
+            if pack32 is not None:
+                ops.kuf_tf32(self.X[s:e], pack32, sf2, out=Kc)
+            else:
+                ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
             y = self._ensure_y()
             ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
             self.kernel_launches += 4

@@ -139,6 +139,41 @@ def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
     return K, b
 
 
+class InducingPackTF32(object):
+    """Device image of Z / l for the TF32-split cross-covariance kernel (edrgp_pack_inducing_tf32)."""
+
+    def __init__(self, Z, ell):
+        _need_cuda(Z, ell)
+        lib = _lib.load()
+        self.m, self.d = Z.shape
+        if self.d % 2:
+            Z = pad_even(Z)
+            ell = torch.cat([ell, torch.ones(1, dtype=F64, device=ell.device)])
+            self.d += 1
+        if self.d > 64:
+            raise ValueError("the TF32-split mode covers d <= 64 (got %d)" % self.d)
+        self.ell = ell.contiguous()
+        self.buf = torch.empty(lib.edrgp_pack_tf32_bytes(self.m, self.d) // 8, dtype=F64, device=Z.device)
+        _lib.check(lib.edrgp_pack_inducing_tf32(_ptr(Z), _ptr(self.ell), self.m, self.d, _ptr(self.buf), _stream()),
+                   'edrgp_pack_inducing_tf32')
+
+
+def kuf_tf32(X, pack, sf2, out=None):
+    """Kfu (n, m) in the TF32-split mode: tcgen05 distance contraction, FP64 entries out."""
+    lib = _lib.load()
+    X = pad_even(X)
+    _need_cuda(X)
+    n, ldx = X.shape
+    if ldx != pack.d:
+        raise ValueError("X has %d features, the pack %d" % (ldx, pack.d))
+    ldk = pack.m + (pack.m & 1)
+    K = out if out is not None else torch.empty(n, ldk, dtype=F64, device=X.device)
+    with _Timed('kuf'):
+        _lib.check(lib.edrgp_kuf_tf32x3(_ptr(X), ldx, n, ldx, _ptr(pack.ell), _ptr(pack.buf), pack.m, float(sf2),
+                                        _ptr(K), K.shape[1], _stream()), 'edrgp_kuf_tf32x3')
+    return K if ldk == pack.m else K[:, :pack.m]
+
+
 def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
     """Posterior-mean gradients G (n, d) and/or their Gram matrix C = G^T G (d, d)."""
     lib = _lib.load()

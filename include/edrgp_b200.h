@@ -80,6 +80,23 @@ int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack
               void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1 in the TF32-split mode ("tf32x3"): the same cross-covariance as edrgp_kuf -- GPy RBF.K(X, Z),
+ * edrgp/gp_model/base.py:69,187 -- with the (x/l).(z/l) contraction on the tcgen05 tensor cores.
+ * Every FP64 operand is split into two TF32 values (22 significant bits) and three products are
+ * accumulated in FP32 tensor memory; norms are reduced in FP64, the exponential is ex2.approx in
+ * FP32, the entries are stored as FP64.  Entries agree with edrgp_kuf to ~1e-6 relative for
+ * standardised inputs (the mode's contract is 1e-4).  d even, d <= 64; X (n, ldx) with ldx even.
+ *   edrgp_pack_inducing_tf32: builds, once per hyper-parameter set, the device image the kernel
+ *       streams: -|z/l|^2 log2(e) / 2 per inducing point (FP32), then per 128 points the hi and lo
+ *       TF32 matrices of Z / l in the 128-byte-swizzled K-major layout tcgen05.mma reads.
+ *   edrgp_kuf_tf32x3: Kfu (n, ldk) = sf2 exp(-r^2 / 2), r^2 clipped at 0; ldk >= m, even.
+ * ------------------------------------------------------------------------------------------- */
+size_t edrgp_pack_tf32_bytes(int m, int d);
+int edrgp_pack_inducing_tf32(const double* Z, const double* ell, int m, int d, void* pack, void* stream);
+int edrgp_kuf_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack,
+                     int m, double sf2, double* Kfu, int64_t ldk, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K1+K4+K5 fused  posterior-mean gradients and their outer product.
  *   G_iq = scale * sum_j K_ij alpha_j (z_jq - x_iq) / l_q^2      (zero where clip(r^2) == 0)
  *   C    = G^T G  (d x d)
