@@ -41,6 +41,19 @@ N_TOTAL, D, M, K_TRUE = 4_000_000, 64, 512, 3
 NOISE, SF2 = 0.1, 1.0
 
 
+def _hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the
+    profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs'])
+    except (OSError, ValueError, KeyError):
+        return 6500.0
+
+
+HBM_PEAK_GBS = _hbm_peak_gbs()
+
+
 def flops_per_point(d, m):
     """Algorithmic FP64 flops per point of one sweep (symmetric halves NOT
     discounted): stats 2md + 2m^2 + 3m, pipeline 4md + 2d^2 + m."""
@@ -213,16 +226,16 @@ def run_ours(args):
     Z = Z0.cpu().numpy()
     ell = hyper(d)
 
-    def make_estimator():
+    def make_estimator(precision=None):
         return eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, SF2, ell, ARD=True), Z=Z, normalizer=True,
                                                  method='fixed', noise_var=NOISE, chunk_rows=args.chunk_rows,
-                                                 deferred_checks=True)
+                                                 deferred_checks=True, precision=precision or args.precision)
 
-    def sweep(Xin, yin):
+    def sweep(Xin, yin, precision=None):
         """One fixed-hyper-parameter EDR sweep through the public classes.  The input validation and
         the Cholesky flag are computed on the device inside the sweep and read (and raised) once, after
         the directions have been read back: no host round trip between the row passes."""
-        est = make_estimator().fit(Xin, yin)
+        est = make_estimator(precision).fit(Xin, yin)
         _, C = est.estimator_.gradient_gram(want_G=False, check=False)
         edist.allreduce_sum_(C)
         tr = eb.GramEighTransformer(n_components=K_TRUE).fit_gram(C, n)
@@ -286,6 +299,37 @@ def run_ours(args):
     pa = ops.stop_timing()
     pipe_alone_ms, pipe_alone_n = pa.get('grad_gram', (0.0, 1))
     del est0, gpack
+
+    # ---- the same sweep in the TF32-split mode (informational; the headline above is FP64): the training
+    # rows' cross-covariance on the tcgen05 tensor cores, everything downstream unchanged
+    tf32_mode = None
+    if d + (d & 1) <= 64 and args.precision == 'fp64' and not args.no_tf32:
+        for _ in range(2):
+            sweep(X, y, 'tf32x3')
+        ops.start_timing()
+        t_steps = max(1, min(args.steps, 5))
+        t_ms, comps32 = timed(lambda: sweep(X, y, 'tf32x3'), t_steps)
+        t_ops = ops.stop_timing()
+        k_ms, k_n = t_ops.get('kuf', (0.0, 1))
+        rows_chk = min(n_local, 4096)
+        pk64 = ops.InducingPack(torch.as_tensor(Z, device=dev), torch.as_tensor(ell, device=dev))
+        pk32 = ops.InducingPackTF32(torch.as_tensor(Z, device=dev), torch.as_tensor(ell, device=dev))
+        K64, _ = ops.kuf(X[:rows_chk], pk64, SF2)
+        K32 = ops.kuf_tf32(X[:rows_chk], pk32, SF2)
+        from edrgp_b200.utils import principal_angle as _pa
+        tf32_mode = {
+            "ms_per_step": t_ms / t_steps, "value": n / (t_ms / t_steps * 1e-3), "unit": UNIT, "steps": t_steps,
+            "kernel": "kuf_tf32_kernel (tcgen05.mma kind::tf32, 3 products per entry, FP32 accumulators in TMEM)",
+            "kuf_ms_per_step": k_ms / t_steps, "kuf_avg_launch_ms": k_ms / max(k_n, 1),
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": HBM_PEAK_GBS,
+                         "achieved": (m + d) * 8.0 * n_local * t_steps / (k_ms * 1e-3) / 1e9 if k_ms else None,
+                         "frac": (m + d) * 8.0 * n_local * t_steps / (k_ms * 1e-3) / 1e9 / HBM_PEAK_GBS if k_ms else None,
+                         "note": "algorithmic bytes per point: 8 m written (Kfu, FP64) + 8 d read (X); peak = "
+                                 "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
+            "max_rel_err_entries_vs_fp64": float(((K32 - K64).abs() / K64).max()),
+            "leading_direction_angle_vs_fp64_rad": float(_pa(comps32[:1], comps[:1])),
+            "tolerance": "1e-4 relative on kernel entries (BASELINE north_star, TF32-split mode)"}
+        del K64, K32, pk64, pk32
 
     # quality of the directions found (not a timing): principal angle to the true subspace
     from edrgp_b200.utils import principal_angle
@@ -373,12 +417,12 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64" if args.precision == 'fp64' else "f64 (cross-covariance contraction: tf32 x 3)", "data": "synthetic",
         "config": {"workload": workload_name(args), "n": n, "d": d, "m": m, "rows_per_rank": n_local,
                    "hyperparameters": "fixed (lengthscales sqrt(d)(1+u/2), variance 1, noise 0.1)",
                    "l2": "inputs (%.2f GB X per rank + %.1f GB Kfu blocks) exceed the 126 MB L2; no flush needed"
                          % (n_local * d * 8 / 1e9, n_local * m * 8 / 1e9),
-                   "chunk_rows": args.chunk_rows, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
+                   "chunk_rows": args.chunk_rows, "precision": args.precision, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                 "api": "SparseGaussianProcessRegressor(method='fixed').fit(X_host, y_host) -> gradient_gram -> "
@@ -428,6 +472,7 @@ def run_ours(args):
                             "direction, so only the leading direction is expected to lie in span(B)"},
         "cpu_baseline": cpu,
         "edr_fit": edr_fit,
+        "tf32x3_mode": tf32_mode,
     }
     print(json.dumps(line))
     if world > 1:
@@ -447,6 +492,9 @@ def main():
     ap.add_argument('--cpu-rows', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-edr', action='store_true')
+    ap.add_argument('--no-tf32', action='store_true', help="skip the informational TF32-split arm")
+    ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32x3'],
+                    help="arithmetic of the cross-covariance pass (the headline is fp64)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -292,11 +292,18 @@ class SparseGPRegression(object):
             need = self.n_local * ldk * 8
             budget = self.cache_bytes
             if budget is None:
-                # (cudaMemGetInfo costs ~25 ms per call on this driver: use the allocator's counters)
+                # (cudaMemGetInfo costs ~25 ms per call on this driver and the allocator's statistics
+                # ~0.2 ms: a matrix under a quarter of the device memory is simply tried)
                 total = torch.cuda.get_device_properties(self.device).total_memory
-                budget = int(0.5 * max(0, total - torch.cuda.memory_allocated(self.device)))
+                if need <= total // 4:
+                    budget = need
+                else:
+                    budget = int(0.5 * max(0, total - torch.cuda.memory_allocated(self.device)))
             if need <= budget:
-                self._Kcache = torch.empty(self.n_local, ldk, dtype=F64, device=self.device)
+                try:
+                    self._Kcache = torch.empty(self.n_local, ldk, dtype=F64, device=self.device)
+                except torch.cuda.OutOfMemoryError:
+                    self._Kcache = None                       # one reusable block instead (recompute path)
         if getattr(self, '_Kbuf', None) is None or self._Kbuf.shape[1] != ldk:
             rows = min(self.chunk_rows, self.n_local)
             self._Kbuf = torch.empty(rows, ldk, dtype=F64, device=self.device)

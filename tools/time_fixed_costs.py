@@ -13,9 +13,11 @@ Z = X[:m].cpu().numpy()
 ell = np.sqrt(d) * (1 + 0.5 * np.random.RandomState(1).uniform(size=d))
 def sync(): torch.cuda.synchronize(); return time.perf_counter()
 def sweep():
-    est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True, method='fixed', noise_var=0.1, chunk_rows=524288).fit(X, y)
-    _, C = est.estimator_.gradient_gram(want_G=False)
-    return eb.GramEighTransformer(n_components=3).fit_gram(C, n).components_
+    est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True, method='fixed', noise_var=0.1, chunk_rows=524288, deferred_checks=True).fit(X, y)
+    _, C = est.estimator_.gradient_gram(want_G=False, check=False)
+    tr = eb.GramEighTransformer(n_components=3).fit_gram(C, n)
+    est.estimator_.finish_checks()
+    return tr.components_
 for _ in range(3): sweep()
 ts = []
 for _ in range(10):
@@ -29,4 +31,4 @@ import cProfile, pstats, io
 pr = cProfile.Profile(); pr.enable()
 for _ in range(10): sweep()
 torch.cuda.synchronize(); pr.disable()
-sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats('tottime').print_stats(22); print(sio.getvalue()[:4500])
+sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats('tottime').print_stats(40); print(sio.getvalue()[:9000])
