@@ -113,6 +113,34 @@ int edrgp_kuf_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const doubl
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf_tf32x3");
 }
 
+size_t edrgp_pack_grad_tf32_bytes(int m, int d) {
+  if (m <= 0 || d <= 0 || d > 64) return 0;
+  return edrgp::pack_grad_tf32_bytes(m, d);
+}
+
+int edrgp_pack_grad_tf32(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
+                         void* pack, void* stream) {
+  if (!Z || !ell || !coef || !pack || m <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "pack_grad_tf32: bad argument");
+  if (d > 64) return fail(EDRGP_ERR_UNSUPPORTED, "pack_grad_tf32: d=%d > 64 is outside the TF32-split mode", d);
+  if (!aligned16(pack)) return fail(EDRGP_ERR_ARG, "pack_grad_tf32: pack must be 16-byte aligned");
+  cudaError_t e = edrgp::launch_pack_grad_tf32(Z, ell, coef, coef_scale, m, d, pack, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "pack_grad_tf32");
+}
+
+int edrgp_grad_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
+                      const double* ell, const void* pack, int m, double* G, int64_t ldg, void* stream) {
+  if (!X || !Kfu || !ell || !pack || !G || n <= 0 || d <= 0 || m <= 0) return fail(EDRGP_ERR_ARG, "grad_tf32x3: bad argument");
+  if (d > 64) return fail(EDRGP_ERR_UNSUPPORTED, "grad_tf32x3: d=%d > 64 is outside the TF32-split mode", d);
+  if ((d & 1) || ldx < d || (ldx & 1) || ldg < d || (ldg & 1) || ldk < m || (ldk & 1))
+    return fail(EDRGP_ERR_ARG, "grad_tf32x3: d, ldx, ldg, ldk must be even and cover d / m");
+  if (!aligned16(X) || !aligned16(Kfu) || !aligned16(G) || !aligned16(pack))
+    return fail(EDRGP_ERR_ARG, "grad_tf32x3: X, Kfu, G and pack must be 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "grad_tf32x3: no CUDA device");
+  cudaError_t e = edrgp::launch_grad_tf32(X, ldx, n, d, Kfu, ldk, sf2, ell, pack, m, G, ldg, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_tf32x3");
+}
+
 size_t edrgp_grad_gram_workspace_bytes(int d) {
   const int dp = edrgp::padded_dim(d);
   int sms = sm_count_cached();

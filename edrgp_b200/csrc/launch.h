@@ -54,6 +54,13 @@ cudaError_t launch_pack_tf32(const double* Z, const double* ell, int m, int d, v
 cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack, int m,
                             double sf2, double* K, int64_t ldk, int sms, cudaStream_t st);
 
+size_t pack_grad_tf32_bytes(int m, int d);
+cudaError_t launch_pack_grad_tf32(const double* Z, const double* ell, const double* coef, double coef_scale, int m,
+                                  int d, void* pack, cudaStream_t st);
+cudaError_t launch_grad_tf32(const double* X, int64_t ldx, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
+                             const double* ell, const void* pack, int m, double* G, int64_t ldg, int sms,
+                             cudaStream_t st);
+
 cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

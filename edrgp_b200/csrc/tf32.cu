@@ -83,6 +83,42 @@ __device__ __forceinline__ void split_tf32(double v, uint32_t& hi, uint32_t& lo)
   hi = to_tf32((float)v);
   lo = to_tf32((float)(v - (double)__uint_as_float(hi)));
 }
+// The same split for the hot conversion loops WITHOUT FP64 <-> FP32 conversion instructions: those run on
+// the transcendental (XU) pipe at 16 lanes per clock and SM, and three of them per element made that pipe
+// the limiter of the gradient kernel (ncu: XU saturated, HBM at 43 %).  Veltkamp's multiplication by
+// 2^42 + 1 rounds v to 11 significant bits in FP64 (exactly a TF32 value); FP32 bit patterns are then
+// assembled from the double's words with integer instructions.  The low part keeps its spare mantissa
+// bits (the tensor core reads the TF32 field of the 32-bit container).  |v| < 2^-126 flushes to zero.
+__device__ __forceinline__ uint32_t f32_bits_of(double x) {
+  const int h = __double2hiint(x);
+  const uint32_t l = (uint32_t)__double2loint(x);
+  const int a = h & 0x7fffffff;
+  uint32_t f = ((uint32_t)(a - 0x38000000) << 3) | (l >> 29);
+  f = a < 0x38100000 ? 0u : f;
+  return f | ((uint32_t)h & 0x80000000u);
+}
+// FP32 bits of a double that carries at most 21 significant bits (only its high word matters)
+__device__ __forceinline__ uint32_t f32_bits_of_short(double x) {
+  const int h = __double2hiint(x);
+  const int a = h & 0x7fffffff;
+  const uint32_t f = (uint32_t)(a - 0x38000000) << 3;
+  return (a < 0x38100000 ? 0u : f) | ((uint32_t)h & 0x80000000u);
+}
+// v >= 0 (kernel entries): no sign handling for the high part; the low part keeps 20 mantissa bits
+__device__ __forceinline__ void split_tf32_bits_nonneg(double v, uint32_t& hi, uint32_t& lo) {
+  const double t = __dmul_rn(v, 4398046511105.0);
+  const double hd = __dsub_rn(t, __dsub_rn(t, v));
+  const int a = __double2hiint(hd);
+  hi = a < 0x38100000 ? 0u : (uint32_t)(a - 0x38000000) << 3;
+  lo = f32_bits_of_short(__dsub_rn(v, hd));
+}
+__device__ __forceinline__ void split_tf32_bits(double v, uint32_t& hi, uint32_t& lo) {
+  // (explicitly rounded operations: an FMA contraction of t - v would undo the rounding this relies on)
+  const double t = __dmul_rn(v, 4398046511105.0);          // 2^42 + 1
+  const double hd = __dsub_rn(t, __dsub_rn(t, v));         // v rounded to 11 significant bits
+  hi = f32_bits_of(hd);
+  lo = f32_bits_of(__dsub_rn(v, hd));
+}
 
 // ---- tcgen05 wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -293,8 +329,8 @@ __global__ void __launch_bounds__(THREADS, 1) kuf_tf32_kernel(const Params p) {
           const double a = v[i].x * il0, b = v[i].y * il1;           // GPy: X / lengthscale
           double nn = fma(a, a, b * b);
           uint32_t h0, l0, h1, l1;
-          split_tf32(a, h0, l0);
-          split_tf32(b, h1, l1);
+          split_tf32_bits(a, h0, l0);
+          split_tf32_bits(b, h1, l1);
           if (in_k) {
             const uint32_t off = blk + sw128_offset(r, kq);
             *reinterpret_cast<uint2*>(sXt + off) = make_uint2(h0, h1);
@@ -410,6 +446,286 @@ inline size_t smem_bytes(int m) {
 
 }  // namespace tf32
 
+// =================================================================================================
+// TF32-split posterior-mean gradients from the STORED cross-covariance (units K4 of the path):
+//     G_iq = sum_j K_ij c_j (z_jq - x_iq) / l_q^2 = (K B)_i,1+q - (K B)_i,0 x_iq / l_q^2,
+//     B_j,0 = c_j,  B_j,1+q = c_j z_jq / l_q^2,   c = alpha * scale
+// i.e. ONE tall-skinny contraction K (n x m, FP64 in HBM) times B (m x (d + 1)) on tcgen05, the FP64
+// operand converted to hi / lo TF32 on the fly.  Bound by the 8 m bytes per point it reads.
+//   warp 0      producer : B k-blocks (32 inducing points: hi | lo images, prepacked) by TMA bulk copy
+//   warp 1      MMA      : 12 tcgen05.mma (3 products x 4 k-steps) per k-block into a 128 x NPAD accumulator
+//   warps 2-17  convert  : Kfu tile k-block (128 rows x 32 columns FP64, 32-byte loads, three blocks in
+//                          flight in registers) -> hi / lo TF32 by a Veltkamp split and integer repacking
+//                          (no FP64 <-> FP32 conversion instructions) -> 128-byte-swizzled shared memory
+//   warps 18-21 epilogue : TMEM -> FP64, subtract rowsum * x / l^2, store the G row
+// =================================================================================================
+namespace g32 {
+using namespace tf32;
+
+constexpr int STAGES = 4;
+constexpr int NPAD_MAX = 80;                         // d <= 64: 1 + 64 columns, rounded up to 16
+constexpr int A_BYTES = 2 * BLK_BYTES;               // hi | lo: 32 KB
+constexpr int B_BYTES_MAX = 2 * NPAD_MAX * 128;      // hi | lo: 20 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;   // 52 KB (multiple of 1024)
+constexpr int CONV_W = 16, EPI_W = 4;
+constexpr int PF = 3;                                // k-blocks of Kfu loads in flight per converter thread
+constexpr int NTHREADS = 32 * (2 + CONV_W + EPI_W);
+
+struct GParams {
+  const double* Kin; int64_t ldk;
+  const double* X; int64_t ldx;
+  const double* ell;
+  const uint8_t* pack;
+  double* G; int64_t ldg;
+  int64_t n, ntiles;
+  int m, d, npad, kblocks;
+  double sf2;
+};
+
+struct __align__(8) GBars {
+  uint64_t full[STAGES], empty[STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+};
+
+__global__ void pack_grad_tf32_kernel(const double* __restrict__ Z, const double* __restrict__ ell,
+                                      const double* __restrict__ coef, double coef_scale, int m, int d, int npad,
+                                      uint8_t* __restrict__ pack) {
+  const int kblocks = (m + KBLK - 1) / KBLK;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)kblocks * KBLK * npad) return;
+  const int j = (int)(idx / npad), nn = (int)(idx % npad);
+  double v = 0.0;
+  if (j < m) {
+    const double c = coef[j] * coef_scale;
+    if (nn == 0) v = c;
+    else if (nn <= d) { const double l = ell[nn - 1]; v = c * Z[(size_t)j * d + nn - 1] / (l * l); }
+  }
+  uint32_t hi, lo;
+  split_tf32(v, hi, lo);
+  uint8_t* blk = pack + (size_t)(j / KBLK) * (2 * npad * 128);
+  const uint32_t off = sw128_offset(nn, j % KBLK);
+  *reinterpret_cast<uint32_t*>(blk + off) = hi;
+  *reinterpret_cast<uint32_t*>(blk + npad * 128 + off) = lo;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) grad_tf32_kernel(const GParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  double* sIl2 = reinterpret_cast<double*>(smem + (size_t)STAGES * STAGE_BYTES);      // 64 doubles
+  GBars* bars = reinterpret_cast<GBars*>(sIl2 + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.kblocks;
+  const int64_t my_tiles = blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = my_tiles * KB;                       // (tile, k-block) work items of this CTA
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], CONV_W + 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], EPI_W); }
+    mbar_fence_init();
+  }
+  if (tid < 64) { const double l = tid < p.d ? p.ell[tid] : 1.0; sIl2[tid] = tid < p.d ? 1.0 / (l * l) : 0.0; }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t bbytes = (uint32_t)(2 * p.npad * 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int64_t it = 0; it < total; ++it) {
+        const int s = (int)(it % STAGES), kb = (int)(it % KB);
+        mbar_wait(&bars->empty[s], (uint32_t)((it / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->full[s], bbytes);
+        bulk_g2s(smem + (size_t)s * STAGE_BYTES + A_BYTES, p.pack + (size_t)kb * bbytes, bbytes, &bars->full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(TM, p.npad);
+      int64_t it = 0;
+      for (int64_t tl = 0; tl < my_tiles; ++tl) {
+        const int slot = (int)(tl & 1);
+        mbar_wait(&bars->acc_empty[slot], (uint32_t)((tl >> 1) & 1) ^ 1);
+        const uint32_t dcol = tmem_base + (uint32_t)(slot * 128);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          mbar_wait(&bars->full[s], (uint32_t)((it / STAGES) & 1));
+          tc_fence_after();
+          const uint32_t aa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t ba = aa + A_BYTES;
+#pragma unroll 1
+          for (int combo = 0; combo < 3; ++combo) {
+            const uint32_t aoff = (combo == 0) ? (uint32_t)BLK_BYTES : 0u;            // K lo | hi | hi
+            const uint32_t boff = (combo == 1) ? (uint32_t)(p.npad * 128) : 0u;       // B hi | lo | hi
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_tf32(dcol, smem_desc_sw128(aa + aoff + ks * 32), smem_desc_sw128(ba + boff + ks * 32), idesc, acc);
+              acc = 1;
+            }
+          }
+          tc_commit(&bars->empty[s]);
+        }
+        tc_commit(&bars->acc_full[slot]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + CONV_W) {
+    // ===== converters: thread = (column group g of 4, rows rbase + 64 i) =====
+    // (GPy's dropped pairs -- entries equal to sf2, r = 0 -- are NOT special-cased here: their terms
+    //  c_j K (z_j - x_i) cancel between the contraction and the rowsum * x correction to the mode's
+    //  rounding level, like every other term)
+    const int ct = tid - 64;                          // 0 .. 511
+    const int g = ct & 7, rbase = ct >> 3;            // rows rbase + 64 i, i = 0 .. 1
+    // fast path: 32-byte aligned rows and m a multiple of 32 -> one unpredicated 32-byte load per item
+    const bool fastp = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Kin) & 31) == 0) && (p.m % KBLK == 0);
+    double buf[PF][2][4];
+    // (tile, k-block) of the next load, advanced incrementally (no 64-bit divisions in the loop)
+    int64_t ld_tile = blockIdx.x;
+    int ld_kb = 0;
+    const double* rp0 = nullptr;                      // row pointers of the tile being loaded (+ 4 g)
+    const double* rp1 = nullptr;
+    auto set_tile = [&]() {
+      const int64_t r0 = ld_tile * TM + rbase, r1 = r0 + 64;
+      rp0 = r0 < p.n ? p.Kin + r0 * p.ldk + 4 * g : nullptr;
+      rp1 = r1 < p.n ? p.Kin + r1 * p.ldk + 4 * g : nullptr;
+    };
+    set_tile();
+    auto load1 = [&](const double* rp, double (&dst)[4]) {
+      dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+      if (rp != nullptr) {
+        const double* src = rp + ld_kb * KBLK;
+        if (fastp) {
+          asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f64 {%0, %1, %2, %3}, [%4];"
+                       : "=d"(dst[0]), "=d"(dst[1]), "=d"(dst[2]), "=d"(dst[3]) : "l"(src));
+        } else {
+          const int c0 = ld_kb * KBLK + 4 * g;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + e < p.m) dst[e] = __ldg(src + e);
+        }
+      }
+    };
+    auto load = [&](double (&dst)[2][4]) {
+      load1(rp0, dst[0]);
+      load1(rp1, dst[1]);
+      if (++ld_kb == KB) { ld_kb = 0; ld_tile += gridDim.x; set_tile(); }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < total) load(buf[u]);
+    uint32_t s = 0, ph = 1;                           // stage and the parity to wait for on its empty barrier
+    const uint32_t off0 = sw128_offset(rbase, 4 * g), off1 = sw128_offset(rbase + 64, 4 * g);
+    for (int64_t it0 = 0; it0 < total; it0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int64_t it = it0 + u;
+        if (it < total) {
+          mbar_wait(&bars->empty[s], ph);
+          uint8_t* sA = smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32_bits_nonneg(buf[u][i][e], hi[e], lo[e]);
+            const uint32_t off = i ? off1 : off0;
+            *reinterpret_cast<uint4*>(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(sA + BLK_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->full[s]);
+          if (it + PF < total) load(buf[u]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: a thread per row, 16 features at a time =====
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const bool xvec = (p.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 31) == 0);
+    const bool gvec = (p.ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.G) & 31) == 0);
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int slot = (int)(tl & 1);
+      const int64_t row = (blockIdx.x + tl * gridDim.x) * TM + row_in_tile;
+      const bool rowok = row < p.n;
+      const double* xr = p.X + (rowok ? row : 0) * p.ldx;
+      double* gr = p.G + (rowok ? row : 0) * p.ldg;
+      mbar_wait(&bars->acc_full[slot], (uint32_t)((tl >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
+      uint32_t rsb;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rsb) : "r"(taddr) : "memory");
+      double rs = 0.0;
+#pragma unroll 1
+      for (int c16 = 0; c16 < p.d; c16 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + 1 + c16, v);                       // features c16 .. c16 + 15 (column 0 holds the row sum)
+        double x[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c0 = c16 + 4 * q4;
+          x[4 * q4] = x[4 * q4 + 1] = x[4 * q4 + 2] = x[4 * q4 + 3] = 0.0;
+          if (rowok && c0 < p.d) {
+            if (xvec && c0 + 3 < p.d) {
+              asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                           : "=d"(x[4 * q4]), "=d"(x[4 * q4 + 1]), "=d"(x[4 * q4 + 2]), "=d"(x[4 * q4 + 3]) : "l"(xr + c0));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c0 + e < p.d) x[4 * q4 + e] = __ldg(xr + c0 + e);
+            }
+          }
+        }
+        tmem_ld_wait();
+        if (c16 == 0) rs = (double)__uint_as_float(rsb);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c0 = c16 + 4 * q4;
+          double o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = fma(-rs * x[4 * q4 + e], sIl2[(c0 + e) & 63], (double)__uint_as_float(v[4 * q4 + e]));
+          if (rowok && c0 < p.d) {
+            if (gvec && c0 + 3 < p.d) {
+              st_v4_f64(gr + c0, o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c0 + e < p.d) gr[c0 + e] = o[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+inline size_t smem_bytes() { return 1024 + (size_t)STAGES * STAGE_BYTES + 64 * 8 + sizeof(GBars) + 16; }
+
+}  // namespace g32
+
+
 size_t pack_tf32_bytes(int m, int d) {
   const int kb = (d + tf32::KBLK - 1) / tf32::KBLK;
   return tf32::cz_bytes(m) + (size_t)(tf32::mpad(m) / tf32::TN) * tf32::chunk_bytes(kb);
@@ -441,6 +757,37 @@ cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, cons
   cudaError_t e = cudaFuncSetAttribute(tf32::kuf_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   tf32::kuf_tf32_kernel<<<grid, tf32::THREADS, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+size_t pack_grad_tf32_bytes(int m, int d) {
+  const int npad = (d + 1 + 15) / 16 * 16;
+  return (size_t)((m + tf32::KBLK - 1) / tf32::KBLK) * 2 * npad * 128;
+}
+
+cudaError_t launch_pack_grad_tf32(const double* Z, const double* ell, const double* coef, double coef_scale, int m,
+                                  int d, void* pack, cudaStream_t st) {
+  const int npad = (d + 1 + 15) / 16 * 16;
+  const int64_t total = (int64_t)((m + tf32::KBLK - 1) / tf32::KBLK) * tf32::KBLK * npad;
+  g32::pack_grad_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, ell, coef, coef_scale, m, d, npad,
+                                                                             static_cast<uint8_t*>(pack));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_tf32(const double* X, int64_t ldx, int64_t n, int d, const double* Kin, int64_t ldk, double sf2,
+                             const double* ell, const void* pack, int m, double* G, int64_t ldg, int sms,
+                             cudaStream_t st) {
+  g32::GParams p{};
+  p.Kin = Kin; p.ldk = ldk; p.X = X; p.ldx = ldx; p.ell = ell; p.pack = static_cast<const uint8_t*>(pack);
+  p.G = G; p.ldg = ldg; p.n = n; p.ntiles = (n + tf32::TM - 1) / tf32::TM; p.m = m; p.d = d;
+  p.npad = (d + 1 + 15) / 16 * 16; p.kblocks = (m + tf32::KBLK - 1) / tf32::KBLK; p.sf2 = sf2;
+  const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+  const size_t smem = g32::smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(g32::grad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  g32::grad_tf32_kernel<<<grid, g32::NTHREADS, smem, st>>>(p);
   count_launch();
   return cudaGetLastError();
 }

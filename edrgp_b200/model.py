@@ -674,7 +674,14 @@ class SparseGPRegression(object):
             return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
         use_cache = X is None and getattr(self, '_Kcache', None) is not None
         sf2 = float(self.kern.variance)
-        if use_cache and self.d_even <= 64:
+        if use_cache and self.d_even <= 64 and self.precision == 'tf32x3':
+            # TF32-split mode: W Z and the row sums as one tcgen05 contraction over the stored Kfu; the
+            # Gram matrix of the gradients stays on the FP64 reduction
+            coef, cs = self._grad_coef(scale)
+            G = ops.grad_tf32(Xd, self._Kcache, self._Z_dev, self._ell_dev, coef, cs, sf2, G_out=G_out)
+            C = ops.syrk(G) if want_C else None
+            self.kernel_launches += 4
+        elif use_cache and self.d_even <= 64:
             # training rows with their cross-covariance already in HBM: no Kuf recompute, no exp
             pack = ops.InducingPack(self._Z_dev, self._ell_dev, *self._grad_coef(scale), block=64)
             G, C = ops.grad_gram_cached(Xd, self._Kcache, pack, sf2, want_G=want_G, want_C=want_C, G_out=G_out)

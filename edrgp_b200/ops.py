@@ -174,6 +174,32 @@ def kuf_tf32(X, pack, sf2, out=None):
     return K if ldk == pack.m else K[:, :pack.m]
 
 
+def grad_tf32(X, K, Z, ell, coef, coef_scale, sf2, G_out=None):
+    """Posterior-mean gradients G (n, d) from a stored cross-covariance block K (n, ldk) in the TF32-split
+    mode: one tcgen05 contraction K x [c | c z / l^2] (c = coef * coef_scale), FP64 correction and output."""
+    lib = _lib.load()
+    d_user = X.shape[1]
+    X = pad_even(X)
+    Z = pad_even(Z)
+    if ell.shape[0] != X.shape[1]:
+        ell = torch.cat([ell, torch.ones(X.shape[1] - ell.shape[0], dtype=F64, device=ell.device)])
+    _need_cuda(X, K, Z, ell, coef)
+    n, d = X.shape
+    m = Z.shape[0]
+    if d > 64:
+        raise ValueError("the TF32-split mode covers d <= 64 (got %d)" % d)
+    if K.shape[0] != n or K.shape[1] < m:
+        raise ValueError("K and X / Z shapes differ")
+    pack = torch.empty(lib.edrgp_pack_grad_tf32_bytes(m, d) // 8, dtype=F64, device=X.device)
+    _lib.check(lib.edrgp_pack_grad_tf32(_ptr(Z), _ptr(ell), _ptr(coef), float(coef_scale), m, d, _ptr(pack), _stream()),
+               'edrgp_pack_grad_tf32')
+    G = G_out if (G_out is not None and d == d_user) else torch.empty(n, d, dtype=F64, device=X.device)
+    with _Timed('grad_tf32'):
+        _lib.check(lib.edrgp_grad_tf32x3(_ptr(X), d, n, d, _ptr(K), K.shape[1], float(sf2), _ptr(ell), _ptr(pack), m,
+                                         _ptr(G), G.shape[1], _stream()), 'edrgp_grad_tf32x3')
+    return G if d == d_user else G[:, :d_user].contiguous()
+
+
 def grad_gram(X, pack, want_G=True, want_C=True, G_out=None):
     """Posterior-mean gradients G (n, d) and/or their Gram matrix C = G^T G (d, d)."""
     lib = _lib.load()

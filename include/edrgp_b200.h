@@ -96,6 +96,21 @@ int edrgp_pack_inducing_tf32(const double* Z, const double* ell, int m, int d, v
 int edrgp_kuf_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* ell, const void* pack,
                      int m, double sf2, double* Kfu, int64_t ldk, void* stream);
 
+/* K4 in the TF32-split mode: posterior-mean gradients from the STORED cross-covariance block,
+ *     G_iq = sum_j K_ij c_j (z_jq - x_iq) / l_q^2,   c = alpha * scale
+ * (GPy GP.predictive_gradients -> Stationary.gradients_X, edrgp/gp_model/base.py:222) as ONE contraction
+ * K (n, m) x B (m, 1 + d) on tcgen05 (B_j0 = c_j: the row sums; B_j,1+q = c_j z_jq / l_q^2), K split into
+ * hi / lo TF32 on the fly, FP32 accumulation in tensor memory, the rowsum * x / l^2 term subtracted in
+ * FP64.  GPy's dropped pairs (r = 0, entries equal to sf2) are not special-cased: their terms cancel
+ * between the contraction and the correction to the mode's rounding level (sf2 is accepted for symmetry
+ * with edrgp_grad_gram_cached).  d even, d <= 64; ldk, ldx, ldg even.  The Gram matrix G^T G then runs on the FP64 reduction (edrgp_syrk).
+ *   edrgp_pack_grad_tf32: builds B's device image (per 32 inducing points: hi | lo, 128-byte swizzled). */
+size_t edrgp_pack_grad_tf32_bytes(int m, int d);
+int edrgp_pack_grad_tf32(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
+                         void* pack, void* stream);
+int edrgp_grad_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
+                      const double* ell, const void* pack, int m, double* G, int64_t ldg, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K1+K4+K5 fused  posterior-mean gradients and their outer product.
  *   G_iq = scale * sum_j K_ij alpha_j (z_jq - x_iq) / l_q^2      (zero where clip(r^2) == 0)

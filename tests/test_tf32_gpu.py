@@ -77,6 +77,24 @@ def test_tf32_rejects_wide_inputs():
                              torch.ones(66, dtype=torch.float64, device='cuda'))
 
 
+@pytest.mark.parametrize("n,d,m", SHAPES[:7])
+def test_tf32_gradients_from_stored_kfu_within_tolerance(n, d, m):
+    """The tcgen05 gradient contraction over a stored Kfu against the oracle's FP64 gradients."""
+    from edrgp_b200 import ops
+    w = op.make_workload(max(n, m), d, m, seed=n + d)
+    X = w['X'][:n]
+    alpha = np.random.RandomState(3).standard_normal(m)
+    Xd, Zd, ld = _dev(X), _dev(w['Z']), _dev(w['ell'])
+    Kbuf = torch.empty(n, m + (m & 1), dtype=torch.float64, device='cuda')       # even leading dimension
+    ops.kuf(Xd, ops.InducingPack(Zd, ld), 1.7, out=Kbuf)
+    G = ops.grad_tf32(Xd, Kbuf, Zd, ld, _dev(alpha), 0.8, 1.7).cpu().numpy()
+    Gref = op.gradients_faithful(X, w['Z'], w['ell'], 1.7, alpha, scale=0.8)
+    assert G.shape == (n, d)
+    assert np.isfinite(G).all()
+    assert np.max(np.abs(G - Gref)) / np.max(np.abs(Gref)) < 1e-4       # the mode's contract (max norm)
+    assert np.max(np.abs(G - Gref)) / np.max(np.abs(Gref)) < 2e-5       # observed ~1e-6 .. 6e-6
+
+
 @pytest.mark.parametrize("n,d,m", [(3000, 10, 20), (6000, 64, 256)])
 def test_tf32_model_posterior_and_directions(n, d, m):
     """Fixed-hyper-parameter fit in the TF32-split mode: posterior weights, gradient Gram matrix and the
