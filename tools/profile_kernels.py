@@ -1,6 +1,7 @@
 """Runs the n-scale kernels of the sweep once each after a warm-up, at one 524288-row block of the
 headline shape (d=64, m=512), for ncu captures: kuf_kernel (pipelined), gemm_tn_kernel (symmetric),
-grad_gram_kernel (cached-Kfu variant and the fused recompute variant)."""
+grad_gram_kernel (cached-Kfu variant and the fused recompute variant), the TF32-split pair
+(kuf_tf32_kernel, grad_tf32_kernel) and the d x d Jacobi eigensolver."""
 import sys
 import torch
 sys.path.insert(0, '.')
@@ -16,10 +17,14 @@ alpha = torch.randn(m, dtype=torch.float64, device='cuda', generator=g)
 pack = ops.InducingPack(Z, ell)
 cpack = ops.InducingPack(Z, ell, alpha, 1.0, block=64)
 K = torch.empty(n, m, dtype=torch.float64, device='cuda')
+p32 = ops.InducingPackTF32(Z, ell)
 for it in range(2):
+    ops.kuf_tf32(X, p32, 1.0, out=K)
+    G32 = ops.grad_tf32(X, K, Z, ell, alpha, 1.0, 1.0)
     ops.kuf(X, pack, 1.0, out=K)
     P, byy = ops.inducing_stats(K, y, m)
     G, C = ops.grad_gram_cached(X, K, cpack, 1.0, want_G=False)
     G2, C2 = ops.grad_gram(X, cpack, want_G=False)
+    ev, comps = ops.eigh(C)
 torch.cuda.synchronize()
 print("ok", float(P[0, 0]), float(C[0, 0]), float(C2[0, 0]))
