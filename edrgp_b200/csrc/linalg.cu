@@ -281,17 +281,31 @@ __global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ L,
       for (int r = k0 + nb + tid; r < m; r += blockDim.x) {
         const double* lr = L + (int64_t)r * ldl + k0;
         double v = xs[r];
-#pragma unroll 8
-        for (int k = 0; k < NBK; ++k) if (k < nb) v = fma(-lr[k], xs[k0 + k], v);
-        xs[r] = v;
+        double lv[NBK];
+#pragma unroll
+        for (int k = 0; k < NBK; ++k) lv[k] = k < nb ? lr[k] : 0.0;          // all loads in flight at once
+        double v1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NBK; k += 2) {
+          v = fma(-lv[k], k < nb ? xs[k0 + k] : 0.0, v);
+          v1 = fma(-lv[k + 1], k + 1 < nb ? xs[k0 + k + 1] : 0.0, v1);
+        }
+        xs[r] = v + v1;
       }
     } else {
       // entries above: x_r -= sum_k L[k0+k][r] x_k   (coalesced over r)
       for (int r = tid; r < k0; r += blockDim.x) {
         double v = xs[r];
-#pragma unroll 8
-        for (int k = 0; k < NBK; ++k) if (k < nb) v = fma(-L[(int64_t)(k0 + k) * ldl + r], xs[k0 + k], v);
-        xs[r] = v;
+        double lv[NBK];
+#pragma unroll
+        for (int k = 0; k < NBK; ++k) lv[k] = k < nb ? L[(int64_t)(k0 + k) * ldl + r] : 0.0;
+        double v1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NBK; k += 2) {
+          v = fma(-lv[k], k < nb ? xs[k0 + k] : 0.0, v);
+          v1 = fma(-lv[k + 1], k + 1 < nb ? xs[k0 + k + 1] : 0.0, v1);
+        }
+        xs[r] = v + v1;
       }
     }
     __syncthreads();
