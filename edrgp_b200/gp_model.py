@@ -196,18 +196,22 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         Xd = torch.zeros(n, de, dtype=torch.float64, device=dev) if de != d else \
             torch.empty(n, d, dtype=torch.float64, device=dev)
         Xh = torch.from_numpy(X)
-        yd = torch.from_numpy(y).to(dev, non_blocking=True)
+        yh = torch.from_numpy(y)
+        yd = torch.empty(yh.shape, dtype=torch.float64, device=dev)
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         copy_stream.wait_stream(main)                       # Xd's allocation / zero fill
-        rows = int(max(1024, min(self.chunk_rows, max(n, 1))))
-        rows += rows & 1
+        # copy granularity: a quarter of chunk_rows (the size of the statistics blocks while the rows are
+        # arriving, see SparseGPRegression._chunks); the look-ahead below stays one full chunk_rows
+        rows = int(max(1024, min(self.chunk_rows // 4 if self.chunk_rows >= 65536 else self.chunk_rows, max(n, 1))))
+        rows &= ~1
+        ahead = int(max(rows, min(self.chunk_rows, max(n, 1))))
         events = []                                         # (end row, event), in row order
-        state = {'next': 0}
+        state = {'next': 0, 'y': None}
 
         def loader(s, e):
-            # enqueue copies up to one block beyond e, then make the compute stream wait for rows < e
-            while state['next'] < n and state['next'] < e + rows:
+            # enqueue copies up to one chunk_rows beyond e, then make the compute stream wait for rows < e
+            while state['next'] < n and state['next'] < e + ahead:
                 s0 = state['next']
                 e0 = min(n, s0 + rows)
                 with torch.cuda.stream(copy_stream):
@@ -216,15 +220,30 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                     ev.record(copy_stream)
                 events.append((s0, ev))
                 state['next'] = e0
+                if state['y'] is None:                      # the targets travel right behind the first X block
+                    with torch.cuda.stream(copy_stream):
+                        yd.copy_(yh, non_blocking=True)
+                        state['y'] = torch.cuda.Event()
+                        state['y'].record(copy_stream)
             while events and events[0][0] < e:
                 main.wait_event(events.pop(0)[1])
 
+        def y_loader():
+            if state['y'] is None:
+                loader(0, min(n, rows))
+            main.wait_event(state['y'])
+
         def check():
             loader(0, n)
+            y_loader()
             return nonfinite_check(Xd, yd)
 
         Xd.record_stream(copy_stream)
-        return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check, **kw)
+        yd.record_stream(copy_stream)
+        if n > 0:
+            loader(0, 0)          # the first blocks start travelling while the model is being set up
+        return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check,
+                                         y_loader=y_loader, **kw)
 
     def _check_data(self, X, y):
         """Validation of ``check_X_y`` (edrgp/gp_model/base.py:72-91) split so that the O(n d) part

@@ -165,7 +165,7 @@ class SparseGPRegression(object):
 
     def __init__(self, X, Y, kernel=None, Z=None, num_inducing=10, X_variance=None, mean_function=None,
                  normalizer=None, device=None, chunk_rows=262144, cache_bytes=None, noise_var=1.0,
-                 row_loader=None, pre_sync_check=None, input_dim=None, precision='fp64'):
+                 row_loader=None, pre_sync_check=None, input_dim=None, precision='fp64', y_loader=None):
         if X_variance is not None or mean_function is not None:
             raise NotImplementedError("uncertain inputs / mean functions are outside the B200 path")
         if not torch.cuda.is_available():
@@ -196,6 +196,7 @@ class SparseGPRegression(object):
         # enqueued (which does not need y), so the device is never idle behind this host-side set-up
         self._Y_raw = Yd
         self._Y_normalized = None
+        self._y_loader = y_loader                  # called once, right before y is first touched
         self.kern = RBF(self.input_dim) if kernel is None else kernel
         if self.kern.input_dim != self.input_dim:
             raise ValueError("kernel input_dim does not match X")
@@ -233,6 +234,9 @@ class SparseGPRegression(object):
     def _ensure_y(self):
         """Normalised targets (GPy ``Standardize``) and the global row count, reduced over ranks."""
         if self._Y_normalized is None:
+            if getattr(self, '_y_loader', None) is not None:
+                self._y_loader()
+                self._y_loader = None
             if self.normalizer is not None:
                 self.normalizer.scale_by_device(self._Y_raw, self._cnt_dev)
                 self._Y_normalized = self.normalizer.normalize_device(self._Y_raw)
@@ -282,8 +286,15 @@ class SparseGPRegression(object):
     # pass 1 + solve (+ pass 2)
     # -------------------------------------------------------------------------------------------
     def _chunks(self):
-        for s in range(0, self.n_local, self.chunk_rows):
-            yield s, min(self.n_local, s + self.chunk_rows)
+        """Row blocks of the n-scale passes.  While the rows are still arriving from the host
+        (``_row_loader``) the blocks are a quarter of ``chunk_rows``: the first kernel then waits for a
+        quarter of a block's transfer, and since a block's statistics take longer than the next block's
+        copy nothing waits afterwards (growing blocks would stall again at every growth step)."""
+        step = self.chunk_rows
+        if self._row_loader is not None and self.chunk_rows >= 65536:
+            step = (self.chunk_rows // 4) & ~1
+        for s in range(0, self.n_local, step):
+            yield s, min(self.n_local, s + step)
 
     def _kbuffers(self, want_cache):
         m = self.num_inducing
