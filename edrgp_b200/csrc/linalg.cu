@@ -634,10 +634,10 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* evals, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// One-sided Jacobi for large d (> 117): the same algorithm with W = C V and V in global memory
-// (column-major, L2-resident) and ONE KERNEL PER ROUND-ROBIN STEP, a warp per column pair, so that
-// all SMs work on the d/2 independent pairs of a step.  The host reads the "rotated" flag once per
-// sweep (the only place where this library synchronises the stream).
+// One-sided Jacobi for large d (> 116): the same algorithm with W = C V and V in global memory
+// (column-major, L2-resident), a warp per column pair, so that many SMs work on the d/2 independent
+// pairs of a step; all steps and sweeps run inside one persistent kernel (grid barrier per step) and
+// nothing synchronises the stream.
 // ---------------------------------------------------------------------------------------------
 __global__ void eig_init_kernel(const double* __restrict__ C, int d, double* __restrict__ W, double* __restrict__ V) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,42 +647,128 @@ __global__ void eig_init_kernel(const double* __restrict__ C, int d, double* __r
   V[i] = r == c ? 1.0 : 0.0;
 }
 
-__global__ void __launch_bounds__(256) eig_step_kernel(double* __restrict__ W, double* __restrict__ V, int d, int step,
-                                                       int* __restrict__ rotated) {
+// All sweeps in ONE persistent kernel: a warp per column pair, a grid-wide barrier (global counter, every
+// CTA resident: the grid never exceeds the SM count) after every round-robin step instead of a kernel
+// launch (~11 us each, 6 600 of them at d = 512).  W and V live in global memory (L2) and are accessed
+// with ld/st.global.cg: another CTA rewrote them one step ago.  ctrl[0] = barrier counter,
+// ctrl[1 + (sweep & 1)] = "a rotation happened in this sweep", ctrl[3] = sweeps done, ctrl[4] = barrier
+// time-out (never expected; it keeps a lost CTA from hanging the device).
+__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& target) {
+  __syncthreads();
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    int ok = 1;
+    unsigned int seen;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (++spins > 200000000LL) { ok = 0; break; }
+    } while ((int)(seen - target) < 0);
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// EPL > 0: d <= 32 EPL and a lane keeps its EPL entries of all four columns (w_p, w_q, v_p, v_q) in
+// registers: ONE L2 round trip per step (all loads in flight before the first use) instead of two
+// passes of short dependent batches.  EPL = 0: any d, looping.
+template <int EPL>
+__global__ void __launch_bounds__(256) eig_persistent_kernel(double* __restrict__ W, double* __restrict__ V, int d,
+                                                             int max_sweeps, unsigned int* __restrict__ ctrl) {
   const int dd = d + (d & 1), np = dd / 2;
   const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (k >= np) return;
-  const int a0 = (k == 0) ? dd - 1 : (step + k) % (dd - 1);
-  const int b0 = (step + dd - 1 - k) % (dd - 1);
-  const int p = min(a0, b0), q = max(a0, b0);
-  if (q >= d) return;
-  double* wa = W + (int64_t)p * d;
-  double* wb = W + (int64_t)q * d;
-  double alpha = 0.0, beta = 0.0, gamma = 0.0;
-  for (int r = lane; r < d; r += 32) {
-    const double x = wa[r], y = wb[r];
-    alpha = fma(x, x, alpha); beta = fma(y, y, beta); gamma = fma(x, y, gamma);
-  }
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  unsigned int target = 0;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    unsigned int* flag = ctrl + 1 + (sweep & 1);
+    for (int step = 0; step < dd - 1; ++step) {
+      for (int k = gw; k < np; k += nw) {
+        int a0 = step + k, b0 = step + dd - 1 - k;
+        if (a0 >= dd - 1) a0 -= dd - 1;
+        if (b0 >= dd - 1) b0 -= dd - 1;
+        if (k == 0) a0 = dd - 1;
+        const int p = min(a0, b0), q = max(a0, b0);
+        if (q >= d) continue;
+        double* wa = W + (int64_t)p * d;
+        double* wb = W + (int64_t)q * d;
+        double* va = V + (int64_t)p * d;
+        double* vb = V + (int64_t)q * d;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        if (EPL > 0) {
+          constexpr int E = EPL > 0 ? EPL : 1;
+          double xa[E], xb[E], ua[E], ub[E];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-    beta += __shfl_xor_sync(0xffffffffu, beta, o);
-    gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+          for (int e = 0; e < E; ++e) {
+            const int r = lane + 32 * e;
+            const bool ok = r < d;
+            xa[e] = ok ? __ldcg(wa + r) : 0.0;
+            xb[e] = ok ? __ldcg(wb + r) : 0.0;
+            ua[e] = ok ? __ldcg(va + r) : 0.0;
+            ub[e] = ok ? __ldcg(vb + r) : 0.0;
+          }
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            alpha = fma(xa[e], xa[e], alpha); beta = fma(xb[e], xb[e], beta); gamma = fma(xa[e], xb[e], gamma);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+            beta += __shfl_xor_sync(0xffffffffu, beta, o);
+            gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+          }
+          if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) continue;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
+          if (lane == 0) *flag = 1u;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int r = lane + 32 * e;
+            if (r < d) {
+              __stcg(wa + r, c * xa[e] - s * xb[e]); __stcg(wb + r, s * xa[e] + c * xb[e]);
+              __stcg(va + r, c * ua[e] - s * ub[e]); __stcg(vb + r, s * ua[e] + c * ub[e]);
+            }
+          }
+          continue;
+        }
+        for (int r = lane; r < d; r += 32) {
+          const double x = __ldcg(wa + r), y = __ldcg(wb + r);
+          alpha = fma(x, x, alpha); beta = fma(y, y, beta); gamma = fma(x, y, gamma);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+          beta += __shfl_xor_sync(0xffffffffu, beta, o);
+          gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+        }
+        if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) continue;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
+        if (lane == 0) *flag = 1u;
+        for (int r = lane; r < d; r += 32) {
+          const double x = __ldcg(wa + r), y = __ldcg(wb + r);
+          __stcg(wa + r, c * x - s * y); __stcg(wb + r, s * x + c * y);
+          const double u = __ldcg(va + r), v = __ldcg(vb + r);
+          __stcg(va + r, c * u - s * v); __stcg(vb + r, s * u + c * v);
+        }
+      }
+      if (!grid_barrier(ctrl, gridDim.x, target)) { if (threadIdx.x == 0) ctrl[4] = 1u; return; }
+    }
+    // every CTA reads this sweep's flag after the last barrier; the other flag is cleared for the next sweep
+    unsigned int rot;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(rot) : "l"(flag) : "memory");
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[1 + ((sweep + 1) & 1)] = 0u;
+    if (!grid_barrier(ctrl, gridDim.x, target)) { if (threadIdx.x == 0) ctrl[4] = 1u; return; }
+    if (rot == 0u) break;
   }
-  if (!(gamma * gamma > 1e-30 * alpha * beta) || fabs(gamma) < 1e-300) return;
-  const double zeta = (beta - alpha) / (2.0 * gamma);
-  const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  const double c = fast_rsqrt(fma(tt, tt, 1.0)), s = tt * c;
-  if (lane == 0) *rotated = 1;
-  double* va = V + (int64_t)p * d;
-  double* vb = V + (int64_t)q * d;
-  for (int r = lane; r < d; r += 32) {
-    const double x = wa[r], y = wb[r];
-    wa[r] = c * x - s * y; wb[r] = s * x + c * y;
-    const double u = va[r], v = vb[r];
-    va[r] = c * u - s * v; vb[r] = s * u + c * v;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[3] = (unsigned int)sweep;
 }
 
 // lam[i] = v_i^T C v_i (one warp per vector)
@@ -723,34 +809,30 @@ __global__ void eig_finish_kernel(const double* __restrict__ lam, const double* 
   for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[(int64_t)i * d + r];
 }
 
-size_t eigh_workspace_doubles(int d) { return d <= 116 ? (size_t)d * d : (size_t)2 * d * d + d + 2; }
+size_t eigh_workspace_doubles(int d) { return d <= 116 ? (size_t)d * d : (size_t)2 * d * d + d + 4; }
 
 static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double* evals, double* comps, int* sweeps,
                                      cudaStream_t st) {
   double* W = ws;
   double* V = ws + (size_t)d * d;
   double* lam = V + (size_t)d * d;
-  int* flag = reinterpret_cast<int*>(lam + d);
+  unsigned int* ctrl = reinterpret_cast<unsigned int*>(lam + d);     // 8 words (eigh_workspace_doubles reserves 4 doubles)
   const int dd = d + (d & 1), np = dd / 2;
   eig_init_kernel<<<(unsigned)(((int64_t)d * d + 255) / 256), 256, 0, st>>>(C, d, W, V); count_launch();
-  int sweep = 0;
-  for (; sweep < 60; ++sweep) {
-    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
-    for (int step = 0; step < dd - 1; ++step) {
-      eig_step_kernel<<<(np + 7) / 8, 256, 0, st>>>(W, V, d, step, flag); count_launch();
-    }
-    int rotated = 0;
-    e = cudaMemcpyAsync(&rotated, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    if (!rotated) break;
-  }
+  cudaError_t e = cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  int grid = (np + 7) / 8;                       // 8 warps (pairs) per CTA; every CTA must be resident: <= one per SM
+  if (grid > sms) grid = sms;
+  if (d <= 128) eig_persistent_kernel<4><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
+  else if (d <= 256) eig_persistent_kernel<8><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
+  else if (d <= 512) eig_persistent_kernel<16><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
+  else eig_persistent_kernel<0><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
+  count_launch();
   if (sweeps) {
-    cudaError_t e = cudaMemcpyAsync(sweeps, &sweep, sizeof(int), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(st);       // `sweep` lives on this stack frame
+    e = cudaMemcpyAsync(sweeps, ctrl + 3, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
   }
   eig_rayleigh_kernel<<<(d + 7) / 8, 256, 0, st>>>(C, V, d, lam); count_launch();
