@@ -153,7 +153,18 @@ def make_cpu_sample(rows, d, m, seed=0):
     return w
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank: lift the BLAS pools back to all host cores (the CPU
+    arm runs on rank 0 alone)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def time_cpu(rows, d, m, steps, warmup):
+    use_all_host_threads()
     w = make_cpu_sample(rows, d, m)
     times = []
     for i in range(warmup + steps):
@@ -170,6 +181,7 @@ def run_reference(args):
     if rank != 0:
         return
     rows = args.cpu_rows or 131072
+    use_all_host_threads()
     cores = cpu_threads()
     pts, sec = time_cpu(rows, args.d, args.m, args.steps, args.warmup)
     sample = "%d rows of the same generator per step (n=%d named shape), all host BLAS threads" % (rows, args.n)
@@ -206,9 +218,13 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # ONE JSON line on stdout: native libraries that write to file descriptor 1 (NCCL's version banner)
+    # are sent to stderr; the line itself goes through a duplicate of the original descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ['NCCL_DEBUG'] = 'WARN'        # keep NCCL's version banner off stdout: ONE JSON line
         tdist.init_process_group('nccl', device_id=dev)
     n, d, m = args.n, args.d, args.m
     lo, hi = edist.shard_bounds(n, rank, world)
@@ -474,7 +490,8 @@ def run_ours(args):
         "edr_fit": edr_fit,
         "tf32x3_mode": tf32_mode,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout)
+    real_stdout.flush()
     if world > 1:
         tdist.destroy_process_group()
 

@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256) eig_persistent_kernel(double* __restrict_
         double* va = V + (int64_t)p * d;
         double* vb = V + (int64_t)q * d;
         double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        if (EPL > 0) {
+        if constexpr (EPL > 0) {
           constexpr int E = EPL > 0 ? EPL : 1;
           double xa[E], xb[E], ua[E], ub[E];
 #pragma unroll
@@ -735,8 +735,7 @@ __global__ void __launch_bounds__(256) eig_persistent_kernel(double* __restrict_
               __stcg(va + r, c * ua[e] - s * ub[e]); __stcg(vb + r, s * ua[e] + c * ub[e]);
             }
           }
-          continue;
-        }
+        } else {
         for (int r = lane; r < d; r += 32) {
           const double x = __ldcg(wa + r), y = __ldcg(wb + r);
           alpha = fma(x, x, alpha); beta = fma(y, y, beta); gamma = fma(x, y, gamma);
@@ -757,6 +756,7 @@ __global__ void __launch_bounds__(256) eig_persistent_kernel(double* __restrict_
           __stcg(wa + r, c * x - s * y); __stcg(wb + r, s * x + c * y);
           const double u = __ldcg(va + r), v = __ldcg(vb + r);
           __stcg(va + r, c * u - s * v); __stcg(vb + r, s * u + c * v);
+        }
         }
       }
       if (!grid_barrier(ctrl, gridDim.x, target)) { if (threadIdx.x == 0) ctrl[4] = 1u; return; }

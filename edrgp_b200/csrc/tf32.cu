@@ -354,7 +354,6 @@ __global__ void __launch_bounds__(THREADS, 1) kuf_tf32_kernel(const Params p) {
     const bool vec_ok = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 31) == 0);
     uint32_t it = 0, tl = 0;
     for (int64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tl) {
-      const int64_t row = t * TM + row_in_tile;
       float cx = 0.f;
       bool have_cx = false;
       for (int c = 0; c < nchunks; ++c, ++it) {
