@@ -30,6 +30,9 @@ SIGNATURES = {
     'edrgp_pack_grad_tf32_bytes': (_sz, [_int, _int]),
     'edrgp_pack_grad_tf32': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
     'edrgp_grad_tf32x3': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _dbl, _c_dp, _c_dp, _int, _c_dp, _i64, _c_dp]),
+    'edrgp_pack_weights_tf32_bytes': (_sz, [_int]),
+    'edrgp_pack_weights_tf32': (_int, [_c_dp, _i64, _dbl, _int, _c_dp, _c_dp]),
+    'edrgp_weights_tf32x3': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _c_dp, _c_dp, _dbl, _c_dp, _i64, _c_dp, _c_dp]),
     'edrgp_grad_gram_workspace_bytes': (_sz, [_int]),
     'edrgp_grad_gram': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_grad_gram_cached': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _dbl, _c_dp, _int, _c_dp, _i64, _c_dp,

@@ -141,6 +141,32 @@ int edrgp_grad_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const doub
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "grad_tf32x3");
 }
 
+size_t edrgp_pack_weights_tf32_bytes(int m) {
+  if (m <= 0 || m > 512) return 0;
+  return edrgp::pack_weights_tf32_bytes(m);
+}
+
+int edrgp_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, void* stream) {
+  if (!M || !pack || m <= 0 || ldm < m) return fail(EDRGP_ERR_ARG, "pack_weights_tf32: bad argument");
+  if (m > 512) return fail(EDRGP_ERR_UNSUPPORTED, "pack_weights_tf32: m=%d > 512 is outside the TF32-split weights", m);
+  if (!aligned16(pack)) return fail(EDRGP_ERR_ARG, "pack_weights_tf32: pack must be 16-byte aligned");
+  cudaError_t e = edrgp::launch_pack_weights_tf32(M, ldm, scale, m, pack, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "pack_weights_tf32");
+}
+
+int edrgp_weights_tf32x3(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
+                         const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, void* stream) {
+  if (!K || !pack || n <= 0 || m <= 0) return fail(EDRGP_ERR_ARG, "weights_tf32x3: bad argument");
+  if (m > 512) return fail(EDRGP_ERR_UNSUPPORTED, "weights_tf32x3: m=%d > 512 is outside the TF32-split weights", m);
+  if (ldk < m || (ldk & 1) || (T && (ldt < m || (ldt & 1)))) return fail(EDRGP_ERR_ARG, "weights_tf32x3: ldk / ldt must be even and >= m");
+  if ((y == nullptr) != (alpha == nullptr)) return fail(EDRGP_ERR_ARG, "weights_tf32x3: y and alpha go together");
+  if (!aligned16(K) || !aligned16(pack) || (T && !aligned16(T))) return fail(EDRGP_ERR_ARG, "weights_tf32x3: K, pack and T must be 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "weights_tf32x3: no CUDA device");
+  cudaError_t e = edrgp::launch_weights_tf32(K, n, m, ldk, pack, y, alpha, c_ya, T, ldt, rowsum, sms, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "weights_tf32x3");
+}
+
 size_t edrgp_grad_gram_workspace_bytes(int d) {
   const int dp = edrgp::padded_dim(d);
   int sms = sm_count_cached();

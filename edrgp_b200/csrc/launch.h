@@ -61,6 +61,12 @@ cudaError_t launch_grad_tf32(const double* X, int64_t ldx, int64_t n, int d, con
                              const double* ell, const void* pack, int m, double* G, int64_t ldg, int sms,
                              cudaStream_t st);
 
+size_t pack_weights_tf32_bytes(int m);
+cudaError_t launch_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, cudaStream_t st);
+cudaError_t launch_weights_tf32(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
+                                const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, int sms,
+                                cudaStream_t st);
+
 cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

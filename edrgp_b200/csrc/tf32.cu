@@ -760,6 +760,352 @@ cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, cons
   return cudaGetLastError();
 }
 
+// =================================================================================================
+// TF32-split weights of the hyper-parameter gradient (optimisation path, unit a7):
+//     T = K o (c_ya y alpha^T + K M'),   rowsum(T)        (M' = c_km M, symmetric, m <= 512)
+// i.e. the n x m x m contraction U = K M' on tcgen05 -- 2 n m^2 flop, the largest cost of an objective +
+// gradient evaluation -- with the FP64 K tile converted on the fly exactly as in grad_tf32_kernel, all
+// four 128-column accumulators of a row tile live in the 512 TMEM columns, and an FP64 epilogue that
+// re-reads the K tile (L2), forms T and streams it out with the quad-transposed 32-byte accesses of
+// kuf_tf32_kernel.  Column sums of T are left to a column-moment pass.
+//   warp 0      producer : M' sub-blocks (32 k x 128 columns: hi | lo, 32 KB) by TMA bulk copy, ring of 4
+//   warp 1      MMA      : per k-block and column chunk 12 tcgen05.mma (N = 128)
+//   warps 2-17  convert  : K tile k-blocks -> hi / lo TF32 (two 32 KB stages, three blocks in flight in registers)
+//   warps 18-21 epilogue
+// =================================================================================================
+namespace w32 {
+using namespace tf32;
+
+constexpr int SA = 2, SB = 4;
+constexpr int A_BYTES = 2 * BLK_BYTES;               // 32 KB
+constexpr int B_BYTES = 2 * TN * 128;                // 32 KB: 128 columns x 32 k, hi | lo
+constexpr int CONV_W = 16, EPI_W = 4, PF = 3;
+constexpr int NTHREADS = 32 * (2 + CONV_W + EPI_W);
+constexpr int MAX_M = 512;
+
+struct WParams {
+  const double* Kin; int64_t ldk;
+  const uint8_t* pack;
+  const double* y; const double* alpha; double c_ya;
+  double* T; int64_t ldt;
+  double* rowsum;
+  int64_t n, ntiles;
+  int m, kblocks, nchunks;
+};
+
+struct __align__(8) WBars {
+  uint64_t a_full[SA], a_empty[SA];
+  uint64_t b_full[SB], b_empty[SB];
+  uint64_t acc_full[4], acc_empty[4];
+};
+
+// pack[(kb * nchunks + c)] = hi | lo images of M'[128 c + r][32 kb + kk] (rows = output columns, K-major)
+__global__ void pack_weights_tf32_kernel(const double* __restrict__ M, int64_t ldm, double scale, int m, int nchunks,
+                                         uint8_t* __restrict__ pack) {
+  const int kblocks = (m + KBLK - 1) / KBLK;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)kblocks * nchunks * TN * KBLK;
+  if (idx >= total) return;
+  const int kk = (int)(idx % KBLK);
+  const int r = (int)((idx / KBLK) % TN);
+  const int c = (int)((idx / (KBLK * TN)) % nchunks);
+  const int kb = (int)(idx / ((int64_t)KBLK * TN * nchunks));
+  const int j = c * TN + r, k = kb * KBLK + kk;
+  double v = 0.0;
+  if (j < m && k < m) v = scale * M[(int64_t)j * ldm + k];
+  uint32_t hi, lo;
+  split_tf32(v, hi, lo);
+  uint8_t* blk = pack + (size_t)(kb * nchunks + c) * B_BYTES;
+  const uint32_t off = sw128_offset(r, kk);
+  *reinterpret_cast<uint32_t*>(blk + off) = hi;
+  *reinterpret_cast<uint32_t*>(blk + TN * 128 + off) = lo;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                           // SA x 32 KB
+  uint8_t* sB = smem + (size_t)SA * A_BYTES;                    // SB x 32 KB
+  double* sAlpha = reinterpret_cast<double*>(sB + (size_t)SB * B_BYTES);      // MAX_M doubles
+  WBars* bars = reinterpret_cast<WBars*>(sAlpha + MAX_M);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.kblocks, NC = p.nchunks;
+  const int64_t my_tiles = blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = my_tiles * KB;
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(&bars->a_full[s], CONV_W); mbar_init(&bars->a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], EPI_W); }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < MAX_M; i += NTHREADS) sAlpha[i] = (i < p.m && p.alpha != nullptr) ? p.alpha[i] : 0.0;
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 1;
+      for (int64_t it = 0; it < total; ++it) {
+        const int kb = (int)(it % KB);
+        for (int c = 0; c < NC; ++c) {
+          mbar_wait(&bars->b_empty[s], ph);
+          mbar_arrive_expect_tx(&bars->b_full[s], (uint32_t)B_BYTES);
+          bulk_g2s(sB + (size_t)s * B_BYTES, p.pack + (size_t)(kb * NC + c) * B_BYTES, (uint32_t)B_BYTES, &bars->b_full[s]);
+          if (++s == SB) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(TM, TN);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int64_t tl = 0; tl < my_tiles; ++tl) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&bars->a_full[sa], pa);
+          const uint32_t aa = smem_u32(sA + (size_t)sa * A_BYTES);
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(&bars->b_full[sb], pb);
+            if (kb == 0) mbar_wait(&bars->acc_empty[c], (uint32_t)(tl & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t ba = smem_u32(sB + (size_t)sb * B_BYTES);
+            const uint32_t dcol = tmem_base + (uint32_t)(c * TN);
+            uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll 1
+            for (int combo = 0; combo < 3; ++combo) {
+              const uint32_t aoff = (combo == 0) ? (uint32_t)BLK_BYTES : 0u;          // K lo | hi | hi
+              const uint32_t boff = (combo == 1) ? (uint32_t)(TN * 128) : 0u;         // M' hi | lo | hi
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_tf32(dcol, smem_desc_sw128(aa + aoff + ks * 32), smem_desc_sw128(ba + boff + ks * 32), idesc, acc);
+                acc = 1;
+              }
+            }
+            tc_commit(&bars->b_empty[sb]);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(&bars->a_empty[sa]);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        for (int c = 0; c < NC; ++c) tc_commit(&bars->acc_full[c]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + CONV_W) {
+    const int ct = tid - 64;                          // 0 .. 511
+    const int g = ct & 7, rbase = ct >> 3;
+    const bool fastp = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Kin) & 31) == 0) && (p.m % KBLK == 0);
+    double buf[PF][2][4];
+    int64_t ld_tile = blockIdx.x;
+    int ld_kb = 0;
+    const double* rp0 = nullptr;
+    const double* rp1 = nullptr;
+    auto set_tile = [&]() {
+      const int64_t r0 = ld_tile * TM + rbase, r1 = r0 + 64;
+      rp0 = r0 < p.n ? p.Kin + r0 * p.ldk + 4 * g : nullptr;
+      rp1 = r1 < p.n ? p.Kin + r1 * p.ldk + 4 * g : nullptr;
+    };
+    set_tile();
+    auto load1 = [&](const double* rp, double (&dst)[4]) {
+      dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+      if (rp != nullptr) {
+        const double* src = rp + ld_kb * KBLK;
+        if (fastp) {
+          asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f64 {%0, %1, %2, %3}, [%4];"
+                       : "=d"(dst[0]), "=d"(dst[1]), "=d"(dst[2]), "=d"(dst[3]) : "l"(src));
+        } else {
+          const int c0 = ld_kb * KBLK + 4 * g;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + e < p.m) dst[e] = __ldg(src + e);
+        }
+      }
+    };
+    auto load = [&](double (&dst)[2][4]) {
+      load1(rp0, dst[0]);
+      load1(rp1, dst[1]);
+      if (++ld_kb == KB) { ld_kb = 0; ld_tile += gridDim.x; set_tile(); }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < total) load(buf[u]);
+    uint32_t s = 0, ph = 1;
+    const uint32_t off0 = sw128_offset(rbase, 4 * g), off1 = sw128_offset(rbase + 64, 4 * g);
+    for (int64_t it0 = 0; it0 < total; it0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int64_t it = it0 + u;
+        if (it < total) {
+          mbar_wait(&bars->a_empty[s], ph);
+          uint8_t* dstA = sA + (size_t)s * A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32_bits_nonneg(buf[u][i][e], hi[e], lo[e]);
+            const uint32_t off = i ? off1 : off0;
+            *reinterpret_cast<uint4*>(dstA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dstA + BLK_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_full[s]);
+          if (it + PF < total) load(buf[u]);
+          if (++s == SA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: T = K o (c_ya y alpha^T + U), row sums; quad-transposed accesses =====
+    const int q = warp & 3;
+    const int jq = lane & 3;
+    const bool vec_ok = (p.ldk % 4 == 0) && (p.ldt % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Kin) & 31) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.T) & 31) == 0);
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t quad_row0 = (blockIdx.x + tl * gridDim.x) * TM + q * 32 + (lane & ~3);
+      double yv[4], rsum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho)
+        yv[rho] = (p.y != nullptr && quad_row0 + rho < p.n) ? p.c_ya * __ldg(p.y + quad_row0 + rho) : 0.0;
+      for (int c = 0; c < NC; ++c) {
+        mbar_wait(&bars->acc_full[c], (uint32_t)(tl & 1));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * TN);
+#pragma unroll 1
+        for (int hb = 0; hb < 4; ++hb) {
+          uint32_t v[32];
+          tmem_ld32(taddr + hb * 32, v);
+          tmem_ld_wait();
+          if (hb == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[c]);
+          }
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = __uint_as_float(v[i]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col0 = c * TN + hb * 32 + h * 16 + jq * 4;
+            // this lane's K entries for the quad's four rows (a full 128-byte line per row and quad)
+            double kv[4][4];
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) {
+              const int64_t row = quad_row0 + rho;
+              kv[rho][0] = kv[rho][1] = kv[rho][2] = kv[rho][3] = 0.0;
+              if (row < p.n) {
+                const double* src = p.Kin + row * p.ldk + col0;
+                if (vec_ok && col0 + 3 < p.m) {
+                  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                               : "=d"(kv[rho][0]), "=d"(kv[rho][1]), "=d"(kv[rho][2]), "=d"(kv[rho][3]) : "l"(src));
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (col0 + e < p.m) kv[rho][e] = __ldg(src + e);
+                }
+              }
+            }
+#pragma unroll
+            for (int bit = 1; bit <= 2; bit <<= 1) {
+              const bool up = (lane & bit) != 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j & bit) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float& lo_u = w[16 * h + 4 * j + e];
+                  float& hi_u = w[16 * h + 4 * (j | bit) + e];
+                  const float send = up ? lo_u : hi_u;
+                  const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                  if (up) lo_u = recv; else hi_u = recv;
+                }
+              }
+            }
+            // w[16 h + 4 rho + e] = U(row quad_row0 + rho, column col0 + e)
+            double al[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) al[e] = sAlpha[(col0 + e) & (MAX_M - 1)];
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) {
+              const int64_t row = quad_row0 + rho;
+              double o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                o[e] = kv[rho][e] * fma(yv[rho], al[e], (double)w[16 * h + 4 * rho + e]);
+                rsum[rho] += (col0 + e < p.m) ? o[e] : 0.0;
+              }
+              if (row < p.n && p.T != nullptr) {
+                double* out = p.T + row * p.ldt + col0;
+                if (vec_ok && col0 + 3 < p.m) {
+                  st_v4_f64(out, o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (col0 + e < p.m) out[e] = o[e];
+                }
+              }
+            }
+          }
+        }
+      }
+      if (p.rowsum != nullptr) {
+#pragma unroll
+        for (int rho = 0; rho < 4; ++rho) {
+          rsum[rho] += __shfl_xor_sync(0xffffffffu, rsum[rho], 1);
+          rsum[rho] += __shfl_xor_sync(0xffffffffu, rsum[rho], 2);
+        }
+        const int64_t row = quad_row0 + jq;
+        const double mine = jq == 0 ? rsum[0] : jq == 1 ? rsum[1] : jq == 2 ? rsum[2] : rsum[3];
+        if (row < p.n) p.rowsum[row] = mine;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t smem_bytes() {
+  return 1024 + (size_t)SA * A_BYTES + (size_t)SB * B_BYTES + MAX_M * 8 + sizeof(WBars) + 16;
+}
+
+}  // namespace w32
+
+size_t pack_weights_tf32_bytes(int m) {
+  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nc = (m + tf32::TN - 1) / tf32::TN;
+  return (size_t)kb * nc * w32::B_BYTES;
+}
+
+cudaError_t launch_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, cudaStream_t st) {
+  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nc = (m + tf32::TN - 1) / tf32::TN;
+  const int64_t total = (int64_t)kb * nc * tf32::TN * tf32::KBLK;
+  w32::pack_weights_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, ldm, scale, m, nc,
+                                                                                static_cast<uint8_t*>(pack));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_weights_tf32(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
+                                const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, int sms,
+                                cudaStream_t st) {
+  w32::WParams p{};
+  p.Kin = K; p.ldk = ldk; p.pack = static_cast<const uint8_t*>(pack); p.y = y; p.alpha = alpha; p.c_ya = c_ya;
+  p.T = T; p.ldt = ldt; p.rowsum = rowsum; p.n = n; p.ntiles = (n + tf32::TM - 1) / tf32::TM; p.m = m;
+  p.kblocks = (m + tf32::KBLK - 1) / tf32::KBLK; p.nchunks = (m + tf32::TN - 1) / tf32::TN;
+  const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
+  const size_t smem = w32::smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(w32::weights_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  w32::weights_tf32_kernel<<<grid, w32::NTHREADS, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
 size_t pack_grad_tf32_bytes(int m, int d) {
   const int npad = (d + 1 + 15) / 16 * 16;
   return (size_t)((m + tf32::KBLK - 1) / tf32::KBLK) * 2 * npad * 128;

@@ -487,6 +487,8 @@ class SparseGPRegression(object):
         if getattr(self, '_Tbuf', None) is None or self._Tbuf.shape[1] != ldk:
             self._Tbuf = torch.empty(min(self.chunk_rows, self.n_local), ldk, dtype=F64, device=dev)
         y = self.Y_normalized
+        # TF32-split mode: the n m^2 contraction K M of the weights on tcgen05 (m <= 512)
+        tf32_weights = self.precision == 'tf32x3' and m <= 512
         for i, (s, e) in enumerate(self._chunks()):
             if self._Kcache is not None:
                 Kc = self._Kcache[s:e]
@@ -495,12 +497,22 @@ class SparseGPRegression(object):
                 ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
                 self.kernel_launches += 1
             Tc = self._Tbuf[:e - s]
-            rs = ops.weights(Kc, Mmat, m, y=y[s:e], alpha=self.alpha, c_ya=beta, c_km=2.0, T=Tc,
-                             want_rowsum=True, colsum=cs, accumulate=True)
+            if tf32_weights:
+                rs = ops.weights_tf32(Kc, Mmat, m, y=y[s:e], alpha=self.alpha, c_ya=beta, c_km=2.0, T=Tc,
+                                      want_rowsum=True)
+            else:
+                rs = ops.weights(Kc, Mmat, m, y=y[s:e], alpha=self.alpha, c_ya=beta, c_km=2.0, T=Tc,
+                                 want_rowsum=True, colsum=cs, accumulate=True)
             ops.gemm_tn(Tc, self.X[s:e], ka=m, out=S, accumulate=True)
             ops.col_moments(self.X[s:e], weight=rs, out=mom, accumulate=True)
             self.kernel_launches += 6
-        dist.allreduce_sum_(S, cs, mom)
+        if tf32_weights:
+            # column sums of T without a pass over it: sum_i K_ij (beta y_i alpha_j + 2 (K M)_ij)
+            #   = beta alpha_j b_j + 2 sum_k P_jk M_kj with the (already reduced) statistics P, b
+            dist.allreduce_sum_(S, mom)
+            cs = beta * self.alpha * self._stats[1][:m] + 2.0 * (P * Mmat[:, :m]).sum(1)
+        else:
+            dist.allreduce_sum_(S, cs, mom)
         S = S[:, :d]
         R = mom[self.d_even:self.d_even + d]                     # sum_i rowsum(T)_i x_iq^2
         Z = self._Z_dev[:, :d]

@@ -439,6 +439,26 @@ def weights(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, want_r
     return rowsum
 
 
+def weights_tf32(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, want_rowsum=False):
+    """``weights`` in the TF32-split mode (m <= 512): T = K o (c_ya y alpha^T + c_km K M) with the K M
+    contraction on tcgen05; returns rowsum or None.  Column sums: ``col_moments(T)``."""
+    lib = _lib.load()
+    _need_cuda(K, M, y, alpha, T)
+    n, ldk = K.shape
+    m = ldk if m is None else m
+    pack = torch.empty(lib.edrgp_pack_weights_tf32_bytes(m) // 8, dtype=F64, device=K.device)
+    if pack.numel() == 0:
+        raise ValueError("the TF32-split weights cover m <= 512 (got %d)" % m)
+    _lib.check(lib.edrgp_pack_weights_tf32(_ptr(M), M.shape[1], float(c_km), m, _ptr(pack), _stream()),
+               'edrgp_pack_weights_tf32')
+    rowsum = torch.empty(n, dtype=F64, device=K.device) if want_rowsum else None
+    with _Timed('weights'):
+        _lib.check(lib.edrgp_weights_tf32x3(_ptr(K), n, m, ldk, _ptr(pack), _ptr(y), _ptr(alpha), float(c_ya), _ptr(T),
+                                            0 if T is None else T.shape[1], _ptr(rowsum), _stream()),
+                   'edrgp_weights_tf32x3')
+    return rowsum
+
+
 def count_nonfinite(*tensors):
     """Device int32 tensor holding the number of NaN / Inf entries over all given tensors."""
     lib = _lib.load()

@@ -111,6 +111,18 @@ int edrgp_pack_grad_tf32(const double* Z, const double* ell, const double* coef,
 int edrgp_grad_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, double sf2,
                       const double* ell, const void* pack, int m, double* G, int64_t ldg, void* stream);
 
+/* The weights of the hyper-parameter gradient in the TF32-split mode (edrgp_weights is the FP64 form):
+ *     T = K o (c_ya y alpha^T + K M'),  rowsum_i = sum_j T_ij,        M' = scale * M (symmetric), m <= 512
+ * -- dL/dKfu applied to the stored cross-covariance, GPy VarDTC dL_dpsi1 / dL_dpsi2 reached from
+ * model.optimize (edrgp/gp_model/base.py:69) -- with the n x m x m contraction K M' on tcgen05 (K split
+ * into hi / lo TF32 on the fly, M' prepacked by edrgp_pack_weights_tf32, FP32 accumulation in tensor
+ * memory) and the elementwise part in FP64.  y, alpha may be NULL (c_ya term dropped); T (n, ldt) and
+ * rowsum (n) may be NULL; ldk, ldt even.  Column sums of T: edrgp_col_moments on T. */
+size_t edrgp_pack_weights_tf32_bytes(int m);
+int edrgp_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, void* stream);
+int edrgp_weights_tf32x3(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
+                         const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K1+K4+K5 fused  posterior-mean gradients and their outer product.
  *   G_iq = scale * sum_j K_ij alpha_j (z_jq - x_iq) / l_q^2      (zero where clip(r^2) == 0)
