@@ -156,11 +156,11 @@ int edrgp_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, v
 
 int edrgp_weights_tf32x3(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
                          const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, void* stream) {
-  if (!K || !pack || n <= 0 || m <= 0) return fail(EDRGP_ERR_ARG, "weights_tf32x3: bad argument");
+  if (!K || !pack || !T || n <= 0 || m <= 0) return fail(EDRGP_ERR_ARG, "weights_tf32x3: bad argument");
   if (m > 512) return fail(EDRGP_ERR_UNSUPPORTED, "weights_tf32x3: m=%d > 512 is outside the TF32-split weights", m);
-  if (ldk < m || (ldk & 1) || (T && (ldt < m || (ldt & 1)))) return fail(EDRGP_ERR_ARG, "weights_tf32x3: ldk / ldt must be even and >= m");
+  if (ldk < m || (ldk & 1) || ldt < m || (ldt & 1)) return fail(EDRGP_ERR_ARG, "weights_tf32x3: ldk / ldt must be even and >= m");
   if ((y == nullptr) != (alpha == nullptr)) return fail(EDRGP_ERR_ARG, "weights_tf32x3: y and alpha go together");
-  if (!aligned16(K) || !aligned16(pack) || (T && !aligned16(T))) return fail(EDRGP_ERR_ARG, "weights_tf32x3: K, pack and T must be 16-byte aligned");
+  if (!aligned16(K) || !aligned16(pack) || !aligned16(T)) return fail(EDRGP_ERR_ARG, "weights_tf32x3: K, pack and T must be 16-byte aligned");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "weights_tf32x3: no CUDA device");
   cudaError_t e = edrgp::launch_weights_tf32(K, n, m, ldk, pack, y, alpha, c_ya, T, ldt, rowsum, sms, (cudaStream_t)stream);

@@ -768,17 +768,20 @@ cudaError_t launch_kuf_tf32(const double* X, int64_t ldx, int64_t n, int d, cons
 // four 128-column accumulators of a row tile live in the 512 TMEM columns, and an FP64 epilogue that
 // re-reads the K tile (L2), forms T and streams it out with the quad-transposed 32-byte accesses of
 // kuf_tf32_kernel.  Column sums of T are left to a column-moment pass.
-//   warp 0      producer : M' sub-blocks (32 k x 128 columns: hi | lo, 32 KB) by TMA bulk copy, ring of 4
-//   warp 1      MMA      : per k-block and column chunk 12 tcgen05.mma (N = 128)
+//   warp 0      producer : M' sub-blocks (32 k x 256 columns: hi | lo, 64 KB) by TMA bulk copies, ring of 2
+//   warp 1      MMA      : per k-block and 256-column group 12 tcgen05.mma (N = 256: in SS mode every MMA pays
+//                          ~170 cycles for fetching its 128 x 8 A slice from shared memory whatever N is --
+//                          tools/umma_rate.cu -- so wide MMAs halve that overhead)
 //   warps 2-17  convert  : K tile k-blocks -> hi / lo TF32 (two 32 KB stages, three blocks in flight in registers)
 //   warps 18-21 epilogue
 // =================================================================================================
 namespace w32 {
 using namespace tf32;
 
-constexpr int SA = 2, SB = 4;
+constexpr int SA = 2, SB = 2;
 constexpr int A_BYTES = 2 * BLK_BYTES;               // 32 KB
-constexpr int B_BYTES = 2 * TN * 128;                // 32 KB: 128 columns x 32 k, hi | lo
+constexpr int NSUB_MAX = 256;                        // output columns per MMA (and per M' sub-block)
+constexpr int B_BYTES = 2 * NSUB_MAX * 128;          // 64 KB: 256 columns x 32 k, hi | lo
 constexpr int CONV_W = 16, EPI_W = 4, PF = 3;
 constexpr int NTHREADS = 32 * (2 + CONV_W + EPI_W);
 constexpr int MAX_M = 512;
@@ -790,7 +793,8 @@ struct WParams {
   double* T; int64_t ldt;
   double* rowsum;
   int64_t n, ntiles;
-  int m, kblocks, nchunks;
+  int m, kblocks, nchunks;     // nchunks: 128-column accumulator chunks (epilogue granularity)
+  int nsub, nhalves;           // MMA width (256, or 128 when m <= 128) and the number of such column groups
 };
 
 struct __align__(8) WBars {
@@ -799,26 +803,26 @@ struct __align__(8) WBars {
   uint64_t acc_full[4], acc_empty[4];
 };
 
-// pack[(kb * nchunks + c)] = hi | lo images of M'[128 c + r][32 kb + kk] (rows = output columns, K-major)
-__global__ void pack_weights_tf32_kernel(const double* __restrict__ M, int64_t ldm, double scale, int m, int nchunks,
-                                         uint8_t* __restrict__ pack) {
+// pack[(kb * nhalves + h)] = hi | lo images of M'[nsub h + r][32 kb + kk] (rows = output columns, K-major)
+__global__ void pack_weights_tf32_kernel(const double* __restrict__ M, int64_t ldm, double scale, int m, int nsub,
+                                         int nhalves, uint8_t* __restrict__ pack) {
   const int kblocks = (m + KBLK - 1) / KBLK;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)kblocks * nchunks * TN * KBLK;
+  const int64_t total = (int64_t)kblocks * nhalves * nsub * KBLK;
   if (idx >= total) return;
   const int kk = (int)(idx % KBLK);
-  const int r = (int)((idx / KBLK) % TN);
-  const int c = (int)((idx / (KBLK * TN)) % nchunks);
-  const int kb = (int)(idx / ((int64_t)KBLK * TN * nchunks));
-  const int j = c * TN + r, k = kb * KBLK + kk;
+  const int r = (int)((idx / KBLK) % nsub);
+  const int h = (int)((idx / ((int64_t)KBLK * nsub)) % nhalves);
+  const int kb = (int)(idx / ((int64_t)KBLK * nsub * nhalves));
+  const int j = h * nsub + r, k = kb * KBLK + kk;
   double v = 0.0;
   if (j < m && k < m) v = scale * M[(int64_t)j * ldm + k];
   uint32_t hi, lo;
   split_tf32(v, hi, lo);
-  uint8_t* blk = pack + (size_t)(kb * nchunks + c) * B_BYTES;
+  uint8_t* blk = pack + (size_t)(kb * nhalves + h) * (2 * nsub * 128);
   const uint32_t off = sw128_offset(r, kk);
   *reinterpret_cast<uint32_t*>(blk + off) = hi;
-  *reinterpret_cast<uint32_t*>(blk + TN * 128 + off) = lo;
+  *reinterpret_cast<uint32_t*>(blk + nsub * 128 + off) = lo;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams p) {
@@ -830,7 +834,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
   WBars* bars = reinterpret_cast<WBars*>(sAlpha + MAX_M);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KB = p.kblocks, NC = p.nchunks;
+  const int KB = p.kblocks, NC = p.nchunks, NH = p.nhalves;
+  const uint32_t bbytes = (uint32_t)(2 * p.nsub * 128);
   const int64_t my_tiles = blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t total = my_tiles * KB;
 
@@ -852,10 +857,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
       uint32_t s = 0, ph = 1;
       for (int64_t it = 0; it < total; ++it) {
         const int kb = (int)(it % KB);
-        for (int c = 0; c < NC; ++c) {
+        for (int h = 0; h < NH; ++h) {
           mbar_wait(&bars->b_empty[s], ph);
-          mbar_arrive_expect_tx(&bars->b_full[s], (uint32_t)B_BYTES);
-          bulk_g2s(sB + (size_t)s * B_BYTES, p.pack + (size_t)(kb * NC + c) * B_BYTES, (uint32_t)B_BYTES, &bars->b_full[s]);
+          mbar_arrive_expect_tx(&bars->b_full[s], bbytes);
+          const uint8_t* src = p.pack + (size_t)(kb * NH + h) * bbytes;
+          for (uint32_t o = 0; o < bbytes; o += 16384)
+            bulk_g2s(sB + (size_t)s * B_BYTES + o, src + o, 16384, &bars->b_full[s]);
           if (++s == SB) { s = 0; ph ^= 1; }
         }
       }
@@ -863,23 +870,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(TM, TN);
+      const uint32_t idesc = instr_desc(TM, p.nsub);
+      const int cph = p.nsub / TN;                       // accumulator chunks per MMA column group
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int64_t tl = 0; tl < my_tiles; ++tl) {
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&bars->a_full[sa], pa);
           const uint32_t aa = smem_u32(sA + (size_t)sa * A_BYTES);
-          for (int c = 0; c < NC; ++c) {
+          for (int h = 0; h < NH; ++h) {
             mbar_wait(&bars->b_full[sb], pb);
-            if (kb == 0) mbar_wait(&bars->acc_empty[c], (uint32_t)(tl & 1) ^ 1);
+            if (kb == 0)
+              for (int c = h * cph; c < (h + 1) * cph && c < NC; ++c) mbar_wait(&bars->acc_empty[c], (uint32_t)(tl & 1) ^ 1);
             tc_fence_after();
             const uint32_t ba = smem_u32(sB + (size_t)sb * B_BYTES);
-            const uint32_t dcol = tmem_base + (uint32_t)(c * TN);
+            const uint32_t dcol = tmem_base + (uint32_t)(h * p.nsub);
             uint32_t acc = kb > 0 ? 1u : 0u;
 #pragma unroll 1
             for (int combo = 0; combo < 3; ++combo) {
               const uint32_t aoff = (combo == 0) ? (uint32_t)BLK_BYTES : 0u;          // K lo | hi | hi
-              const uint32_t boff = (combo == 1) ? (uint32_t)(TN * 128) : 0u;         // M' hi | lo | hi
+              const uint32_t boff = (combo == 1) ? (uint32_t)(p.nsub * 128) : 0u;     // M' hi | lo | hi
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 mma_tf32(dcol, smem_desc_sw128(aa + aoff + ks * 32), smem_desc_sw128(ba + boff + ks * 32), idesc, acc);
@@ -961,14 +970,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
       }
     }
   } else {
-    // ===== epilogue: T = K o (c_ya y alpha^T + U), row sums; quad-transposed accesses =====
+    // ===== epilogue: S = c_ya y alpha^T + U -> the T buffer (quad-transposed 32-byte stores); the product with
+    // K and the row sums follow in mul_rowsum_kernel =====
     const int q = warp & 3;
     const int jq = lane & 3;
-    const bool vec_ok = (p.ldk % 4 == 0) && (p.ldt % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Kin) & 31) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.T) & 31) == 0);
+    const bool vec_ok = (p.ldt % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.T) & 31) == 0);
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
       const int64_t quad_row0 = (blockIdx.x + tl * gridDim.x) * TM + q * 32 + (lane & ~3);
-      double yv[4], rsum[4] = {0.0, 0.0, 0.0, 0.0};
+      double yv[4];
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho)
         yv[rho] = (p.y != nullptr && quad_row0 + rho < p.n) ? p.c_ya * __ldg(p.y + quad_row0 + rho) : 0.0;
@@ -992,24 +1001,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int col0 = c * TN + hb * 32 + h * 16 + jq * 4;
-            // this lane's K entries for the quad's four rows (a full 128-byte line per row and quad)
-            double kv[4][4];
-#pragma unroll
-            for (int rho = 0; rho < 4; ++rho) {
-              const int64_t row = quad_row0 + rho;
-              kv[rho][0] = kv[rho][1] = kv[rho][2] = kv[rho][3] = 0.0;
-              if (row < p.n) {
-                const double* src = p.Kin + row * p.ldk + col0;
-                if (vec_ok && col0 + 3 < p.m) {
-                  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-                               : "=d"(kv[rho][0]), "=d"(kv[rho][1]), "=d"(kv[rho][2]), "=d"(kv[rho][3]) : "l"(src));
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (col0 + e < p.m) kv[rho][e] = __ldg(src + e);
-                }
-              }
-            }
 #pragma unroll
             for (int bit = 1; bit <= 2; bit <<= 1) {
               const bool up = (lane & bit) != 0;
@@ -1036,8 +1027,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
               double o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                o[e] = kv[rho][e] * fma(yv[rho], al[e], (double)w[16 * h + 4 * rho + e]);
-                rsum[rho] += (col0 + e < p.m) ? o[e] : 0.0;
+                o[e] = fma(yv[rho], al[e], (double)w[16 * h + 4 * rho + e]);
               }
               if (row < p.n && p.T != nullptr) {
                 double* out = p.T + row * p.ldt + col0;
@@ -1053,21 +1043,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) weights_tf32_kernel(const WParams
           }
         }
       }
-      if (p.rowsum != nullptr) {
-#pragma unroll
-        for (int rho = 0; rho < 4; ++rho) {
-          rsum[rho] += __shfl_xor_sync(0xffffffffu, rsum[rho], 1);
-          rsum[rho] += __shfl_xor_sync(0xffffffffu, rsum[rho], 2);
-        }
-        const int64_t row = quad_row0 + jq;
-        const double mine = jq == 0 ? rsum[0] : jq == 1 ? rsum[1] : jq == 2 ? rsum[2] : rsum[3];
-        if (row < p.n) p.rowsum[row] = mine;
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// T <- K o T (T holds S on entry), rowsum_i = sum_j T_ij: one streaming pass, a warp per row.  Kept out of the
+// GEMM kernel's epilogue on purpose: there the K entries had to be re-read ~100 us after the converters'
+// pass, came from HBM again, and with few loads in flight per epilogue thread that latency -- while all
+// 512 TMEM columns blocked the next tile's MMAs -- was three quarters of the kernel's time.
+__global__ void __launch_bounds__(256) mul_rowsum_kernel(const double* __restrict__ K, int64_t ldk, double* __restrict__ T,
+                                                         int64_t ldt, int64_t n, int m, double* __restrict__ rowsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n; row += nwarps) {
+    const double* kr = K + row * ldk;
+    double* tr = T + row * ldt;
+    double acc = 0.0;
+    for (int j = 2 * lane; j < m; j += 64) {
+      if (j + 1 < m) {
+        const double2 kv = *reinterpret_cast<const double2*>(kr + j);
+        double2 tv = *reinterpret_cast<const double2*>(tr + j);
+        tv.x *= kv.x; tv.y *= kv.y;
+        acc += tv.x + tv.y;
+        *reinterpret_cast<double2*>(tr + j) = tv;
+      } else {
+        const double t = tr[j] * kr[j];
+        acc += t;
+        tr[j] = t;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && rowsum != nullptr) rowsum[row] = acc;
+  }
 }
 
 inline size_t smem_bytes() {
@@ -1076,15 +1088,17 @@ inline size_t smem_bytes() {
 
 }  // namespace w32
 
+static int weights_nsub(int m) { return m > tf32::TN ? w32::NSUB_MAX : tf32::TN; }
+
 size_t pack_weights_tf32_bytes(int m) {
-  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nc = (m + tf32::TN - 1) / tf32::TN;
-  return (size_t)kb * nc * w32::B_BYTES;
+  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nsub = weights_nsub(m), nh = (m + nsub - 1) / nsub;
+  return (size_t)kb * nh * 2 * nsub * 128;
 }
 
 cudaError_t launch_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, cudaStream_t st) {
-  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nc = (m + tf32::TN - 1) / tf32::TN;
-  const int64_t total = (int64_t)kb * nc * tf32::TN * tf32::KBLK;
-  w32::pack_weights_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, ldm, scale, m, nc,
+  const int kb = (m + tf32::KBLK - 1) / tf32::KBLK, nsub = weights_nsub(m), nh = (m + nsub - 1) / nsub;
+  const int64_t total = (int64_t)kb * nh * nsub * tf32::KBLK;
+  w32::pack_weights_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, ldm, scale, m, nsub, nh,
                                                                                 static_cast<uint8_t*>(pack));
   count_launch();
   return cudaGetLastError();
@@ -1097,11 +1111,16 @@ cudaError_t launch_weights_tf32(const double* K, int64_t n, int m, int64_t ldk, 
   p.Kin = K; p.ldk = ldk; p.pack = static_cast<const uint8_t*>(pack); p.y = y; p.alpha = alpha; p.c_ya = c_ya;
   p.T = T; p.ldt = ldt; p.rowsum = rowsum; p.n = n; p.ntiles = (n + tf32::TM - 1) / tf32::TM; p.m = m;
   p.kblocks = (m + tf32::KBLK - 1) / tf32::KBLK; p.nchunks = (m + tf32::TN - 1) / tf32::TN;
+  p.nsub = weights_nsub(m); p.nhalves = (m + p.nsub - 1) / p.nsub;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);
   const size_t smem = w32::smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(w32::weights_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   w32::weights_tf32_kernel<<<grid, w32::NTHREADS, smem, st>>>(p);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  w32::mul_rowsum_kernel<<<sms * 8, 256, 0, st>>>(K, ldk, T, ldt, n, m, rowsum);
   count_launch();
   return cudaGetLastError();
 }

@@ -452,6 +452,8 @@ def weights_tf32(K, M, m=None, y=None, alpha=None, c_ya=0.0, c_km=1.0, T=None, w
     _lib.check(lib.edrgp_pack_weights_tf32(_ptr(M), M.shape[1], float(c_km), m, _ptr(pack), _stream()),
                'edrgp_pack_weights_tf32')
     rowsum = torch.empty(n, dtype=F64, device=K.device) if want_rowsum else None
+    if T is None:
+        T = torch.empty(n, ldk, dtype=F64, device=K.device)
     with _Timed('weights'):
         _lib.check(lib.edrgp_weights_tf32x3(_ptr(K), n, m, ldk, _ptr(pack), _ptr(y), _ptr(alpha), float(c_ya), _ptr(T),
                                             0 if T is None else T.shape[1], _ptr(rowsum), _stream()),

@@ -116,8 +116,10 @@ int edrgp_grad_tf32x3(const double* X, int64_t ldx, int64_t n, int d, const doub
  * -- dL/dKfu applied to the stored cross-covariance, GPy VarDTC dL_dpsi1 / dL_dpsi2 reached from
  * model.optimize (edrgp/gp_model/base.py:69) -- with the n x m x m contraction K M' on tcgen05 (K split
  * into hi / lo TF32 on the fly, M' prepacked by edrgp_pack_weights_tf32, FP32 accumulation in tensor
- * memory) and the elementwise part in FP64.  y, alpha may be NULL (c_ya term dropped); T (n, ldt) and
- * rowsum (n) may be NULL; ldk, ldt even.  Column sums of T: edrgp_col_moments on T. */
+ * memory) and the elementwise part in FP64 (the contraction kernel writes c_ya y alpha^T + K M' into T, a
+ * streaming pass multiplies by K and reduces the rows).  y, alpha may be NULL (c_ya term dropped); rowsum (n)
+ * may be NULL; T (n, ldt) is required; ldk, ldt even.  Column sums of T need no pass over it:
+ * sum_i T_ij = c_ya alpha_j (K^T y)_j + sum_k (K^T K)_jk M'_kj. */
 size_t edrgp_pack_weights_tf32_bytes(int m);
 int edrgp_pack_weights_tf32(const double* M, int64_t ldm, double scale, int m, void* pack, void* stream);
 int edrgp_weights_tf32x3(const double* K, int64_t n, int m, int64_t ldk, const void* pack, const double* y,
