@@ -240,8 +240,6 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
         Xd.record_stream(copy_stream)
         yd.record_stream(copy_stream)
-        if n > 0:
-            loader(0, 0)          # the first blocks start travelling while the model is being set up
         return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check,
                                          y_loader=y_loader, **kw)
 

@@ -21,6 +21,10 @@ p32 = ops.InducingPackTF32(Z, ell)
 for it in range(2):
     ops.kuf_tf32(X, p32, 1.0, out=K)
     G32 = ops.grad_tf32(X, K, Z, ell, alpha, 1.0, 1.0)
+    Mw = torch.randn(m, m, dtype=torch.float64, device='cuda', generator=g); Mw = 0.5 * (Mw + Mw.T) / m
+    Tw = torch.empty(n, m, dtype=torch.float64, device='cuda')
+    ops.weights_tf32(K, Mw, m, y=y, alpha=alpha, c_ya=0.7, c_km=2.0, T=Tw, want_rowsum=True)
+    del Tw
     ops.kuf(X, pack, 1.0, out=K)
     P, byy = ops.inducing_stats(K, y, m)
     G, C = ops.grad_gram_cached(X, K, cpack, 1.0, want_G=False)
