@@ -139,9 +139,10 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
     ``chunk_rows`` bounds the rows whose cross-covariance block is in HBM at a time, and
     ``noise_var`` sets the initial Gaussian noise variance (GPy's default 1.0; the dense
     ``GaussianProcessRegressor`` of the reference has the same parameter).
-    ``precision='tf32x3'`` evaluates the training rows' cross-covariance with the TF32-split tcgen05
-    kernel (entries within 1e-4 relative of the FP64 ones; at most 64 features); the default
-    ``'fp64'`` is the reference's arithmetic.
+    ``precision='tf32x3'`` runs the large contractions over the training rows on the TF32-split tcgen05
+    kernels where they apply -- cross-covariance and posterior-mean gradients for at most 64 features,
+    the weights of the hyper-parameter gradient for at most 512 inducing points -- with entries within
+    1e-4 relative of the FP64 ones; the default ``'fp64'`` is the reference's arithmetic.
     ``deferred_checks=True`` keeps ``fit`` from synchronising with the device: the non-finite scan
     of the input (sklearn's ``check_X_y``) and the positive-definiteness flag of the Cholesky step
     are still computed, but they are read -- and raise -- at the first host read-back

@@ -176,8 +176,8 @@ class SparseGPRegression(object):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.X = ops.pad_even(_as_device(X, self.device))          # (n_local, d_even)
         self.n_local, self.d_even = self.X.shape
-        if precision == 'tf32x3' and self.d_even > 64:
-            raise ValueError("precision='tf32x3' covers at most 64 features (got %d)" % X.shape[1])
+        # 'tf32x3' applies kernel by kernel: cross-covariance and gradients for d <= 64, the weights of the
+        # hyper-parameter gradient for m <= 512; everything else runs the FP64 kernels
         # input_dim: X may arrive already padded to an even width (estimator's overlapped loader)
         self.input_dim = X.shape[1] if input_dim is None else int(input_dim)
         Yd = _as_device(Y, self.device).reshape(-1)
@@ -339,7 +339,8 @@ class SparseGPRegression(object):
         self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
         # TF32-split mode: the training rows' cross-covariance (the n m d contraction) runs on the tcgen05
         # tensor cores; everything downstream (statistics, solve, gradients, eigh) stays FP64
-        pack32 = ops.InducingPackTF32(self._Z_dev, self._ell_dev) if self.precision == 'tf32x3' else None
+        pack32 = ops.InducingPackTF32(self._Z_dev, self._ell_dev) \
+            if (self.precision == 'tf32x3' and self.d_even <= 64) else None
         P = torch.empty(m, m, dtype=F64, device=dev)
         byy = torch.empty(m + 1, dtype=F64, device=dev)
         for i, (s, e) in enumerate(self._chunks()):

@@ -181,3 +181,19 @@ def test_tf32_hyperparameter_gradients_within_tolerance(n, d, m, ARD):
     assert abs(mod.grad_noise - ref.grad_noise) < 1e-4 * max(1.0, abs(ref.grad_noise))
     assert rel(mod.grad_lengthscale, ref.grad_lengthscale) < 1e-3
     assert rel(mod.grad_Z, ref.grad_Z) < 1e-3
+
+
+def test_tf32_mode_applies_per_kernel_for_wide_inputs():
+    """d > 64: the cross-covariance and gradient kernels stay FP64 (results equal the FP64 fit), the mode
+    does not raise."""
+    import edrgp_b200 as eb
+    from edrgp_b200 import model as emodel
+    n, d, m = 1500, 70, 40
+    w = op.make_workload(n, d, m, seed=9)
+    out = {}
+    for prec in ('fp64', 'tf32x3'):
+        est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.1, w['ell'], ARD=True), Z=w['Z'], normalizer=True,
+                                                method='fixed', noise_var=0.1, precision=prec).fit(w['X'], w['y'])
+        _, C = est.estimator_.gradient_gram(want_G=False)
+        out[prec] = C.cpu().numpy()
+    assert np.array_equal(out['fp64'], out['tf32x3'])
