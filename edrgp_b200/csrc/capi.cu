@@ -313,6 +313,13 @@ int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream) {
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "potrf");
 }
 
+int edrgp_posv(double* A, int m, int64_t ld, double* L, int64_t ldl, double* rhs, double* x, int* info, void* stream) {
+  if (!A || !L || !info || m <= 0 || ld < m || ldl < m || (rhs && (!x || x == rhs)) || A == L)
+    return fail(EDRGP_ERR_ARG, "posv: bad argument");
+  cudaError_t e = edrgp::launch_posv(A, m, ld, L, ldl, rhs, x, info, (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "posv");
+}
+
 int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream) {
   if (!L || !B || m <= 0 || nrhs <= 0) return fail(EDRGP_ERR_ARG, "trsm: bad argument");
   cudaError_t e = edrgp::launch_trsm(L, m, m, B, nrhs, nrhs, trans, (cudaStream_t)stream);

@@ -26,6 +26,8 @@ cudaError_t launch_gemm_tn(const double* A, int64_t lda, int ka, const double* B
                            int sym, const double* y, double* C, int64_t ldc, double* bout, int accumulate,
                            double* workspace, int sms, cudaStream_t st);
 cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t st);
+cudaError_t launch_posv(double* A, int m, int64_t ld, double* L, int64_t ldl, double* rhs, double* x, int* info,
+                        cudaStream_t st);
 cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
                         cudaStream_t st);
 cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitter, cudaStream_t st);

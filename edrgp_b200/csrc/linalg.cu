@@ -192,6 +192,278 @@ cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t s
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cholesky solve with ONE right-hand side (LAPACK dposv, nrhs = 1), the posterior weights of the
+// fixed-hyper-parameter sweep.  What bounds it is the chain of dependent blocked steps, not work, so
+// one blocked step is ONE launch: CTA (i, j) of step k re-derives the factor of the 32 x 32 diagonal
+// block for itself (a warp; the finished column is broadcast through shared memory), solves the two
+// panel tiles it needs (a warp each, a lane per row, right-looking so that the 31 updates behind a
+// finished unknown are independent) and applies its own 32 x 32 trailing update.  The factor goes to
+// a SEPARATE output matrix -- every CTA of the step reads block column k of A while one of them
+// produces L's -- and the right-hand side rides along as one more row of the matrix, which makes the
+// forward substitution free: after the last step that row holds L^-1 rhs.  A's lower triangle is
+// destroyed; the backward substitution is trsv_kernel.
+// ---------------------------------------------------------------------------------------------
+// FP64 operations cost ~40 cycles each on a dependent chain here (measured: chol_profile tool), so the
+// routines below are arranged around the number of DEPENDENT FP64 operations per column.
+//
+// reciprocal / reciprocal square root of a positive normal double: hardware FP64 seed (~20 bits) + two
+// Newton steps, branch free over the whole normal range (the unrolled factorisation below must stay ONE
+// basic block for the scheduler to interleave its independent chains)
+__device__ __forceinline__ double rcp_seeded(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_seeded(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double hd = 0.5 * d;
+  y = y * fma(-hd * y, y, 1.5);
+  y = y * fma(-hd * y, y, 1.5);
+  return y;
+}
+
+// Factor the 32 x 32 block whose row `lane` is in a[] (identity padded).  Column j is broadcast UNSCALED
+// through shared memory (col: 64 doubles owned by this warp, alternating halves) as soon as it is final,
+// the trailing update uses u_i u_c / d_j with the reciprocal of the pivot, and the next pivot is formed
+// on its own lane from that lane's own entry and fetched by one shuffle: the chain from pivot to pivot is
+// reciprocal -> fma -> shuffle; the reciprocal square root that scales the column into L runs beside it.
+// Returns the reciprocal of this lane's diagonal entry of L; *bad = 1 + index of the first non-positive pivot (0: none).
+__device__ __forceinline__ double potf2_bcast(double (&a)[NBK], double* col, int lane, int nb, int k0, int* bad) {
+  double dj = __shfl_sync(0xffffffffu, a[0], 0);
+  double myinv = 1.0;
+  int first_bad = 0;
+#pragma unroll
+  for (int j = 0; j < NBK; ++j) {
+    const double u = a[j];
+    double* cj = col + (j & 1) * NBK;
+    cj[lane] = u;
+    first_bad = (first_bad == 0 && j < nb && !(dj > 0.0)) ? k0 + j + 1 : first_bad;
+    const double rcp = rcp_seeded(dj);
+    const double nusq = -(u * u);                  // ready before the reciprocal is
+    double dnext = 0.0;
+    if (j + 1 < NBK) dnext = __shfl_sync(0xffffffffu, fma(nusq, rcp, a[(j + 1) % NBK]), (j + 1) % NBK);
+    const double nt = -(u * rcp);
+    __syncwarp();
+#pragma unroll
+    for (int c2 = (j + 1) / 2; c2 < NBK / 2; ++c2) {
+      const double2 l = *reinterpret_cast<const double2*>(cj + 2 * c2);
+      if (2 * c2 > j) a[2 * c2] = fma(nt, l.x, a[2 * c2]);
+      a[2 * c2 + 1] = fma(nt, l.y, a[2 * c2 + 1]);
+    }
+    const double inv = rsqrt_seeded(dj);
+    a[j] = lane == j ? dj * inv : u * inv;          // lanes above the diagonal carry unused values
+    myinv = lane == j ? inv : myinv;
+    dj = dnext;
+  }
+  *bad = first_bad;
+  return myinv;
+}
+
+// z (one row per lane) <- z L11^-T for rows pre-scaled as z_c = x_c / L11[c][c], with
+// Mt[q][c] = L11[c][q] / L11[c][c] in shared memory: one dependent fma per column.
+__device__ __forceinline__ void panel_solve_rows(double (&z)[NBK], const double* Mt) {
+#pragma unroll
+  for (int c = 0; c < NBK; ++c) {
+    const double nz = -z[c];
+#pragma unroll
+    for (int q2 = (c + 1) / 2; q2 < NBK / 2; ++q2) {
+      const double2 l = *reinterpret_cast<const double2*>(Mt + c * NBK + 2 * q2);
+      if (2 * q2 > c) z[2 * q2] = fma(nz, l.x, z[2 * q2]);
+      z[2 * q2 + 1] = fma(nz, l.y, z[2 * q2 + 1]);
+    }
+  }
+}
+
+#ifdef CHOL_PROFILE
+// tuning build (EDRGP_NVCC_EXTRA=-DCHOL_PROFILE): clock64 stamps of CTA 0's warp 0 per step
+__device__ long long chol_prof[64][8];
+#define CHOL_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) chol_prof[kb & 63][i] = clock64(); } while (0)
+#else
+#define CHOL_STAMP(i) do { } while (0)
+#endif
+
+// Panel tiles live in shared memory swizzled, element (r, c) at r * 32 + (c ^ f(r)): a lane per row with
+// a fixed column (the solves) and the DMMA fragment pattern (rows g, columns t) are both conflict free.
+__device__ __forceinline__ int pswz(int r, int c) { return r * NBK + (c ^ (((r & 3) << 2) | ((r >> 2) & 3))); }
+
+struct __align__(16) CholWarpSmem {
+  double Mt[NBK * NBK];          // transposed diagonal factor, rows scaled by their diagonal entry
+  double P[NBK * NBK];           // panel tile (swizzled): in A_ik, out L_ik
+  double col[2 * NBK];
+  double dinv[NBK];
+};
+
+// Step kb of the solve.  Row blocks kb+1 .. nblk-1 of A plus (rhs != NULL) the right-hand side as row
+// block nblk; CTAs = trailing tiles (i >= j > kb) + one finisher that stores L_kk and the solved
+// piece of the right-hand side (into cvec).
+__global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, int64_t ld, int m, int kb,
+                                                        double* __restrict__ Lout, int64_t ldl,
+                                                        double* __restrict__ rhs, double* __restrict__ cvec,
+                                                        int* __restrict__ info) {
+  __shared__ double D[NBK][NBK + 1];
+  __shared__ CholWarpSmem ws[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (m + NBK - 1) / NBK;
+  const int k0 = kb * NBK, nb = min(NBK, m - k0);
+  const int nt = nblk - kb - 1;                       // trailing block columns
+  const int nrow = nt + (rhs != nullptr ? 1 : 0);     // trailing block rows
+  // blockIdx -> (ii, jj), ii >= jj, column by column; past the last tile: the finisher
+  int jj = 0, rem = blockIdx.x;
+  while (jj < nt && rem >= nrow - jj) { rem -= nrow - jj; ++jj; }
+  const bool finisher = jj >= nt;
+  const int ib = finisher ? nblk : kb + 1 + jj + rem; // row block of this CTA's tile (nblk = the rhs row)
+  const int jb = kb + 1 + jj;
+  const bool is_rhs = ib >= nblk;
+  const bool diag = !finisher && ib == jb;
+  const bool two = !finisher && !diag;                // a second panel tile (block row jb)
+  // programmatic dependent launch: the next step's CTAs may be scheduled now (they wait below for this
+  // grid to complete), which takes the launch latency out of the chain of dependent steps
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  CHOL_STAMP(0);
+  // ---- stage the diagonal block and the panel tiles: every load in flight before the first store --------
+  {
+    double vd[4], vi[4], vj[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + 256 * it, r = e >> 5, c = e & 31;
+      vd[it] = r == c ? 1.0 : 0.0;
+      if (r < nb && c < nb && c <= r) vd[it] = A[(int64_t)(k0 + r) * ld + k0 + c];
+      vi[it] = 0.0;
+      if (c < nb) {
+        if (is_rhs) { if (r == 0 && rhs != nullptr) vi[it] = rhs[k0 + c]; }
+        else if (ib * NBK + r < m) vi[it] = A[(int64_t)(ib * NBK + r) * ld + k0 + c];
+      }
+      vj[it] = 0.0;
+      if (two && c < nb && jb * NBK + r < m) vj[it] = A[(int64_t)(jb * NBK + r) * ld + k0 + c];
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + 256 * it, r = e >> 5, c = e & 31;
+      D[r][c] = vd[it];
+      ws[0].P[pswz(r, c)] = vi[it];
+      if (two) ws[1].P[pswz(r, c)] = vj[it];
+    }
+  }
+  // this thread's entries of the trailing tile in the DMMA accumulator layout: warp w owns rows
+  // 8 (w / 2) + g and the two 8-column blocks at 16 (w % 2); lane = 4 g + t holds columns 2t, 2t + 1 of each
+  const int g = lane >> 2, t4 = lane & 3;
+  const int tr = 8 * (warp >> 1) + g, tcb = 16 * (warp & 1) + 2 * t4;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};               // (block 0: 2t, 2t + 1), (block 1: 2t, 2t + 1)
+  if (!finisher) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int gc = jb * NBK + tcb + (cc >> 1) * 8 + (cc & 1);
+      if (gc < m) {
+        if (is_rhs) { if (tr == 0) acc[cc] = rhs[gc]; }
+        else if (ib * NBK + tr < m) acc[cc] = A[(int64_t)(ib * NBK + tr) * ld + gc];
+      }
+    }
+  }
+  __syncthreads();
+  CHOL_STAMP(1);
+  // ---- warps 0 / 1: factor the diagonal block, solve one panel tile each -----------------------------
+  if (warp < 2 && (warp == 0 || two)) {
+    CholWarpSmem& w = ws[warp];
+    double a[NBK];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) a[c] = D[lane][c];
+    int bad;
+    const double dinv = potf2_bcast(a, w.col, lane, nb, k0, &bad);
+    if (finisher && lane == 0 && bad != 0) atomicCAS(info, 0, bad);
+    CHOL_STAMP(2);
+    w.dinv[lane] = dinv;
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) w.Mt[c * NBK + lane] = a[c] * dinv;
+    if (finisher) {
+#pragma unroll
+      for (int c = 0; c < NBK; ++c)
+        if (c < nb && c <= lane && lane < nb) Lout[(int64_t)(k0 + lane) * ldl + k0 + c] = a[c];
+    }
+    __syncwarp();
+    double z[NBK];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) z[c] = w.P[pswz(lane, c)] * w.dinv[c];
+    panel_solve_rows(z, w.Mt);
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) w.P[pswz(lane, c)] = z[c];
+    CHOL_STAMP(3);
+  }
+  __syncthreads();
+  CHOL_STAMP(4);
+  if (finisher) {
+    if (rhs != nullptr && tid < nb) cvec[k0 + tid] = ws[0].P[pswz(0, tid)];
+    return;
+  }
+  // ---- panel output (first trailing column only) and the trailing update on the FP64 tensor pipe -------
+  if (jj == 0 && !is_rhs) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + 256 * it, r = e >> 5, c = e & 31;
+      if (c < nb && ib * NBK + r < m) Lout[(int64_t)(ib * NBK + r) * ldl + k0 + c] = ws[0].P[pswz(r, c)];
+    }
+  }
+  const double* Pi = ws[0].P;
+  const double* Pj = diag ? ws[0].P : ws[1].P;
+  const int cb = 16 * (warp & 1);
+#pragma unroll
+  for (int q0 = 0; q0 < NBK; q0 += 4) {
+    const double na = -Pi[pswz(tr, q0 + t4)];
+    const double b0 = Pj[pswz(cb + g, q0 + t4)], b1 = Pj[pswz(cb + 8 + g, q0 + t4)];
+    dmma(acc[0], acc[1], na, b0);
+    dmma(acc[2], acc[3], na, b1);
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int lc = tcb + (cc >> 1) * 8 + (cc & 1), gc = jb * NBK + lc;
+    if (gc >= m) continue;
+    if (is_rhs) { if (tr == 0) rhs[gc] = acc[cc]; }
+    else if (ib * NBK + tr < m && (!diag || lc <= tr)) A[(int64_t)(ib * NBK + tr) * ld + gc] = acc[cc];
+  }
+  CHOL_STAMP(5);
+}
+
+cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
+                        cudaStream_t st);
+
+#ifdef CHOL_PROFILE
+extern "C" int edrgp_debug_chol_prof(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, chol_prof, sizeof(chol_prof));
+}
+#endif
+
+// A x = rhs by Cholesky: A (m, ld) lower triangle destroyed, L (m, ldl) receives the factor (lower
+// triangle), x (m) the solution; rhs (m) is destroyed (may be NULL: factor only, x unused).
+cudaError_t launch_posv(double* A, int m, int64_t ld, double* L, int64_t ldl, double* rhs, double* x, int* info,
+                        cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const int nblk = (m + NBK - 1) / NBK;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int nt = nblk - kb - 1, nrow = nt + (rhs != nullptr ? 1 : 0);
+    const int tiles = nt * nrow - nt * (nt - 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles + 1));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, chol_step_kernel, A, ld, m, kb, L, ldl, rhs, x, info); count_launch();
+    if (e != cudaSuccess) return e;
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (rhs != nullptr) return launch_trsm(L, m, ldl, x, 1, 1, 1, st);
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Triangular solves with the lower factor L (m x m):  trans = 0: L X = B,  trans = 1: L^T X = B.
 // B is m x nrhs row-major, overwritten with X.
 // ---------------------------------------------------------------------------------------------
@@ -466,110 +738,13 @@ static int jacobi_variant() {
   return v;
 }
 
-template <int L, int R>
-__global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
-    const double* __restrict__ C, int d, double* __restrict__ evals, double* __restrict__ comps, int max_sweeps,
-    int* __restrict__ sweeps_out) {
-  extern __shared__ double sh[];
-  const int ds = d + 1 + ((d + 1) & 1);       // column stride: breaks the power-of-two bank pattern
-  double* W = sh;                             // [d][ds] column-major: W[c * ds + r]
-  double* V = sh + (size_t)d * ds;
-  __shared__ int rotated;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int dd = d + (d & 1), np = dd / 2;
-  for (int i = tid; i < d * d; i += nt) {
-    const int c = i / d, r = i - c * d;
-    W[c * ds + r] = C[(int64_t)r * d + c];
-    V[c * ds + r] = r == c ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  const int k = tid / L, l = tid % L;         // pair slot and lane within the pair group
-  const bool active = k < np;
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    if (tid == 0) rotated = 0;
-    __syncthreads();
-    for (int step = 0; step < dd - 1; ++step) {
-      int p = 0, q = d;
-      if (active) {                           // round-robin tournament; step, k < dd - 1: one conditional subtract
-        int a0 = step + k, b0 = step + dd - 1 - k;
-        if (a0 >= dd - 1) a0 -= dd - 1;
-        if (b0 >= dd - 1) b0 -= dd - 1;
-        if (k == 0) a0 = dd - 1;
-        p = min(a0, b0); q = max(a0, b0);
-      }
-      const bool live = active && q < d;      // q == d: the bye of an odd dimension / idle slot
-      double* Wp = W + p * ds + l;
-      double* Wq = W + (live ? q : p) * ds + l;
-      double* Vp = V + p * ds + l;
-      double* Vq = V + (live ? q : p) * ds + l;
-      constexpr bool HOIST = R <= 4;          // V columns fetched ahead of the rotation parameters (register budget)
-      double wa[R], wb[R], va[HOIST ? R : 1], vb[HOIST ? R : 1];
-      double alpha = 0.0, beta = 0.0, gamma = 0.0;
-#pragma unroll
-      for (int e = 0; e < R; ++e) {
-        const bool ok = live && l + L * e < d;
-        wa[e] = ok ? Wp[L * e] : 0.0;
-        wb[e] = ok ? Wq[L * e] : 0.0;
-      }
-      if (HOIST) {
-#pragma unroll
-        for (int e = 0; e < R; ++e) {
-          const bool ok = live && l + L * e < d;
-          va[HOIST ? e : 0] = ok ? Vp[L * e] : 0.0;
-          vb[HOIST ? e : 0] = ok ? Vq[L * e] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < R; ++e) {
-        alpha = fma(wa[e], wa[e], alpha); beta = fma(wb[e], wb[e], beta); gamma = fma(wa[e], wb[e], gamma);
-      }
-#pragma unroll
-      for (int o = L / 2; o > 0; o >>= 1) {
-        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
-        beta += __shfl_xor_sync(0xffffffffu, beta, o);
-        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
-      }
-      if (live && gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
-        double c, s;
-        const double sum = alpha + beta;
-        const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
-        if (ex > 64 && ex < 1983) {                                 // 2^-959 < alpha + beta < 2^960
-          const double scale = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex): sum * scale in [1, 2)
-          const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;   // both in [-2, 2]
-          const double ih = fast_rsqrt(fma(dn, dn, gn * gn));       // argument in [~1e-31, 8]
-          const double x = fma(0.5 * fabs(dn), ih, 0.5);            // (1 + cos 2t) / 2 in [0.5, 1]
-          const double r = fast_rsqrt(x);
-          c = x * r;
-          s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
-        } else {                                                    // out of the scaled range: IEEE path
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
-        }
-        if (l == 0) rotated = 1;
-#pragma unroll
-        for (int e = 0; e < R; ++e) {
-          if (l + L * e < d) {
-            Wp[L * e] = c * wa[e] - s * wb[e];
-            Wq[L * e] = s * wa[e] + c * wb[e];
-            const double x = HOIST ? va[HOIST ? e : 0] : Vp[L * e], y = HOIST ? vb[HOIST ? e : 0] : Vq[L * e];
-            Vp[L * e] = c * x - s * y;
-            Vq[L * e] = s * x + c * y;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (!rotated) break;
-    __syncthreads();
-  }
-  if (tid == 0 && sweeps_out) *sweeps_out = sweep;
+// Eigenvalues and output for the vectors V (column i at V + i * ds, shared or global memory): lam is
+// d doubles of shared scratch; the whole CTA calls this after a barrier.
+__device__ __forceinline__ void jacobi_finish(const double* __restrict__ C, int d, const double* V, int ds, double* lam,
+                                              double* __restrict__ evals, double* __restrict__ comps, int tid, int nt) {
   // eigenvalues: Rayleigh quotients v^T C v against the input (C is symmetric: read it by rows so that
   // the lanes of a warp touch consecutive addresses), one warp per vector, four independent chains
   const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-  double* lam = W;                      // reused once every warp is done with W
-  __syncthreads();
   for (int i0 = 0; i0 < d; i0 += nwarps) {
     const int i = i0 + warp;
     double acc = 0.0;
@@ -618,18 +793,242 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
   }
 }
 
-template <int L, int R>
-static cudaError_t launch_jacobi_small(const double* C, int d, double* evals, double* comps, int* sweeps, cudaStream_t st) {
-  const int ds = d + 1 + ((d + 1) & 1);
-  const size_t smem = (size_t)2 * d * ds * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel<L, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+
+// LOGV: V is NOT carried here.  Its update never feeds back into the rotations, yet it is half of the
+// shared-memory traffic and a fifth of the FP64 instructions of every step of this latency chain; the
+// kernel only records (c, s) of every pair and step (rotlog[(sweep (dd - 1) + step) np + slot]; (1, 0)
+// where nothing rotates) and the number of recorded sweeps (nlog), and jacobi_vectors_kernel replays the
+// log on the rows of V -- independent of one another -- across several SMs, then finishes (Rayleigh
+// quotients, order, signs).
+template <int L, int R, bool LOGV>
+__global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
+    const double* __restrict__ C, int d, double* __restrict__ evals, double* __restrict__ comps, int max_sweeps,
+    int* __restrict__ sweeps_out, double2* __restrict__ rotlog, int* __restrict__ nlog) {
+  extern __shared__ double sh[];
+  const int ds = d + 1 + ((d + 1) & 1);       // column stride: breaks the power-of-two bank pattern
+  double* W = sh;                             // [d][ds] column-major: W[c * ds + r]
+  double* V = LOGV ? sh : sh + (size_t)d * ds;
+  __shared__ int rotated;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int dd = d + (d & 1), np = dd / 2;
+  for (int i = tid; i < d * d; i += nt) {
+    const int c = i / d, r = i - c * d;
+    W[c * ds + r] = C[(int64_t)r * d + c];
+    if (!LOGV) V[c * ds + r] = r == c ? 1.0 : 0.0;
   }
+  __syncthreads();
+  const int k = tid / L, l = tid % L;         // pair slot and lane within the pair group
+  const bool active = k < np;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int step = 0; step < dd - 1; ++step) {
+      int p = 0, q = d;
+      if (active) {                           // round-robin tournament; step, k < dd - 1: one conditional subtract
+        int a0 = step + k, b0 = step + dd - 1 - k;
+        if (a0 >= dd - 1) a0 -= dd - 1;
+        if (b0 >= dd - 1) b0 -= dd - 1;
+        if (k == 0) a0 = dd - 1;
+        p = min(a0, b0); q = max(a0, b0);
+      }
+      const bool live = active && q < d;      // q == d: the bye of an odd dimension / idle slot
+      double* Wp = W + p * ds + l;
+      double* Wq = W + (live ? q : p) * ds + l;
+      double* Vp = V + p * ds + l;
+      double* Vq = V + (live ? q : p) * ds + l;
+      constexpr bool HOIST = R <= 4 && !LOGV; // V columns fetched ahead of the rotation parameters (register budget)
+      double wa[R], wb[R], va[HOIST ? R : 1], vb[HOIST ? R : 1];
+      double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+      for (int e = 0; e < R; ++e) {
+        const bool ok = live && l + L * e < d;
+        wa[e] = ok ? Wp[L * e] : 0.0;
+        wb[e] = ok ? Wq[L * e] : 0.0;
+      }
+      if (HOIST) {
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          const bool ok = live && l + L * e < d;
+          va[HOIST ? e : 0] = ok ? Vp[L * e] : 0.0;
+          vb[HOIST ? e : 0] = ok ? Vq[L * e] : 0.0;
+        }
+      }
+      {
+        // short dependent chains: NA partial sums per product, then a tree
+        constexpr int NA = R >= 8 ? 4 : (R >= 2 ? 2 : 1);
+        double pa[NA], pb[NA], pg[NA];
+#pragma unroll
+        for (int e = 0; e < NA; ++e) { pa[e] = wa[e] * wa[e]; pb[e] = wb[e] * wb[e]; pg[e] = wa[e] * wb[e]; }
+#pragma unroll
+        for (int e = NA; e < R; ++e) {
+          pa[e % NA] = fma(wa[e], wa[e], pa[e % NA]); pb[e % NA] = fma(wb[e], wb[e], pb[e % NA]);
+          pg[e % NA] = fma(wa[e], wb[e], pg[e % NA]);
+        }
+#pragma unroll
+        for (int o = NA / 2; o > 0; o >>= 1) {
+#pragma unroll
+          for (int e = 0; e < o; ++e) { pa[e] += pa[e + o]; pb[e] += pb[e + o]; pg[e] += pg[e + o]; }
+        }
+        alpha = pa[0]; beta = pb[0]; gamma = pg[0];
+      }
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+      }
+      double c = 1.0, s = 0.0;
+      if (live && gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
+        const double sum = alpha + beta;
+        const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
+        if (ex > 64 && ex < 1983) {                                 // 2^-959 < alpha + beta < 2^960
+          const double scale = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex): sum * scale in [1, 2)
+          const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;   // both in [-2, 2]
+          const double ih = fast_rsqrt(fma(dn, dn, gn * gn));       // argument in [~1e-31, 8]
+          const double x = fma(0.5 * fabs(dn), ih, 0.5);            // (1 + cos 2t) / 2 in [0.5, 1]
+          const double r = fast_rsqrt(x);
+          c = x * r;
+          s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
+        } else {                                                    // out of the scaled range: IEEE path
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
+        }
+        // a sweep whose rotations all stay below |cos| = 1e-9 leaves every pair orthogonal to ~1e-18 / gap
+        // (quadratic convergence): it is the last one, no empty sweep is needed to find that out
+        if (l == 0 && gamma * gamma > 1e-18 * alpha * beta) rotated = 1;
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          if (l + L * e < d) {
+            Wp[L * e] = c * wa[e] - s * wb[e];
+            Wq[L * e] = s * wa[e] + c * wb[e];
+            if (!LOGV) {
+              const double x = HOIST ? va[HOIST ? e : 0] : Vp[L * e], y = HOIST ? vb[HOIST ? e : 0] : Vq[L * e];
+              Vp[L * e] = c * x - s * y;
+              Vq[L * e] = s * x + c * y;
+            }
+          }
+        }
+      }
+      if (LOGV && active && l == 0) rotlog[((size_t)sweep * (dd - 1) + step) * np + k] = make_double2(c, s);
+      __syncthreads();
+    }
+    if (!rotated) { ++sweep; break; }
+    __syncthreads();
+  }
+  if (tid == 0 && sweeps_out) *sweeps_out = sweep;
+  if (LOGV) {
+    if (tid == 0) { nlog[0] = sweep; nlog[1] = 0; }      // sweeps recorded; the replay kernel's ticket
+    return;
+  }
+  __syncthreads();
+  jacobi_finish(C, d, V, ds, W, evals, comps, tid, nt);   // W's storage is free once every warp is past the barrier
+}
+
+// Replays the rotation log of jacobi_onesided_kernel<.., true> on V = I.  A warp per ROW of V (rows never
+// mix), lane = pair slot of the round-robin schedule holding that row's entries in the slot's two columns;
+// between steps the columns move one slot along the tournament ring (two shuffles).  The log is fetched
+// sixteen steps ahead.  The last CTA to finish (ticket) computes the eigenvalues and writes the output.
+// d <= 64 (at most 32 slots).
+constexpr int JV_WARPS = 8;
+constexpr int JV_AHEAD = 16;
+__global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_kernel(
+    const double* __restrict__ C, int d, const double2* __restrict__ rotlog, int* ctrl, double* Vt,
+    double* __restrict__ evals, double* __restrict__ comps) {
+  __shared__ double lam[64];
+  __shared__ int last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dd = d + (d & 1), np = dd / 2;
+  const int row = blockIdx.x * JV_WARPS + warp;
+  const int nsteps = ctrl[0] * (dd - 1);
+  if (row < d) {
+    const bool act = lane < np;
+    int step = 0;
+    double va, vb;
+    {
+      const int a0 = lane == 0 ? dd - 1 : lane, b0 = lane == 0 ? 0 : dd - 1 - lane;
+      va = (act && a0 == row) ? 1.0 : 0.0;
+      vb = (act && b0 == row) ? 1.0 : 0.0;
+    }
+    const double2 ident = make_double2(1.0, 0.0);
+    const double2* lp = rotlog + lane;
+    double2 cur[JV_AHEAD], nxt[JV_AHEAD];
+#pragma unroll
+    for (int i = 0; i < JV_AHEAD; ++i) cur[i] = (act && i < nsteps) ? lp[(size_t)i * np] : ident;
+    for (int g0 = 0; g0 < nsteps; g0 += JV_AHEAD) {
+#pragma unroll
+      for (int i = 0; i < JV_AHEAD; ++i) {
+        const int g = g0 + JV_AHEAD + i;
+        nxt[i] = (act && g < nsteps) ? lp[(size_t)g * np] : ident;
+      }
+#pragma unroll
+      for (int i = 0; i < JV_AHEAD; ++i) {
+        if (g0 + i < nsteps) {                      // uniform across the warp
+          int a0 = step + lane, b0 = step + dd - 1 - lane;
+          if (a0 >= dd - 1) a0 -= dd - 1;
+          if (b0 >= dd - 1) b0 -= dd - 1;
+          if (lane == 0) a0 = dd - 1;
+          const double c = cur[i].x, sg = a0 < b0 ? cur[i].y : -cur[i].y;
+          const double na = c * va - sg * vb, nb = sg * va + c * vb;
+          const double dn = __shfl_down_sync(0xffffffffu, na, 1), up = __shfl_up_sync(0xffffffffu, nb, 1);
+          if (np > 1) {
+            va = lane == 0 ? na : (lane == np - 1 ? nb : dn);
+            vb = lane == 0 ? dn : up;
+          } else {
+            va = na; vb = nb;
+          }
+          if (++step == dd - 1) step = 0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < JV_AHEAD; ++i) cur[i] = nxt[i];
+    }
+    if (act) {                                      // step == 0 again: the slots hold their initial columns
+      const int a0 = lane == 0 ? dd - 1 : lane, b0 = lane == 0 ? 0 : dd - 1 - lane;
+      if (a0 < d) Vt[(size_t)a0 * d + row] = va;
+      if (b0 < d) Vt[(size_t)b0 * d + row] = vb;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(ctrl + 1), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  jacobi_finish(C, d, Vt, d, lam, evals, comps, tid, JV_WARPS * 32);
+}
+
+static size_t jacobi_log_doubles(int d) {
+  const int dd = d + (d & 1);
+  return (size_t)60 * (dd - 1) * (dd / 2) * 2;
+}
+
+template <int L, int R>
+static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, double* evals, double* comps, int* sweeps,
+                                       cudaStream_t st) {
+  const int ds = d + 1 + ((d + 1) & 1);
   const int np = (d + 1) / 2;
   int threads = ((np * L + 31) / 32) * 32;
   if (threads < 128) threads = 128;            // at least 4 warps for the Rayleigh / output phase
-  jacobi_onesided_kernel<L, R><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps); count_launch();
+  if (d <= 64) {                               // rotations logged, vectors replayed across SMs
+    double2* rotlog = reinterpret_cast<double2*>(ws);
+    double* Vt = ws + jacobi_log_doubles(d);
+    int* ctrl = reinterpret_cast<int*>(Vt + (size_t)d * d);          // [0] sweeps logged, [1] ticket
+    const size_t smem = (size_t)d * ds * sizeof(double);
+    jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
+    count_launch();
+    jacobi_vectors_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
+    count_launch();
+    return cudaGetLastError();
+  }
+  const size_t smem = (size_t)2 * d * ds * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_onesided_kernel<L, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  jacobi_onesided_kernel<L, R, false><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, nullptr, nullptr);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -809,7 +1208,10 @@ __global__ void eig_finish_kernel(const double* __restrict__ lam, const double* 
   for (int r = 0; r < d; ++r) comps[(int64_t)rank * d + r] = sgn * V[(int64_t)i * d + r];
 }
 
-size_t eigh_workspace_doubles(int d) { return d <= 116 ? (size_t)d * d : (size_t)2 * d * d + d + 4; }
+size_t eigh_workspace_doubles(int d) {
+  if (d <= 64) return jacobi_log_doubles(d) + (size_t)d * d + 2;      // rotation log, V, control words
+  return d <= 116 ? (size_t)d * d : (size_t)2 * d * d + d + 4;
+}
 
 static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double* evals, double* comps, int* sweeps,
                                      cudaStream_t st) {
@@ -844,15 +1246,15 @@ cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comp
   if (d <= 116) {       // two d x (d + 2) matrices in shared memory
     // lanes per pair x rows per lane: threads = pairs x lanes (d = 64: 32 x 16 = 512; d = 116: 58 x 16 = 928)
     const int variant = jacobi_variant();
-    if (d <= 16) return launch_jacobi_small<4, 4>(A, d, evals, comps, sweeps, st);
-    if (d <= 32) return variant == 1 ? launch_jacobi_small<4, 8>(A, d, evals, comps, sweeps, st)
-                                     : launch_jacobi_small<8, 4>(A, d, evals, comps, sweeps, st);
+    if (d <= 16) return launch_jacobi_small<4, 4>(A, d, V, evals, comps, sweeps, st);
+    if (d <= 32) return variant == 1 ? launch_jacobi_small<4, 8>(A, d, V, evals, comps, sweeps, st)
+                                     : launch_jacobi_small<8, 4>(A, d, V, evals, comps, sweeps, st);
     if (d <= 64) {
-      if (variant == 1) return launch_jacobi_small<8, 8>(A, d, evals, comps, sweeps, st);
-      if (variant == 2) return launch_jacobi_small<32, 2>(A, d, evals, comps, sweeps, st);
-      return launch_jacobi_small<16, 4>(A, d, evals, comps, sweeps, st);
+      if (variant == 1) return launch_jacobi_small<8, 8>(A, d, V, evals, comps, sweeps, st);
+      if (variant == 2) return launch_jacobi_small<32, 2>(A, d, V, evals, comps, sweeps, st);
+      return launch_jacobi_small<16, 4>(A, d, V, evals, comps, sweeps, st);
     }
-    return launch_jacobi_small<16, 8>(A, d, evals, comps, sweeps, st);
+    return launch_jacobi_small<16, 8>(A, d, V, evals, comps, sweeps, st);
   }
   return launch_eigh_large(A, d, V, evals, comps, sweeps, st);
 }

@@ -375,13 +375,10 @@ class SparseGPRegression(object):
             # Woodbury inverse and the gradients run the full chain on demand (_ensure_full).
             S = ops.kmm(self._pack, sf2, CONST_JITTER)
             S.add_(P, alpha=beta)
-            S, info = ops.potrf(S)
-            v = byy[:m] * beta
-            ops.trsm(S, v, False)
-            ops.trsm(S, v, True)
-            self.alpha = v                                       # GPy posterior.woodbury_vector (m,)
+            # one launch per blocked Cholesky step, beta b carried as an extra row (forward solve for free)
+            self.alpha, _, info = ops.posv(S, byy[:m] * beta)     # GPy posterior.woodbury_vector (m,)
             self._info_dev = info
-            self.kernel_launches += 40
+            self.kernel_launches += 5 + (m + 31) // 32
             self._enqueue_checks()
 
     def _full_chain(self):

@@ -369,6 +369,21 @@ def potrf(A):
     return A, info
 
 
+def posv(A, rhs):
+    """Solve A x = rhs (one right-hand side) by Cholesky: returns (x, L, info).  A's lower triangle and rhs
+    are consumed; L is a new (m, m) tensor whose lower triangle is the factor."""
+    lib = _lib.load()
+    _need_cuda(A, rhs)
+    m = A.shape[0]
+    L = torch.empty(m, m, dtype=F64, device=A.device)
+    x = torch.empty(m, dtype=F64, device=A.device)
+    info = torch.empty(1, dtype=torch.int32, device=A.device)          # zeroed by the call
+    with _Timed('solve'):
+        _lib.check(lib.edrgp_posv(_ptr(A), m, A.shape[1], _ptr(L), m, _ptr(rhs), _ptr(x), _ptr(info), _stream()),
+                   'edrgp_posv')
+    return x, L, info
+
+
 def trsm(L, B, trans=False):
     """In-place triangular solve with a lower factor: L X = B (trans=False) or L^T X = B."""
     lib = _lib.load()

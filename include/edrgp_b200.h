@@ -222,6 +222,17 @@ int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double bet
  * alpha = LS^-T LS^-1 (beta b): the fixed-hyper-parameter sweep needs nothing else of the chain. */
 int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream);
 
+/* A x = rhs by Cholesky with one right-hand side (LAPACK dposv, nrhs = 1): the posterior weights
+ * alpha = (Kuu + beta P)^-1 beta b of the fixed-hyper-parameter sweep (GPy Posterior.woodbury_vector,
+ * edrgp/gp_model/base.py:69,222) in one call.  One launch per 32-column blocked step (the diagonal
+ * factor, the panel solves and the trailing update of a tile fused in one CTA), the right-hand side
+ * carried as one more row of the matrix so that the forward substitution costs nothing, then one
+ * backward substitution.  A (m, ld): lower triangle DESTROYED;  L (m, ldl), a different buffer:
+ * receives the factor (lower triangle, the rest untouched);  rhs (m): destroyed;  x (m), a different
+ * buffer: the solution.  rhs = x = NULL factors only.  info[0] as in edrgp_potrf. */
+int edrgp_posv(double* A, int m, int64_t ld, double* L, int64_t ldl, double* rhs, double* x, int* info,
+               void* stream);
+
 /* lower-triangular solves with a factor from edrgp_solve: trans = 0: L X = B, 1: L^T X = B;
  * B (m, nrhs) row-major, overwritten.  (GPy dtrtrs.) */
 int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* stream);

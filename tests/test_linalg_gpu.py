@@ -118,6 +118,36 @@ def test_trsm(m, nrhs):
         assert _relerr(X, ref) < 1e-11
 
 
+@pytest.mark.parametrize("m", [1, 5, 32, 33, 64, 100, 257, 512, 1000])
+def test_posv_matches_lapack(m):
+    """One-launch-per-step Cholesky solve (right-hand side carried as an extra row): solution, factor,
+    untouched upper triangle of the factor buffer, run-to-run determinism."""
+    from edrgp_b200 import ops
+    import scipy.linalg as sl
+    rng = np.random.RandomState(m)
+    B = rng.standard_normal((m, m + 3))
+    A = B.dot(B.T) + 0.1 * m * np.eye(m)
+    b = rng.standard_normal(m)
+    x, L, info = ops.posv(_dev(A), _dev(b))
+    assert int(info.cpu()[0]) == 0
+    Lref = np.linalg.cholesky(A)
+    assert _relerr(np.tril(L.cpu().numpy()), Lref) < 1e-12
+    xref = sl.cho_solve((Lref, True), b)
+    assert _relerr(x.cpu().numpy(), xref) < 1e-10
+    x2, L2, _ = ops.posv(_dev(A), _dev(b))
+    assert torch.equal(x, x2) and torch.equal(torch.tril(L), torch.tril(L2))
+    # the same factor as the two-launch-per-step in-place routine
+    L3, _ = ops.potrf(_dev(A))
+    assert _relerr(np.tril(L.cpu().numpy()), np.tril(L3.cpu().numpy())) < 1e-13
+
+
+def test_posv_reports_indefinite():
+    from edrgp_b200 import ops
+    A = np.eye(70); A[40, 40] = -1.0
+    _, _, info = ops.posv(_dev(A), _dev(np.ones(70)))
+    assert int(info.cpu()[0]) == 41
+
+
 def test_potrf_reports_indefinite():
     from edrgp_b200 import ops
     A = np.eye(40); A[17, 17] = -1.0

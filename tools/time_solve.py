@@ -18,5 +18,8 @@ cp = t(lambda: S.copy_(A))
 print(json.dumps({'m': m, 'potrf_ms': t(lambda: (S.copy_(A), ops.potrf(S))) - cp}))
 ops.potrf(S.copy_(A))
 print(json.dumps({'m': m, 'trsv_fwd_ms': t(lambda: ops.trsm(S, v.copy_(b), False)), 'trsv_bwd_ms': t(lambda: ops.trsm(S, v.copy_(b), True))}))
+print(json.dumps({'m': m, 'posv_ms': t(lambda: ops.posv(S.copy_(A), v.copy_(b))) - cp}))
+xp, _, _ = ops.posv(S.copy_(A), v.copy_(b))
+print('posv residual', float((A @ xp - b).abs().max()))
 x = b.clone(); ops.trsm(S, x, False); ops.trsm(S, x, True)
 print('residual', float((A @ x - b).abs().max()))
