@@ -732,7 +732,8 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 //     h = sqrt(diff^2 + 4 gamma^2), cos 2t = |diff| / h,  c = sqrt((1 + cos 2t) / 2),
 //     s = sign(diff) gamma / (h c)            (|t| <= pi / 4, c^2 + s^2 = 1 to rounding)
 // evaluated on operands scaled by a power of two so that the FP32 seeds stay in range.
-// EDRGP_JACOBI_VARIANT (tuning aid, read once): 0 = default lanes / rows split, 1 = fewer lanes, 2 = a warp per pair
+// EDRGP_JACOBI_VARIANT (tuning aid, read once): 0 = default lanes / rows split, 1 = fewer lanes, 2 = a warp per pair,
+// 4 = two-sided solver (d <= 64)
 static int jacobi_variant() {
   static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : 0; }();
   return v;
@@ -794,6 +795,16 @@ __device__ __forceinline__ void jacobi_finish(const double* __restrict__ C, int 
 }
 
 
+#ifdef JAC_PROFILE
+// tuning build (EDRGP_NVCC_EXTRA=-DJAC_PROFILE): clock64 stamps of one thread over steps 4..7 of sweep 1
+__device__ long long jac_prof[2][4][8];
+#define JAC_STAMP(i) do { if (sweep == 1 && step >= 4 && step < 8 && (tid == 0 || tid == nt - 32)) \
+    jac_prof[tid != 0][step - 4][i] = clock64(); } while (0)
+extern "C" int edrgp_debug_jac_prof(long long* out) { return (int)cudaMemcpyFromSymbol(out, jac_prof, sizeof(jac_prof)); }
+#else
+#define JAC_STAMP(i) do { } while (0)
+#endif
+
 // LOGV: V is NOT carried here.  Its update never feeds back into the rotations, yet it is half of the
 // shared-memory traffic and a fifth of the FP64 instructions of every step of this latency chain; the
 // kernel only records (c, s) of every pair and step (rotlog[(sweep (dd - 1) + step) np + slot]; (1, 0)
@@ -825,6 +836,7 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
     __syncthreads();
     for (int step = 0; step < dd - 1; ++step) {
       int p = 0, q = d;
+      JAC_STAMP(0);
       if (active) {                           // round-robin tournament; step, k < dd - 1: one conditional subtract
         int a0 = step + k, b0 = step + dd - 1 - k;
         if (a0 >= dd - 1) a0 -= dd - 1;
@@ -872,6 +884,7 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
         }
         alpha = pa[0]; beta = pb[0]; gamma = pg[0];
       }
+      JAC_STAMP(1);
 #pragma unroll
       for (int o = L / 2; o > 0; o >>= 1) {
         alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
@@ -879,6 +892,7 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
         gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
       }
       double c = 1.0, s = 0.0;
+      JAC_STAMP(2);
       if (live && gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
         const double sum = alpha + beta;
         const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
@@ -898,6 +912,7 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
         // a sweep whose rotations all stay below |cos| = 1e-9 leaves every pair orthogonal to ~1e-18 / gap
         // (quadratic convergence): it is the last one, no empty sweep is needed to find that out
         if (l == 0 && gamma * gamma > 1e-18 * alpha * beta) rotated = 1;
+        JAC_STAMP(3);
 #pragma unroll
         for (int e = 0; e < R; ++e) {
           if (l + L * e < d) {
@@ -912,7 +927,9 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
         }
       }
       if (LOGV && active && l == 0) rotlog[((size_t)sweep * (dd - 1) + step) * np + k] = make_double2(c, s);
+      JAC_STAMP(4);
       __syncthreads();
+      JAC_STAMP(5);
     }
     if (!rotated) { ++sweep; break; }
     __syncthreads();
@@ -924,6 +941,131 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
   }
   __syncthreads();
   jacobi_finish(C, d, V, ds, W, evals, comps, tid, nt);   // W's storage is free once every warp is past the barrier
+}
+
+#undef JAC_STAMP
+// Two-sided (classical) Jacobi for d <= 64 on the symmetric matrix itself, A <- J^T A J.  The rotation of a
+// pair comes from three ENTRIES (a_pp, a_qq, a_pq): no dot products and no lane reduction, which are 45 %
+// of the one-sided step (jac_profile tool: loads + dots + shuffles 860 of 1 940 cycles, parameters 580).  The
+// same parameter code applies (the two-sided condition c s (a_pp - a_qq) + (c^2 - s^2) a_pq = 0 is the
+// one-sided one with the Gram entries), the pairs of a step are disjoint, so all column rotations A J
+// run in parallel, then -- after a barrier -- all row rotations J^T (A J).  Rotations are only recorded
+// (rotlog, as in the LOGV mode above); jacobi_vectors_kernel replays them on V and finishes.  For a positive
+// semi-definite matrix |a_pq| <= sqrt(a_pp a_qq), so the relative rotation test of the one-sided solver
+// keeps its meaning; |a_pp a_qq| guards diagonal entries that rounding has pushed below zero.
+template <int L, int R>
+__global__ void __launch_bounds__(512) jacobi_twosided_kernel(const double* __restrict__ C, int d, int max_sweeps,
+                                                              int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
+                                                              int* __restrict__ nlog) {
+  extern __shared__ double sh[];
+  const int ds = d | 1;                       // odd stride: a column (fixed c) and a row (fixed r) are both conflict free
+  double* A = sh;                             // A[c * ds + r]
+  __shared__ int rotated;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int dd = d + (d & 1), np = dd / 2;
+  for (int i = tid; i < d * d; i += nt) {
+    const int c = i / d, r = i - c * d;
+    A[c * ds + r] = C[(int64_t)r * d + c];
+  }
+  __syncthreads();
+  // The parameters of a step's pairs are computed ONCE, by the first np threads (a thread per pair: one
+  // warp for d = 64), and published through shared memory: sixteen lanes per pair deriving the same (c, s)
+  // kept all sixteen warps issuing ~165 cycles of identical FP64 work per step.
+  __shared__ double2 cs[32];
+  __shared__ int rotf[32];
+  const int k = tid / L, l = tid % L;
+  const bool active = k < np;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int step = 0; step < dd - 1; ++step) {
+      if (tid < np) {                          // pair slot tid
+        int a0 = step + tid, b0 = step + dd - 1 - tid;
+        if (a0 >= dd - 1) a0 -= dd - 1;
+        if (b0 >= dd - 1) b0 -= dd - 1;
+        if (tid == 0) a0 = dd - 1;
+        const int p = min(a0, b0), q = max(a0, b0);
+        double c = 1.0, s = 0.0;
+        int rot = 0;
+        if (q < d) {
+          const double alpha = A[p * ds + p], beta = A[q * ds + q], gamma = A[p * ds + q];
+          const double ab = fabs(alpha * beta);
+          if (gamma * gamma > 1e-30 * ab && fabs(gamma) >= 1e-300) {
+            rot = 1;
+            const double sum = fabs(alpha) + fabs(beta);
+            const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
+            if (ex > 64 && ex < 1983) {
+              const double scale = __hiloint2double((2046 - ex) << 20, 0);
+              const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;
+              const double ih = fast_rsqrt(fma(dn, dn, gn * gn));
+              const double x = fma(0.5 * fabs(dn), ih, 0.5);
+              const double r = fast_rsqrt(x);
+              c = x * r;
+              s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
+            } else {
+              const double zeta = (beta - alpha) / (2.0 * gamma);
+              const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+              c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
+            }
+            if (gamma * gamma > 1e-18 * ab) rotated = 1;
+          }
+        }
+        cs[tid] = make_double2(c, s);
+        rotf[tid] = rot;
+        rotlog[((size_t)sweep * (dd - 1) + step) * np + tid] = make_double2(c, s);
+      }
+      int p = 0, q = d;
+      if (active) {
+        int a0 = step + k, b0 = step + dd - 1 - k;
+        if (a0 >= dd - 1) a0 -= dd - 1;
+        if (b0 >= dd - 1) b0 -= dd - 1;
+        if (k == 0) a0 = dd - 1;
+        p = min(a0, b0); q = max(a0, b0);
+      }
+      const bool live = active && q < d;
+      const int qq = live ? q : p;
+      double xa[R], xb[R];
+#pragma unroll
+      for (int e = 0; e < R; ++e) {
+        const bool ok = live && l + L * e < d;
+        xa[e] = ok ? A[p * ds + l + L * e] : 0.0;
+        xb[e] = ok ? A[qq * ds + l + L * e] : 0.0;
+      }
+      __syncthreads();
+      const bool rot = live && rotf[k] != 0;
+      const double2 csk = active ? cs[k] : make_double2(1.0, 0.0);
+      const double c = csk.x, s = csk.y;
+      if (rot) {
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          if (l + L * e < d) {
+            A[p * ds + l + L * e] = c * xa[e] - s * xb[e];
+            A[q * ds + l + L * e] = s * xa[e] + c * xb[e];
+          }
+        }
+      }
+      __syncthreads();
+      if (rot) {
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          const int j = l + L * e;
+          if (j < d) {
+            const double ya = A[j * ds + p], yb = A[j * ds + q];
+            A[j * ds + p] = c * ya - s * yb;
+            A[j * ds + q] = s * ya + c * yb;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!rotated) { ++sweep; break; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (sweeps_out) *sweeps_out = sweep;
+    nlog[0] = sweep; nlog[1] = 0;
+  }
 }
 
 // Replays the rotation log of jacobi_onesided_kernel<.., true> on V = I.  A warp per ROW of V (rows never
@@ -1016,7 +1158,15 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     double* Vt = ws + jacobi_log_doubles(d);
     int* ctrl = reinterpret_cast<int*>(Vt + (size_t)d * d);          // [0] sweeps logged, [1] ticket
     const size_t smem = (size_t)d * ds * sizeof(double);
-    jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
+    // EDRGP_JACOBI_VARIANT=4: the two-sided solver (tuning aid).  Same time per step as the one-sided one
+    // (0.58 vs 0.56 ms at d = 64 on a spectrum with a few dominant directions, 8 sweeps each), fewer sweeps on
+    // flat spectra (9 vs 14: 0.65 vs 0.89 ms); the one-sided solver stays the default because its relative
+    // rotation test also terminates on numerically rank-deficient matrices, where the entries the two-sided
+    // test looks at are rounding noise.
+    if (jacobi_variant() == 4)
+      jacobi_twosided_kernel<(L > 16 ? 16 : L), (L > 16 ? 2 * R : R)><<<1, min(threads, 512), smem, st>>>(C, d, 60, sweeps, rotlog, ctrl);
+    else
+      jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
     count_launch();
     jacobi_vectors_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
     count_launch();

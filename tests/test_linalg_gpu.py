@@ -148,6 +148,29 @@ def test_posv_reports_indefinite():
     assert int(info.cpu()[0]) == 41
 
 
+def test_eigh_twosided_variant_matches_lapack():
+    """EDRGP_JACOBI_VARIANT=4 (two-sided solver, read once per process: run in a child process)."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch\n"
+        "from edrgp_b200 import ops\n"
+        "for d in (3, 10, 33, 64):\n"
+        "    rng = np.random.RandomState(d)\n"
+        "    G = rng.standard_normal((3 * d + 5, d)) * np.linspace(3.0, 0.1, d)\n"
+        "    C = G.T.dot(G)\n"
+        "    ev, cp = ops.eigh(torch.as_tensor(C, device='cuda'))\n"
+        "    ev, cp = ev.cpu().numpy(), cp.cpu().numpy()\n"
+        "    lam = np.linalg.eigvalsh(C)[::-1]\n"
+        "    assert np.allclose(ev, lam, rtol=1e-12, atol=1e-12 * lam[0])\n"
+        "    assert np.max(np.abs(cp.dot(cp.T) - np.eye(d))) < 1e-12\n"
+        "    assert np.max(np.abs(cp.dot(C).dot(cp.T) - np.diag(ev))) < 1e-11 * lam[0]\n"
+        "print('ok')\n")
+    env = dict(os.environ, EDRGP_JACOBI_VARIANT='4')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
 def test_potrf_reports_indefinite():
     from edrgp_b200 import ops
     A = np.eye(40); A[17, 17] = -1.0

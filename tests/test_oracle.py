@@ -83,6 +83,40 @@ def test_inducing_equals_data_is_dense_gp():
     assert np.allclose(mu_sparse, mu_dense, atol=1e-5)
 
 
+def test_oracle_matches_sklearn_gp_when_inducing_equals_data():
+    """Independent third-party pin: with Z = X the variational sparse GP IS the exact GP, so the oracle's
+    posterior mean, VFE bound, posterior-mean gradient and predictive variance must agree with
+    scikit-learn's GaussianProcessRegressor (an implementation that shares no code with GPy or with this
+    repository) on the same ARD-RBF kernel and noise."""
+    from sklearn.gaussian_process import GaussianProcessRegressor as SkGP
+    from sklearn.gaussian_process.kernels import RBF as SkRBF, ConstantKernel
+    rng = np.random.RandomState(11)
+    n, d = 60, 3
+    X = rng.standard_normal((n, d)); y = np.tanh(X[:, 0] - 0.5 * X[:, 2]) + 0.05 * rng.standard_normal(n)
+    sf2, ell, noise = 1.7, np.array([0.8, 1.9, 1.2]), 0.03
+    kern = gpy.RBF(d, sf2, ell, ARD=True)
+    post, ll, _ = gpy.vardtc_inference(kern, X, X.copy(), noise, y[:, None])
+    sk = SkGP(kernel=ConstantKernel(sf2, 'fixed') * SkRBF(ell, 'fixed'), alpha=noise, optimizer=None).fit(X, y)
+    Xs = rng.standard_normal((25, d))
+    alpha = post.woodbury_vector[:, 0]
+    mu = kern.K(Xs, X).dot(alpha)
+    mu_sk, sd_sk = sk.predict(Xs, return_std=True)
+    # GPy adds 1e-8 jitter to Kuu: agreement to ~1e-6, far above what a wrong formula would leave
+    assert np.allclose(mu, mu_sk, atol=2e-6)
+    assert abs(float(np.asarray(ll).ravel()[0]) - sk.log_marginal_likelihood_value_) < 1e-5 * abs(sk.log_marginal_likelihood_value_)
+    # predictive (latent) variance k** - k*^T W k*
+    Ks = kern.K(Xs, X)
+    var = sf2 - np.einsum('ij,jk,ik->i', Ks, post.woodbury_inv, Ks)
+    assert np.allclose(var, sd_sk ** 2, atol=2e-6)
+    # gradient of the posterior mean against central differences of sklearn's predictor
+    G = op.gradients_faithful(Xs, X, ell, sf2, alpha)
+    h = 1e-5
+    for q in range(d):
+        e = np.zeros(d); e[q] = h
+        fd = (sk.predict(Xs + e) - sk.predict(Xs - e)) / (2 * h)
+        assert np.allclose(G[:, q], fd, atol=5e-6)
+
+
 def test_eigh_of_gram_equals_svd():
     w = _small()
     _, post, _, _ = _fit_fixed(w)

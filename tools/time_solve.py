@@ -21,5 +21,6 @@ print(json.dumps({'m': m, 'trsv_fwd_ms': t(lambda: ops.trsm(S, v.copy_(b), False
 print(json.dumps({'m': m, 'posv_ms': t(lambda: ops.posv(S.copy_(A), v.copy_(b))) - cp}))
 xp, _, _ = ops.posv(S.copy_(A), v.copy_(b))
 print('posv residual', float((A @ xp - b).abs().max()))
+ops.potrf(S.copy_(A))
 x = b.clone(); ops.trsm(S, x, False); ops.trsm(S, x, True)
 print('residual', float((A @ x - b).abs().max()))
