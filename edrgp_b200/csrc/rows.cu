@@ -53,25 +53,41 @@ __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* _
       for (int cc = 0; cc < 16; ++cc) if (cc == c) v = k == 0 ? s1[cc] : s2[cc];
       red[threadIdx.x] = active ? v : 0.0;
       __syncthreads();
+      // pairwise tree over the row-threads (a serial sum by one thread was a chain of CM_THREADS / lanes
+      // dependent FP64 additions: 10 us of a 54 us call for a single column)
+      for (int cnt = rows_per_pass; cnt > 1;) {
+        const int half = (cnt + 1) / 2;
+        if (active && tr < cnt / 2) red[tr * lanes + tc] += red[(tr + half) * lanes + tc];
+        __syncthreads();
+        cnt = half;
+      }
       if (tr == 0 && active) {
-        double acc = 0.0;
-        for (int rr = 0; rr < rows_per_pass; ++rr) acc += red[rr * lanes + tc];
         const int q = tc + c * lanes;
-        if (q < d) part[((size_t)blockIdx.x * 2 + k) * d + q] = acc;
+        if (q < d) part[((size_t)blockIdx.x * 2 + k) * d + q] = red[tc];
       }
       __syncthreads();
     }
   }
 }
 
-__global__ void col_moments_reduce_kernel(const double* __restrict__ part, int nblk, int d, double* __restrict__ out,
-                                          int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over 2*d
+// one warp per output (2 d of them): lanes stride over the CTA partials with two accumulators, then a
+// shuffle tree; fixed order, deterministic
+__global__ void __launch_bounds__(256) col_moments_reduce_kernel(const double* __restrict__ part, int nblk, int d,
+                                                                 double* __restrict__ out, int accumulate) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= 2 * d) return;
   const int k = i / d, q = i - k * d;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += part[((size_t)b * 2 + k) * d + q];
-  out[i] = accumulate ? out[i] + s : s;
+  double s0 = 0.0, s1 = 0.0;
+  int b = lane;
+  for (; b + 32 < nblk; b += 64) {
+    s0 += part[((size_t)b * 2 + k) * d + q];
+    s1 += part[((size_t)(b + 32) * 2 + k) * d + q];
+  }
+  if (b < nblk) s0 += part[((size_t)b * 2 + k) * d + q];
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = accumulate ? out[i] + s : s;
 }
 
 __global__ void standardize_kernel(const double* __restrict__ X, int64_t total, int d, const double* __restrict__ mean,
@@ -162,7 +178,7 @@ cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* 
   col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, weight, workspace); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  col_moments_reduce_kernel<<<(2 * d + 127) / 128, 128, 0, st>>>(workspace, grid, d, out, accumulate); count_launch();
+  col_moments_reduce_kernel<<<(2 * d * 32 + 255) / 256, 256, 0, st>>>(workspace, grid, d, out, accumulate); count_launch();
   return cudaGetLastError();
 }
 

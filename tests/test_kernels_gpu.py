@@ -152,3 +152,26 @@ def test_projection_matches_numpy(n, d, k):
     ref = X.dot(V.T)
     assert out.shape == (n, k)
     assert _relerr(out, ref) < 1e-13
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (7, 1), (100000, 1), (500001, 1), (999, 10), (4097, 33), (20000, 64), (3000, 200),
+                                 (513, 512)])
+def test_col_moments_match_numpy(n, d):
+    """Column sums and sums of squares about a shift, optionally weighted (the scaler / normaliser moments
+    and the lengthscale-gradient moment): tree reductions, deterministic."""
+    from edrgp_b200 import ops
+    rng = np.random.RandomState(n + d)
+    X = rng.standard_normal((n, d)) * 3.0 + 1.5
+    shift = rng.standard_normal(d)
+    w = rng.uniform(0.5, 1.5, size=n)
+    Xd = _dev(X if d > 1 else X[:, 0])
+    s1, s2 = ops.col_moments(Xd)
+    assert np.allclose(s1.cpu().numpy(), X.sum(0), rtol=1e-12, atol=1e-9)
+    assert np.allclose(s2.cpu().numpy(), (X ** 2).sum(0), rtol=1e-12)
+    s1, s2 = ops.col_moments(Xd, shift=_dev(shift), weight=_dev(w))
+    ref1 = (w[:, None] * (X - shift)).sum(0)
+    ref2 = (w[:, None] * (X - shift) ** 2).sum(0)
+    assert np.allclose(s1.cpu().numpy(), ref1, rtol=1e-12, atol=1e-9)
+    assert np.allclose(s2.cpu().numpy(), ref2, rtol=1e-12)
+    t1, t2 = ops.col_moments(Xd, shift=_dev(shift), weight=_dev(w))
+    assert torch.equal(s1, t1) and torch.equal(s2, t2)
