@@ -585,10 +585,100 @@ __global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ L,
   for (int i = tid; i < m; i += blockDim.x) x[i * incx] = xs[i];
 }
 
+// One right-hand side, m <= 704: the same solve with the 32 x 32 diagonal blocks INVERTED first (all
+// blocks at once, a warp per block, a lane per column of the inverse: 32 dependent fma each), so that the
+// sequential part of a block step is a 32 x 32 matrix-vector product (four partial sums: ~10 dependent
+// FP64 operations) instead of 32 substitution steps of shuffle + multiply + fma (~3 300 cycles); the L
+// entries of a block's update are fetched before the product, not after it.  Shared memory: the inverses
+// (33 x 32 doubles per block) and the vector.
+constexpr int TRSV_INV_MAX_BLOCKS = 22;
+__global__ void __launch_bounds__(256) trsv_inv_kernel(const double* __restrict__ L, int64_t ldl, int m,
+                                                       double* __restrict__ x, int64_t incx, int trans) {
+  extern __shared__ __align__(16) double tsm[];
+  const int nblk = (m + NBK - 1) / NBK;
+  double* inv = tsm;                                   // [nblk][32][33]: inv[b][j * 33 + c] = (L_bb^-1)[c][j]
+  double* xs = tsm + (size_t)nblk * NBK * (NBK + 1);   // [m]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < m; i += blockDim.x) xs[i] = x[i * incx];
+  for (int b = warp; b < nblk; b += 8) {
+    const int k0 = b * NBK, nb = min(NBK, m - k0);
+    double* Mt = inv + (size_t)b * NBK * (NBK + 1);    // scratch for the scaled transposed block, then the inverse
+    double a[NBK];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) {
+      a[c] = c == lane ? 1.0 : 0.0;
+      if (lane < nb && c <= lane) a[c] = L[(int64_t)(k0 + lane) * ldl + k0 + c];
+    }
+    double diag = 1.0;
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) diag = c == lane ? a[c] : diag;
+    const double dinv = 1.0 / diag;
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) Mt[c * NBK + lane] = a[c] * dinv;
+    __syncwarp();
+    double z[NBK];
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) z[c] = c == lane ? dinv : 0.0;
+    panel_solve_rows(z, Mt);                            // z[c] = (L_bb^-1)[c][lane]
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NBK; ++c) Mt[lane * (NBK + 1) + c] = z[c];
+  }
+  __syncthreads();
+  for (int bb = 0; bb < nblk; ++bb) {
+    const int b = trans ? nblk - 1 - bb : bb;
+    const int k0 = b * NBK, nb = min(NBK, m - k0);
+    const double* ib = inv + (size_t)b * NBK * (NBK + 1);
+    // this thread's first row / column of the update, fetched ahead of the block solve
+    const int r0 = trans ? tid : k0 + nb + tid;
+    const bool have = trans ? r0 < k0 : r0 < m;
+    double lv[NBK];
+    if (have) {
+#pragma unroll
+      for (int k = 0; k < NBK; ++k)
+        lv[k] = k < nb ? (trans ? L[(int64_t)(k0 + k) * ldl + r0] : L[(int64_t)r0 * ldl + k0 + k]) : 0.0;
+    }
+    if (warp == 0) {
+      double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < NBK; ++j) {
+        // forward: (L^-1)[lane][j] = ib[j * 33 + lane];  backward: (L^-T)[lane][j] = (L^-1)[j][lane] = ib[lane * 33 + j]
+        const double cij = trans ? ib[lane * (NBK + 1) + j] : ib[j * (NBK + 1) + lane];
+        p[j & 3] = fma(cij, j < nb ? xs[k0 + j] : 0.0, p[j & 3]);
+      }
+      __syncwarp();
+      if (lane < nb) xs[k0 + lane] = (p[0] + p[1]) + (p[2] + p[3]);
+    }
+    __syncthreads();
+    for (int r = r0, pass = 0; trans ? r < k0 : r < m; r += blockDim.x, ++pass) {
+      if (pass > 0) {
+#pragma unroll
+        for (int k = 0; k < NBK; ++k)
+          lv[k] = k < nb ? (trans ? L[(int64_t)(k0 + k) * ldl + r] : L[(int64_t)r * ldl + k0 + k]) : 0.0;
+      }
+      double q[4] = {xs[r], 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < NBK; ++k) q[k & 3] = fma(-lv[k], k < nb ? xs[k0 + k] : 0.0, q[k & 3]);
+      xs[r] = (q[0] + q[1]) + (q[2] + q[3]);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += blockDim.x) x[i * incx] = xs[i];
+}
+
 cudaError_t launch_trsm(const double* L, int m, int64_t ldl, double* B, int nrhs, int64_t ldb, int trans,
                         cudaStream_t st) {
   const int nblk = (m + NBK - 1) / NBK;
   cudaError_t e = cudaSuccess;
+  if (nrhs == 1 && nblk <= TRSV_INV_MAX_BLOCKS) {
+    const size_t smem = ((size_t)nblk * NBK * (NBK + 1) + (size_t)m) * sizeof(double);
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(trsv_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    trsv_inv_kernel<<<1, 256, smem, st>>>(L, ldl, m, B, ldb, trans); count_launch();
+    return cudaGetLastError();
+  }
   if (nrhs == 1) {
     const size_t smem = ((size_t)((m + 1) & ~1) + NBK * (NBK + 1)) * sizeof(double);
     if (smem <= 200 * 1024) {
