@@ -201,9 +201,9 @@ cudaError_t launch_potrf(double* A, int m, int64_t ld, int* info, cudaStream_t s
 // a SEPARATE output matrix -- every CTA of the step reads block column k of A while one of them
 // produces L's -- and the right-hand side rides along as one more row of the matrix, which makes the
 // forward substitution free: after the last step that row holds L^-1 rhs.  A's lower triangle is
-// destroyed; the backward substitution is trsv_kernel.
+// destroyed; the backward substitution is trsv_inv_kernel (trsv_kernel beyond 704 unknowns).
 // ---------------------------------------------------------------------------------------------
-// FP64 operations cost ~40 cycles each on a dependent chain here (measured: chol_profile tool), so the
+// FP64 operations cost ~30-37 cycles each on a dependent chain here (tools/chol_profile.py), so the
 // routines below are arranged around the number of DEPENDENT FP64 operations per column.
 //
 // reciprocal / reciprocal square root of a positive normal double: hardware FP64 seed (~20 bits) + two
