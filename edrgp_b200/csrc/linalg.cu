@@ -1231,9 +1231,93 @@ __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_kernel(
   jacobi_finish(C, d, Vt, d, lam, evals, comps, tid, JV_WARPS * 32);
 }
 
-static size_t jacobi_log_doubles(int d) {
+// The same replay with the per-step overhead taken out (the kernel above executes 64 instructions per step
+// and warp of which 4 are FP64, 4 shuffles and 1 a load: profiles/r01c_ncu_small_solvers.txt): the
+// orientation of a slot at every step of a sweep is a 63-bit mask computed once, the log is read through a
+// running pointer sixteen steps ahead without bounds tests (the workspace carries 32 steps of slack), only
+// the tail batch is guarded.  Selected with EDRGP_JACOBI_REPLAY=1.  NOT YET RUN ON A GPU: written after the
+// round's GPU budget was spent; validate with `pytest tests/test_linalg_gpu.py -k eigh` before making it the default.
+__global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
+    const double* __restrict__ C, int d, const double2* __restrict__ rotlog, int* ctrl, double* Vt,
+    double* __restrict__ evals, double* __restrict__ comps) {
+  __shared__ double lam[64];
+  __shared__ int last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dd = d + (d & 1), np = dd / 2, per = dd - 1;
+  const int row = blockIdx.x * JV_WARPS + warp;
+  const int nsteps = ctrl[0] * per;
+  if (row < d) {
+    const bool act = lane < np;
+    unsigned long long flip = 0;                    // bit st: the slot's first column is the larger index at step st
+    for (int st = 0; st < per; ++st) {
+      int a0 = st + lane, b0 = st + per - lane;
+      if (a0 >= per) a0 -= per;
+      if (b0 >= per) b0 -= per;
+      if (lane == 0) a0 = per;
+      if (act && a0 > b0) flip |= 1ull << st;
+    }
+    double va, vb;
+    {
+      const int a0 = lane == 0 ? per : lane, b0 = lane == 0 ? 0 : per - lane;
+      va = (act && a0 == row) ? 1.0 : 0.0;
+      vb = (act && b0 == row) ? 1.0 : 0.0;
+    }
+    const bool is0 = lane == 0, isl = np > 1 && lane == np - 1, ring = np > 1;
+    const double2* lp = rotlog + (act ? lane : 0);
+    const size_t batch = (size_t)JV_AHEAD * np;
+    double2 q[JV_AHEAD];
+#pragma unroll
+    for (int i = 0; i < JV_AHEAD; ++i) q[i] = lp[(size_t)i * np];
+    lp += batch;
+    int st = 0, g = 0;
+#define JV_STEP(cs)                                                                                          \
+    {                                                                                                        \
+      const double c = (cs).x;                                                                               \
+      const unsigned fb = (unsigned)((flip >> st) & 1ull) << 31;                                             \
+      const double sg = __hiloint2double(__double2hiint((cs).y) ^ (int)fb, __double2loint((cs).y));          \
+      const double na = c * va - sg * vb, nb = sg * va + c * vb;                                             \
+      const double dn = __shfl_down_sync(0xffffffffu, na, 1), up = __shfl_up_sync(0xffffffffu, nb, 1);       \
+      va = (is0 || !ring) ? na : (isl ? nb : dn);                                                            \
+      vb = !ring ? nb : (is0 ? dn : up);                                                                     \
+      st = st + 1 == per ? 0 : st + 1;                                                                       \
+    }
+    for (; g + JV_AHEAD <= nsteps; g += JV_AHEAD) {
+#pragma unroll
+      for (int i = 0; i < JV_AHEAD; ++i) {
+        const double2 cs = q[i];
+        q[i] = lp[(size_t)i * np];                  // 16 .. 32 steps ahead: inside the log or its slack
+        JV_STEP(cs)
+      }
+      lp += batch;
+    }
+#pragma unroll
+    for (int i = 0; i < JV_AHEAD; ++i) {
+      if (g + i < nsteps) JV_STEP(q[i])             // uniform across the warp
+    }
+#undef JV_STEP
+    if (act) {                                      // st == 0 again: the slots hold their initial columns
+      const int a0 = lane == 0 ? per : lane, b0 = lane == 0 ? 0 : per - lane;
+      if (a0 < d) Vt[(size_t)a0 * d + row] = va;
+      if (b0 < d) Vt[(size_t)b0 * d + row] = vb;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(ctrl + 1), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  jacobi_finish(C, d, Vt, d, lam, evals, comps, tid, JV_WARPS * 32);
+}
+
+static int jacobi_replay_variant() {
+  static const int v = [] { const char* e = getenv("EDRGP_JACOBI_REPLAY"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+static size_t jacobi_log_doubles(int d) {      // 60 sweeps + 32 steps of slack (read ahead, never used)
   const int dd = d + (d & 1);
-  return (size_t)60 * (dd - 1) * (dd / 2) * 2;
+  return ((size_t)60 * (dd - 1) + 2 * JV_AHEAD) * (dd / 2) * 2;
 }
 
 template <int L, int R>
@@ -1258,7 +1342,10 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     else
       jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
     count_launch();
-    jacobi_vectors_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
+    if (jacobi_replay_variant() == 1)
+      jacobi_vectors_lean_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
+    else
+      jacobi_vectors_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
     count_launch();
     return cudaGetLastError();
   }
