@@ -218,6 +218,9 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # multi-rank runs: keep each rank (and the pinned host buffers it allocates from here on) on the CPUs next
+    # to its GPU; a single rank keeps every host core (the CPU baseline runs in this process)
+    host_affinity = edist.bind_to_local_cpus(local_rank) if world > 1 else 'unchanged (single rank)'
     # ONE JSON line on stdout: native libraries that write to file descriptor 1 (NCCL's version banner)
     # are sent to stderr; the line itself goes through a duplicate of the original descriptor
     sys.stdout.flush()
@@ -435,6 +438,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if args.precision == 'fp64' else "f64 (cross-covariance contraction: tf32 x 3)", "data": "synthetic",
         "config": {"workload": workload_name(args), "n": n, "d": d, "m": m, "rows_per_rank": n_local,
+                   "host_affinity": host_affinity,
                    "hyperparameters": "fixed (lengthscales sqrt(d)(1+u/2), variance 1, noise 0.1)",
                    "l2": "inputs (%.2f GB X per rank + %.1f GB Kfu blocks) exceed the 126 MB L2; no flush needed"
                          % (n_local * d * 8 / 1e9, n_local * m * 8 / 1e9),

@@ -7,6 +7,7 @@ Per fixed-hyper-parameter sweep exactly two all-reduces run on the data path:
 (plus 2d / 2 doubles for the scaler / target normaliser).  Everything else is rank-local.
 """
 import contextlib
+import os
 
 import torch
 
@@ -64,3 +65,46 @@ def shard_bounds(n, r=None, w=None):
     base, rem = divmod(n, w)
     lo = r * base + min(r, rem)
     return lo, lo + base + (1 if r < rem else 0)
+
+
+def bind_to_local_cpus(device_index, min_cpus=2):
+    """Pin this process to the CPUs NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe root),
+    so that the pinned host buffers it allocates AFTERWARDS (first touch) and the threads that feed the copy
+    engine sit next to the GPU.  With eight ranks streaming their row shards from host memory the transfers
+    otherwise cross the socket interconnect.  Does nothing -- and says so in the returned string -- when NVML or
+    the affinity call is unavailable, when the local set is not a strict subset of the CPUs this process may
+    already use, or when it has fewer than ``min_cpus`` CPUs.  Call it once per rank, before any pinned
+    allocation; never raises."""
+    if os.environ.get('EDRGP_BIND_LOCAL_CPUS', '1') == '0':
+        return 'unchanged (EDRGP_BIND_LOCAL_CPUS=0)'
+    try:
+        allowed = os.sched_getaffinity(0)
+    except (AttributeError, OSError) as e:
+        return 'unchanged (no sched_getaffinity: %s)' % e
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(device_index)
+            if visible:                                   # NVML numbers the physical devices
+                ids = [v.strip() for v in visible.split(',') if v.strip()]
+                if idx < len(ids) and ids[idx].isdigit():
+                    idx = int(ids[idx])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = (max(allowed) // 64) + 1 if allowed else 1
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception as e:                                # NVML missing / old driver / container without it
+        return 'unchanged (NVML affinity unavailable: %s)' % type(e).__name__
+    local = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+    target = local & allowed
+    if len(target) < min_cpus or target == allowed:
+        return 'unchanged (%d local of %d allowed CPUs)' % (len(target), len(allowed))
+    try:
+        os.sched_setaffinity(0, target)
+    except OSError as e:
+        return 'unchanged (sched_setaffinity: %s)' % e
+    lo, hi = min(target), max(target)
+    return 'bound to %d CPUs local to GPU %d (%d..%d)' % (len(target), int(device_index), lo, hi)

@@ -88,3 +88,49 @@ def test_shard_bounds_cover_rows_exactly():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _fake_nvml(mask_words):
+    import types
+    m = types.ModuleType('pynvml')
+    m.nvmlInit = lambda: None
+    m.nvmlShutdown = lambda: None
+    m.nvmlDeviceGetHandleByIndex = lambda i: ('gpu', i)
+    m.nvmlDeviceGetCpuAffinity = lambda h, n: list(mask_words)[:n] + [0] * max(0, n - len(mask_words))
+    return m
+
+
+def test_bind_to_local_cpus_guards(monkeypatch):
+    """Rank placement next to the GPU (multi-rank bench runs): binds only to a usable strict subset of the CPUs
+    the process may already use, reports what it did, never raises."""
+    import os
+    import sys
+    from edrgp_b200 import dist
+    calls = []
+    monkeypatch.setattr(os, 'sched_getaffinity', lambda pid: set(range(8)), raising=False)
+    monkeypatch.setattr(os, 'sched_setaffinity', lambda pid, cpus: calls.append(set(cpus)), raising=False)
+    monkeypatch.delenv('CUDA_VISIBLE_DEVICES', raising=False)
+    monkeypatch.delenv('EDRGP_BIND_LOCAL_CPUS', raising=False)
+    # CPUs 4..7 are local: bound
+    monkeypatch.setitem(sys.modules, 'pynvml', _fake_nvml([0xF0]))
+    msg = dist.bind_to_local_cpus(1)
+    assert calls == [{4, 5, 6, 7}] and msg.startswith('bound to 4 CPUs local to GPU 1')
+    # every allowed CPU is local: nothing to do
+    calls.clear()
+    monkeypatch.setitem(sys.modules, 'pynvml', _fake_nvml([0xFF]))
+    assert dist.bind_to_local_cpus(0).startswith('unchanged') and not calls
+    # a single local CPU would serialise the rank's threads: refused
+    monkeypatch.setitem(sys.modules, 'pynvml', _fake_nvml([0x01]))
+    assert dist.bind_to_local_cpus(0).startswith('unchanged') and not calls
+    # local CPUs outside the allowed set (cgroup / taskset): refused
+    monkeypatch.setitem(sys.modules, 'pynvml', _fake_nvml([0xFF00]))
+    assert dist.bind_to_local_cpus(0).startswith('unchanged') and not calls
+    # NVML failing in any way: unchanged, no exception
+    bad = _fake_nvml([0xF0])
+    bad.nvmlInit = lambda: (_ for _ in ()).throw(RuntimeError('no driver'))
+    monkeypatch.setitem(sys.modules, 'pynvml', bad)
+    assert dist.bind_to_local_cpus(0).startswith('unchanged') and not calls
+    # switched off
+    monkeypatch.setenv('EDRGP_BIND_LOCAL_CPUS', '0')
+    monkeypatch.setitem(sys.modules, 'pynvml', _fake_nvml([0xF0]))
+    assert dist.bind_to_local_cpus(0).startswith('unchanged') and not calls
