@@ -823,7 +823,7 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 //     s = sign(diff) gamma / (h c)            (|t| <= pi / 4, c^2 + s^2 = 1 to rounding)
 // evaluated on operands scaled by a power of two so that the FP32 seeds stay in range.
 // EDRGP_JACOBI_VARIANT (tuning aid, read once): 0 = default lanes / rows split, 1 = fewer lanes, 2 = a warp per pair,
-// 4 = two-sided solver (d <= 64)
+// 4 = two-sided solver (d <= 64), 5 = one-sided solver specialised for d = 64 (not yet validated on a GPU)
 static int jacobi_variant() {
   static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : 0; }();
   return v;
@@ -1034,6 +1034,96 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
 }
 
 #undef JAC_STAMP
+// The one-sided solver with recorded rotations, specialised for d = 64 (EDRGP_JACOBI_VARIANT=5): what bounds a
+// step is the NUMBER of instructions each warp issues (228 in the general kernel, of which ~75 are the pair
+// schedule, the `live` / row-bound predicates and address arithmetic: profiles/r01c_ncu_small_solvers.txt), so
+// here the schedule of a whole sweep is a 4 KB shared-memory table built once, every pair is live, every lane
+// owns exactly four rows and the log is written through a running pointer.  The arithmetic is the general
+// kernel's, operation for operation.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent):
+// validate with `EDRGP_JACOBI_VARIANT=5 python tools/check_replay_variant.py` before making it the default.
+__global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restrict__ C, int max_sweeps,
+                                                         int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
+                                                         int* __restrict__ nlog) {
+  constexpr int D = 64, DS = 66, NP = 32, PER = 63, L = 16, R = 4;
+  extern __shared__ double sh[];
+  double* W = sh;                             // [D][DS] column-major
+  __shared__ unsigned short sched[PER * NP];  // p | q << 8 of slot k at step s
+  __shared__ int rotated;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < D * D; i += 512) {
+    const int c = i >> 6, r = i & 63;
+    W[c * DS + r] = C[(int64_t)r * D + c];
+  }
+  for (int i = tid; i < PER * NP; i += 512) {
+    const int step = i >> 5, k = i & 31;
+    int a0 = step + k, b0 = step + PER - k;
+    if (a0 >= PER) a0 -= PER;
+    if (b0 >= PER) b0 -= PER;
+    if (k == 0) a0 = PER;
+    sched[i] = (unsigned short)(min(a0, b0) | (max(a0, b0) << 8));
+  }
+  __syncthreads();
+  const int k = tid >> 4, l = tid & 15;
+  double2* rl = rotlog + k;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int step = 0; step < PER; ++step) {
+      const unsigned pq = sched[step * NP + k];
+      double* Wp = W + (pq & 0xffu) * DS + l;
+      double* Wq = W + (pq >> 8) * DS + l;
+      double wa[R], wb[R];
+#pragma unroll
+      for (int e = 0; e < R; ++e) { wa[e] = Wp[L * e]; wb[e] = Wq[L * e]; }
+      double pa0 = wa[0] * wa[0], pb0 = wb[0] * wb[0], pg0 = wa[0] * wb[0];
+      double pa1 = wa[1] * wa[1], pb1 = wb[1] * wb[1], pg1 = wa[1] * wb[1];
+      pa0 = fma(wa[2], wa[2], pa0); pb0 = fma(wb[2], wb[2], pb0); pg0 = fma(wa[2], wb[2], pg0);
+      pa1 = fma(wa[3], wa[3], pa1); pb1 = fma(wb[3], wb[3], pb1); pg1 = fma(wa[3], wb[3], pg1);
+      double alpha = pa0 + pa1, beta = pb0 + pb1, gamma = pg0 + pg1;
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+      }
+      double c = 1.0, s = 0.0;
+      if (gamma * gamma > 1e-30 * alpha * beta && fabs(gamma) >= 1e-300) {
+        const double sum = alpha + beta;
+        const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
+        if (ex > 64 && ex < 1983) {
+          const double scale = __hiloint2double((2046 - ex) << 20, 0);
+          const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;
+          const double ih = fast_rsqrt(fma(dn, dn, gn * gn));
+          const double x = fma(0.5 * fabs(dn), ih, 0.5);
+          const double r = fast_rsqrt(x);
+          c = x * r;
+          s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
+        } else {
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
+        }
+        if (l == 0 && gamma * gamma > 1e-18 * alpha * beta) rotated = 1;
+#pragma unroll
+        for (int e = 0; e < R; ++e) {
+          Wp[L * e] = c * wa[e] - s * wb[e];
+          Wq[L * e] = s * wa[e] + c * wb[e];
+        }
+      }
+      if (l == 0) *rl = make_double2(c, s);
+      rl += NP;
+      __syncthreads();
+    }
+    if (!rotated) { ++sweep; break; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (sweeps_out) *sweeps_out = sweep;
+    nlog[0] = sweep; nlog[1] = 0;
+  }
+}
+
 // Two-sided (classical) Jacobi for d <= 64 on the symmetric matrix itself, A <- J^T A J.  The rotation of a
 // pair comes from three ENTRIES (a_pp, a_qq, a_pq): no dot products and no lane reduction, which are 45 %
 // of the one-sided step (jac_profile tool: loads + dots + shuffles 860 of 1 940 cycles, parameters 580).  The
@@ -1337,7 +1427,9 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     // flat spectra (9 vs 14: 0.65 vs 0.89 ms); the one-sided solver stays the default because its relative
     // rotation test also terminates on numerically rank-deficient matrices, where the entries the two-sided
     // test looks at are rounding noise.
-    if (jacobi_variant() == 4)
+    if (jacobi_variant() == 5 && d == 64)
+      jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl);
+    else if (jacobi_variant() == 4)
       jacobi_twosided_kernel<(L > 16 ? 16 : L), (L > 16 ? 2 * R : R)><<<1, min(threads, 512), smem, st>>>(C, d, 60, sweeps, rotlog, ctrl);
     else
       jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);

@@ -3,6 +3,7 @@ budget was spent, so it is OFF by default and has not run on a GPU yet).
 
     EDRGP_JACOBI_REPLAY=1 python tools/check_replay_variant.py     # parity vs LAPACK + timing
     python tools/check_replay_variant.py                           # the default replay kernel, for comparison
+    EDRGP_JACOBI_VARIANT=5 python tools/check_replay_variant.py    # the d = 64 specialised solver (also unvalidated)
 """
 import json, os, sys
 import numpy as np, torch
@@ -30,4 +31,4 @@ e0.record()
 for _ in range(20):
     ops.eigh(C)
 e1.record(); e1.synchronize()
-print(json.dumps({'replay_variant': os.environ.get('EDRGP_JACOBI_REPLAY', '0'), 'parity': 'ok', 'eigh_d64_ms': e0.elapsed_time(e1) / 20}))
+print(json.dumps({'replay_variant': os.environ.get('EDRGP_JACOBI_REPLAY', '0'), 'jacobi_variant': os.environ.get('EDRGP_JACOBI_VARIANT', '0'), 'parity': 'ok', 'eigh_d64_ms': e0.elapsed_time(e1) / 20}))
