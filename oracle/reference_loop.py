@@ -94,3 +94,40 @@ def fit_reference_style(X, y, num_inducing=10, n_components=None, step=None, nor
     return {'components_': out_components, 'num_iter': num_iter, '_first_gradients_': first_gradients,
             'subspace_gradients_': subspace_gradients, 'subspace_variance_': var,
             'subspace_variance_ratio_': ratio, 'estimator_': est}
+
+
+class EconomySVDTransformer(object):
+    """Host transformer with the semantics of the reference's ``SVDTransformer`` (edrgp/utils.py:81-175:
+    uncentred PCA, ``components_ = Vh[:k]``, ``subspace_variance_ = S^2``, ratio ``S^2 / sum S^2``, k capped
+    by the number of rows) on the ECONOMY SVD -- same Vh and S, without the n x n ``U`` that makes the
+    reference's own class unusable beyond a few ten thousand rows.  TEST ORACLE: the GPU tests use it as "any
+    host transformer with fit + components_" where the reference copy is not needed."""
+
+    def __init__(self, n_components=None):
+        self.n_components = n_components
+
+    def get_params(self, deep=True):
+        return {'n_components': self.n_components}
+
+    def set_params(self, **params):
+        for k, v in params.items():
+            setattr(self, k, v)
+        return self
+
+    def fit(self, X, y=None):
+        X = np.array(X, dtype=np.float64)
+        _, S, Vh = np.linalg.svd(X, full_matrices=False)
+        ratio = S ** 2 / np.sum(S ** 2)
+        nc, k = self.n_components, X.shape[1]
+        if isinstance(nc, (int, np.integer)) and 0 < nc <= X.shape[1]:
+            k = int(nc)
+        elif isinstance(nc, float) and 0 < nc < 1:
+            k = int(np.sum(np.cumsum(ratio) < nc, dtype=int)) + 1
+        k = min(X.shape[0], k)
+        self.components_ = Vh[:k, :]
+        self.subspace_variance_ = (S ** 2)[:k]
+        self.subspace_variance_ratio_ = ratio[:k]
+        return self
+
+    def transform(self, X):
+        return np.asarray(X).dot(self.components_.T)

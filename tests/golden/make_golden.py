@@ -67,6 +67,25 @@ def main():
                    first_grad_variance=first.grad_variance, first_grad_noise=first.grad_noise,
                    first_pred_grad=first.predictive_gradients(Xs[:64])[0][:, :, 0],
                    first_pred_mean=first.predict(Xs[:64])[0][:, 0], first_pred_var=first.predict(Xs[:64])[1][:, 0])
+        # the public surface behind the fit (edrgp/base.py:202-239, edrgp/edr.py:115-140,199-289): refit on the
+        # kept first gradients (all rows, a row subset, a sparse transformer), gradients of the final
+        # estimator at new rows mapped back to the raw features, projection, feature importances
+        kk = 2 if c['k'] is None else c['k']
+        Xq = X[:40] + 0.01
+        out.update(get_estimator_gradients=edr.get_estimator_gradients(Xq), transform=edr.transform(Xq),
+                   feature_importances_=edr.feature_importances_)
+        edr.refit(SVDTransformer(n_components=kk))
+        out.update(refit_components_=edr.refit_components_, refit_subspace_variance_=edr.refit_subspace_variance_,
+                   refit_subspace_variance_ratio_=edr.refit_subspace_variance_ratio_,
+                   refit_transform=edr.transform(Xq, refitted=True))
+        rows = np.arange(0, c['n'], 3)
+        edr.refit(SVDTransformer(n_components=kk), rows)
+        out.update(refit_rows=rows, refit_rows_components_=edr.refit_components_,
+                   refit_rows_subspace_variance_ratio_=edr.refit_subspace_variance_ratio_)
+        from sklearn.decomposition import SparsePCA
+        edr.refit(SparsePCA(n_components=kk, alpha=0.5, random_state=0))
+        out.update(refit_sparse_components_=edr.refit_components_,
+                   refit_sparse_subspace_variance_ratio_=edr.refit_subspace_variance_ratio_)
         for k, v in c.items():
             out['cfg_' + k] = np.array(-1 if v is None else v)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)

@@ -207,3 +207,45 @@ def test_wide_inputs_feature_blocked(n, d, m):
     tr = eb.GramEighTransformer(n_components=2).fit_gram(C, n)
     cref, _, _ = op.edr_from_gram(G_ref.T.dot(G_ref), 2)
     assert op.principal_angle(tr.components_, cref) < 1e-6
+
+
+@pytest.mark.parametrize("n,d,m", [(8192, 512, 1024),     # BASELINE config 4 at its real d and m (Z = 4.2 MB, no SMEM fit)
+                                   (8192, 128, 2048),     # BASELINE config 5 at its real d and m
+                                   (10000, 32, 256)])     # BASELINE config 2 shape
+def test_baseline_configs_at_their_real_inducing_counts(n, d, m):
+    """C2 / C4 / C5 of BASELINE.json with the REAL feature and inducing-point counts (only n is reduced so
+    that the CPU oracle finishes in seconds): bound, training-row gradients from the stored Kfu blocks, their
+    Gram matrix, new-row gradients (recompute path), posterior mean and the EDR directions against the
+    oracle's row-chunked forms (oracle/pipeline.py; pinned against the faithful restatement in test_oracle)."""
+    from edrgp_b200 import model
+    import edrgp_b200 as eb
+    w = op.make_workload(n, d, m, seed=d + m, k_true=3)
+    w['y'] = 2.0 * w['y'] - 0.7
+    mean, std = w['y'].mean(), w['y'].std()
+    yn = (w['y'] - mean) / std
+    P, b, yy = op.inducing_stats_chunked(w['X'], yn, w['Z'], w['ell'], w['sf2'])
+    sol = op.solve_from_stats(op.kuu(w['Z'], w['ell'], w['sf2']), P, b, yy, n, w['sf2'], w['noise'])
+    G_ref = op.gradients_chunked(w['X'], w['Z'], w['ell'], w['sf2'], sol['alpha'], scale=std)
+    C_ref = G_ref.T.dot(G_ref)
+
+    mod = model.SparseGPRegression(w['X'], w['y'][:, None], kernel=model.RBF(d, w['sf2'], w['ell'], ARD=True), Z=w['Z'],
+                                   normalizer=True, noise_var=w['noise'], chunk_rows=4096)
+    Pd, byy = mod._stats
+    assert _relerr(Pd.cpu().numpy(), P) < 1e-11
+    assert _relerr(byy.cpu().numpy()[:m], b) < 1e-11
+    ll = float(mod.log_likelihood()[0, 0])
+    assert abs(ll - sol['bound']) < 1e-9 * abs(sol['bound'])
+    G, C = mod.gradient_gram(want_G=True, want_C=True)
+    assert _relerr(G.cpu().numpy(), G_ref) < 1e-8
+    assert _relerr(C.cpu().numpy(), C_ref) < 1e-8
+    Xnew = np.random.RandomState(3).standard_normal((300, d))
+    Gn_ref = op.gradients_chunked(Xnew, w['Z'], w['ell'], w['sf2'], sol['alpha'], scale=std)
+    assert _relerr(mod.predictive_gradients(Xnew)[0][:, :, 0], Gn_ref) < 1e-8
+    mu_ref = op.kuf_faithful(Xnew, w['Z'], w['ell'], w['sf2']).dot(sol['alpha']) * std + mean
+    assert _relerr(mod.predict(Xnew, want_variance=False)[0][:, 0], mu_ref) < 1e-8
+    # the workload's Gram matrix has ONE separated eigenvalue (the rest is a near-degenerate bulk, where a
+    # subspace of fixed size is not a well-posed target): leading direction, and the whole spectrum
+    tr = eb.GramEighTransformer().fit_gram(C, n)
+    cref, lam, _ = op.edr_from_gram(C_ref, None)
+    assert op.principal_angle(tr.components_[:1], cref[:1]) < 1e-6
+    assert np.allclose(tr.subspace_variance_, lam, rtol=1e-7, atol=1e-9 * lam[0])
