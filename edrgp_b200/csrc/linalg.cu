@@ -822,10 +822,10 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 //     h = sqrt(diff^2 + 4 gamma^2), cos 2t = |diff| / h,  c = sqrt((1 + cos 2t) / 2),
 //     s = sign(diff) gamma / (h c)            (|t| <= pi / 4, c^2 + s^2 = 1 to rounding)
 // evaluated on operands scaled by a power of two so that the FP32 seeds stay in range.
-// EDRGP_JACOBI_VARIANT (tuning aid, read once): 0 = default lanes / rows split, 1 = fewer lanes, 2 = a warp per pair,
-// 4 = two-sided solver (d <= 64), 5 = one-sided solver specialised for d = 64 (not yet validated on a GPU)
+// EDRGP_JACOBI_VARIANT (tuning aid, read once): unset = default (the d = 64 specialisation where it applies),
+// 0 = the general kernel everywhere, 1 = fewer lanes per pair, 2 = a warp per pair
 static int jacobi_variant() {
-  static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : 0; }();
+  static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : -1; }();
   return v;
 }
 
@@ -898,7 +898,7 @@ extern "C" int edrgp_debug_jac_prof(long long* out) { return (int)cudaMemcpyFrom
 // LOGV: V is NOT carried here.  Its update never feeds back into the rotations, yet it is half of the
 // shared-memory traffic and a fifth of the FP64 instructions of every step of this latency chain; the
 // kernel only records (c, s) of every pair and step (rotlog[(sweep (dd - 1) + step) np + slot]; (1, 0)
-// where nothing rotates) and the number of recorded sweeps (nlog), and jacobi_vectors_kernel replays the
+// where nothing rotates) and the number of recorded sweeps (nlog), and jacobi_vectors_lean_kernel replays the
 // log on the rows of V -- independent of one another -- across several SMs, then finishes (Rayleigh
 // quotients, order, signs).
 template <int L, int R, bool LOGV>
@@ -1034,13 +1034,13 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
 }
 
 #undef JAC_STAMP
-// The one-sided solver with recorded rotations, specialised for d = 64 (EDRGP_JACOBI_VARIANT=5): what bounds a
+// The one-sided solver with recorded rotations, specialised for d = 64: what bounds a
 // step is the NUMBER of instructions each warp issues (228 in the general kernel, of which ~75 are the pair
 // schedule, the `live` / row-bound predicates and address arithmetic: profiles/r01c_ncu_small_solvers.txt), so
 // here the schedule of a whole sweep is a 4 KB shared-memory table built once, every pair is live, every lane
 // owns exactly four rows and the log is written through a running pointer.  The arithmetic is the general
-// kernel's, operation for operation.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent):
-// validate with `EDRGP_JACOBI_VARIANT=5 python tools/check_replay_variant.py` before making it the default.
+// kernel's, operation for operation (0.55 -> 0.51 ms on the bench's spectrum, profiles/r02_jacobi_variants.txt);
+// the default for d = 64, EDRGP_JACOBI_VARIANT=0 selects the general kernel.
 __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restrict__ C, int max_sweeps,
                                                          int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
                                                          int* __restrict__ nlog) {
@@ -1124,209 +1124,18 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
   }
 }
 
-// Two-sided (classical) Jacobi for d <= 64 on the symmetric matrix itself, A <- J^T A J.  The rotation of a
-// pair comes from three ENTRIES (a_pp, a_qq, a_pq): no dot products and no lane reduction, which are 45 %
-// of the one-sided step (jac_profile tool: loads + dots + shuffles 860 of 1 940 cycles, parameters 580).  The
-// same parameter code applies (the two-sided condition c s (a_pp - a_qq) + (c^2 - s^2) a_pq = 0 is the
-// one-sided one with the Gram entries), the pairs of a step are disjoint, so all column rotations A J
-// run in parallel, then -- after a barrier -- all row rotations J^T (A J).  Rotations are only recorded
-// (rotlog, as in the LOGV mode above); jacobi_vectors_kernel replays them on V and finishes.  For a positive
-// semi-definite matrix |a_pq| <= sqrt(a_pp a_qq), so the relative rotation test of the one-sided solver
-// keeps its meaning; |a_pp a_qq| guards diagonal entries that rounding has pushed below zero.
-template <int L, int R>
-__global__ void __launch_bounds__(512) jacobi_twosided_kernel(const double* __restrict__ C, int d, int max_sweeps,
-                                                              int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
-                                                              int* __restrict__ nlog) {
-  extern __shared__ double sh[];
-  const int ds = d | 1;                       // odd stride: a column (fixed c) and a row (fixed r) are both conflict free
-  double* A = sh;                             // A[c * ds + r]
-  __shared__ int rotated;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int dd = d + (d & 1), np = dd / 2;
-  for (int i = tid; i < d * d; i += nt) {
-    const int c = i / d, r = i - c * d;
-    A[c * ds + r] = C[(int64_t)r * d + c];
-  }
-  __syncthreads();
-  // The parameters of a step's pairs are computed ONCE, by the first np threads (a thread per pair: one
-  // warp for d = 64), and published through shared memory: sixteen lanes per pair deriving the same (c, s)
-  // kept all sixteen warps issuing ~165 cycles of identical FP64 work per step.
-  __shared__ double2 cs[32];
-  __shared__ int rotf[32];
-  const int k = tid / L, l = tid % L;
-  const bool active = k < np;
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    if (tid == 0) rotated = 0;
-    __syncthreads();
-    for (int step = 0; step < dd - 1; ++step) {
-      if (tid < np) {                          // pair slot tid
-        int a0 = step + tid, b0 = step + dd - 1 - tid;
-        if (a0 >= dd - 1) a0 -= dd - 1;
-        if (b0 >= dd - 1) b0 -= dd - 1;
-        if (tid == 0) a0 = dd - 1;
-        const int p = min(a0, b0), q = max(a0, b0);
-        double c = 1.0, s = 0.0;
-        int rot = 0;
-        if (q < d) {
-          const double alpha = A[p * ds + p], beta = A[q * ds + q], gamma = A[p * ds + q];
-          const double ab = fabs(alpha * beta);
-          if (gamma * gamma > 1e-30 * ab && fabs(gamma) >= 1e-300) {
-            rot = 1;
-            const double sum = fabs(alpha) + fabs(beta);
-            const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
-            if (ex > 64 && ex < 1983) {
-              const double scale = __hiloint2double((2046 - ex) << 20, 0);
-              const double dn = (beta - alpha) * scale, gn = 2.0 * gamma * scale;
-              const double ih = fast_rsqrt(fma(dn, dn, gn * gn));
-              const double x = fma(0.5 * fabs(dn), ih, 0.5);
-              const double r = fast_rsqrt(x);
-              c = x * r;
-              s = (dn >= 0.0 ? 0.5 : -0.5) * gn * ih * r;
-            } else {
-              const double zeta = (beta - alpha) / (2.0 * gamma);
-              const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-              c = 1.0 / sqrt(fma(tt, tt, 1.0)); s = tt * c;
-            }
-            if (gamma * gamma > 1e-18 * ab) rotated = 1;
-          }
-        }
-        cs[tid] = make_double2(c, s);
-        rotf[tid] = rot;
-        rotlog[((size_t)sweep * (dd - 1) + step) * np + tid] = make_double2(c, s);
-      }
-      int p = 0, q = d;
-      if (active) {
-        int a0 = step + k, b0 = step + dd - 1 - k;
-        if (a0 >= dd - 1) a0 -= dd - 1;
-        if (b0 >= dd - 1) b0 -= dd - 1;
-        if (k == 0) a0 = dd - 1;
-        p = min(a0, b0); q = max(a0, b0);
-      }
-      const bool live = active && q < d;
-      const int qq = live ? q : p;
-      double xa[R], xb[R];
-#pragma unroll
-      for (int e = 0; e < R; ++e) {
-        const bool ok = live && l + L * e < d;
-        xa[e] = ok ? A[p * ds + l + L * e] : 0.0;
-        xb[e] = ok ? A[qq * ds + l + L * e] : 0.0;
-      }
-      __syncthreads();
-      const bool rot = live && rotf[k] != 0;
-      const double2 csk = active ? cs[k] : make_double2(1.0, 0.0);
-      const double c = csk.x, s = csk.y;
-      if (rot) {
-#pragma unroll
-        for (int e = 0; e < R; ++e) {
-          if (l + L * e < d) {
-            A[p * ds + l + L * e] = c * xa[e] - s * xb[e];
-            A[q * ds + l + L * e] = s * xa[e] + c * xb[e];
-          }
-        }
-      }
-      __syncthreads();
-      if (rot) {
-#pragma unroll
-        for (int e = 0; e < R; ++e) {
-          const int j = l + L * e;
-          if (j < d) {
-            const double ya = A[j * ds + p], yb = A[j * ds + q];
-            A[j * ds + p] = c * ya - s * yb;
-            A[j * ds + q] = s * ya + c * yb;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (!rotated) { ++sweep; break; }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    if (sweeps_out) *sweeps_out = sweep;
-    nlog[0] = sweep; nlog[1] = 0;
-  }
-}
-
-// Replays the rotation log of jacobi_onesided_kernel<.., true> on V = I.  A warp per ROW of V (rows never
-// mix), lane = pair slot of the round-robin schedule holding that row's entries in the slot's two columns;
-// between steps the columns move one slot along the tournament ring (two shuffles).  The log is fetched
-// sixteen steps ahead.  The last CTA to finish (ticket) computes the eigenvalues and writes the output.
-// d <= 64 (at most 32 slots).
+// Replays the rotation log of the solver on V = I.  A warp per ROW of V (rows never mix), lane = pair slot
+// of the round-robin schedule holding that row's entries in the slot's two columns; between steps the columns
+// move one slot along the tournament ring (two shuffles).  The last CTA to finish (ticket) computes the
+// eigenvalues and writes the output.  d <= 64 (at most 32 slots).
+// Per-step overhead is what this kernel is made of (4 FP64 operations, 4 shuffles and 1 load per step), so the
+// orientation of a slot at every step of a sweep is a 63-bit mask computed once, the log is read through a
+// running pointer sixteen steps ahead without bounds tests (the workspace carries 32 steps of slack) and only the
+// tail batch is guarded: 26 instructions per step and warp (the first version, with the schedule recomputed
+// and every access guarded, executed 64: profiles/r01c_ncu_small_solvers.txt; 0.11 -> 0.08 ms at d = 64,
+// profiles/r02_jacobi_variants.txt).  Index logic emulated lane by lane on the CPU in tests/test_replay_logic.py.
 constexpr int JV_WARPS = 8;
 constexpr int JV_AHEAD = 16;
-__global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_kernel(
-    const double* __restrict__ C, int d, const double2* __restrict__ rotlog, int* ctrl, double* Vt,
-    double* __restrict__ evals, double* __restrict__ comps) {
-  __shared__ double lam[64];
-  __shared__ int last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int dd = d + (d & 1), np = dd / 2;
-  const int row = blockIdx.x * JV_WARPS + warp;
-  const int nsteps = ctrl[0] * (dd - 1);
-  if (row < d) {
-    const bool act = lane < np;
-    int step = 0;
-    double va, vb;
-    {
-      const int a0 = lane == 0 ? dd - 1 : lane, b0 = lane == 0 ? 0 : dd - 1 - lane;
-      va = (act && a0 == row) ? 1.0 : 0.0;
-      vb = (act && b0 == row) ? 1.0 : 0.0;
-    }
-    const double2 ident = make_double2(1.0, 0.0);
-    const double2* lp = rotlog + lane;
-    double2 cur[JV_AHEAD], nxt[JV_AHEAD];
-#pragma unroll
-    for (int i = 0; i < JV_AHEAD; ++i) cur[i] = (act && i < nsteps) ? lp[(size_t)i * np] : ident;
-    for (int g0 = 0; g0 < nsteps; g0 += JV_AHEAD) {
-#pragma unroll
-      for (int i = 0; i < JV_AHEAD; ++i) {
-        const int g = g0 + JV_AHEAD + i;
-        nxt[i] = (act && g < nsteps) ? lp[(size_t)g * np] : ident;
-      }
-#pragma unroll
-      for (int i = 0; i < JV_AHEAD; ++i) {
-        if (g0 + i < nsteps) {                      // uniform across the warp
-          int a0 = step + lane, b0 = step + dd - 1 - lane;
-          if (a0 >= dd - 1) a0 -= dd - 1;
-          if (b0 >= dd - 1) b0 -= dd - 1;
-          if (lane == 0) a0 = dd - 1;
-          const double c = cur[i].x, sg = a0 < b0 ? cur[i].y : -cur[i].y;
-          const double na = c * va - sg * vb, nb = sg * va + c * vb;
-          const double dn = __shfl_down_sync(0xffffffffu, na, 1), up = __shfl_up_sync(0xffffffffu, nb, 1);
-          if (np > 1) {
-            va = lane == 0 ? na : (lane == np - 1 ? nb : dn);
-            vb = lane == 0 ? dn : up;
-          } else {
-            va = na; vb = nb;
-          }
-          if (++step == dd - 1) step = 0;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < JV_AHEAD; ++i) cur[i] = nxt[i];
-    }
-    if (act) {                                      // step == 0 again: the slots hold their initial columns
-      const int a0 = lane == 0 ? dd - 1 : lane, b0 = lane == 0 ? 0 : dd - 1 - lane;
-      if (a0 < d) Vt[(size_t)a0 * d + row] = va;
-      if (b0 < d) Vt[(size_t)b0 * d + row] = vb;
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(ctrl + 1), 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  jacobi_finish(C, d, Vt, d, lam, evals, comps, tid, JV_WARPS * 32);
-}
-
-// The same replay with the per-step overhead taken out (the kernel above executes 64 instructions per step
-// and warp of which 4 are FP64, 4 shuffles and 1 a load: profiles/r01c_ncu_small_solvers.txt): the
-// orientation of a slot at every step of a sweep is a 63-bit mask computed once, the log is read through a
-// running pointer sixteen steps ahead without bounds tests (the workspace carries 32 steps of slack), only
-// the tail batch is guarded.  Selected with EDRGP_JACOBI_REPLAY=1.  NOT YET RUN ON A GPU: written after the
-// round's GPU budget was spent; validate with `pytest tests/test_linalg_gpu.py -k eigh` before making it the default.
 __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
     const double* __restrict__ C, int d, const double2* __restrict__ rotlog, int* ctrl, double* Vt,
     double* __restrict__ evals, double* __restrict__ comps) {
@@ -1400,11 +1209,6 @@ __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
   jacobi_finish(C, d, Vt, d, lam, evals, comps, tid, JV_WARPS * 32);
 }
 
-static int jacobi_replay_variant() {
-  static const int v = [] { const char* e = getenv("EDRGP_JACOBI_REPLAY"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 static size_t jacobi_log_doubles(int d) {      // 60 sweeps + 32 steps of slack (read ahead, never used)
   const int dd = d + (d & 1);
   return ((size_t)60 * (dd - 1) + 2 * JV_AHEAD) * (dd / 2) * 2;
@@ -1422,22 +1226,14 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     double* Vt = ws + jacobi_log_doubles(d);
     int* ctrl = reinterpret_cast<int*>(Vt + (size_t)d * d);          // [0] sweeps logged, [1] ticket
     const size_t smem = (size_t)d * ds * sizeof(double);
-    // EDRGP_JACOBI_VARIANT=4: the two-sided solver (tuning aid).  Same time per step as the one-sided one
-    // (0.58 vs 0.56 ms at d = 64 on a spectrum with a few dominant directions, 8 sweeps each), fewer sweeps on
-    // flat spectra (9 vs 14: 0.65 vs 0.89 ms); the one-sided solver stays the default because its relative
-    // rotation test also terminates on numerically rank-deficient matrices, where the entries the two-sided
-    // test looks at are rounding noise.
-    if (jacobi_variant() == 5 && d == 64)
+    // (a two-sided solver on the matrix itself was tried here: same time per step, fewer sweeps on flat spectra,
+    // but its absolute rotation test does not terminate cleanly on numerically rank-deficient matrices)
+    if (jacobi_variant() < 0 && d == 64)
       jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl);
-    else if (jacobi_variant() == 4)
-      jacobi_twosided_kernel<(L > 16 ? 16 : L), (L > 16 ? 2 * R : R)><<<1, min(threads, 512), smem, st>>>(C, d, 60, sweeps, rotlog, ctrl);
     else
       jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
     count_launch();
-    if (jacobi_replay_variant() == 1)
-      jacobi_vectors_lean_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
-    else
-      jacobi_vectors_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
+    jacobi_vectors_lean_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
     count_launch();
     return cudaGetLastError();
   }

@@ -74,8 +74,8 @@ struct Smem {
   static constexpr size_t z_off = x_off + (size_t)XS * BM * S * 8;
   static constexpr size_t il2_off = z_off + (size_t)NS * TILE * 8;
   static constexpr size_t hx_off = il2_off + (size_t)DP * 8;
-  static constexpr size_t tab_off = hx_off + (size_t)BM * 8;             // exp table, 64 doubles
-  static constexpr size_t bar_off = tab_off + 64 * 8;
+  static constexpr size_t tab_off = hx_off + (size_t)BM * 8;             // exp table, replicated per half-warp lane
+  static constexpr size_t bar_off = tab_off + (size_t)EXP_TABLE_DOUBLES * 8;
   static constexpr size_t bytes = bar_off + (size_t)(2 * XS + 2 * NS) * 8;
 };
 
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
   double* zbuf = reinterpret_cast<double*>(smem_raw + L::z_off);
   double* il2s = reinterpret_cast<double*>(smem_raw + L::il2_off);
   double* hxs = reinterpret_cast<double*>(smem_raw + L::hx_off);
-  double* etab = reinterpret_cast<double*>(smem_raw + L::tab_off);
+  double* etab_base = reinterpret_cast<double*>(smem_raw + L::tab_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::bar_off);
   uint64_t* xfull = bars;
   uint64_t* xempty = bars + XS;
@@ -274,13 +274,14 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) grad_gram_kernel(const Pi
   uint64_t* zempty = bars + 2 * XS + NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* etab = etab_base + (lane & 15);       // this lane's copy of the exp table: its own bank pair
   if (tid == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], WARPS); }
     for (int i = 0; i < NS; ++i) { mbar_init(&zfull[i], 1); mbar_init(&zempty[i], WARPS); }
     mbar_fence_init();
   }
   for (int i = tid; i < DP; i += blockDim.x) il2s[i] = p.pack[i];
-  exp_table_init(etab, tid);
+  exp_table_init(etab_base, tid, blockDim.x);
   // padding columns of the X buffers must be finite zeros (bulk copies fill only d columns)
   for (int i = tid; i < XS * BM * S; i += blockDim.x) xbuf[i] = 0.0;
   fence_proxy_async();
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
   double* zbuf = reinterpret_cast<double*>(smem_raw + L::z_off);
   double* il2s = reinterpret_cast<double*>(smem_raw + L::il2_off);
   double* hxs = reinterpret_cast<double*>(smem_raw + L::hx_off);
-  double* etab = reinterpret_cast<double*>(smem_raw + L::tab_off);
+  double* etab_base = reinterpret_cast<double*>(smem_raw + L::tab_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::bar_off);
   uint64_t* xfull = bars;
   uint64_t* xempty = bars + XS;
@@ -500,13 +501,14 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
   uint64_t* zempty = bars + 2 * XS + NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* etab = etab_base + (lane & 15);       // this lane's copy of the exp table: its own bank pair
   if (tid == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], WARPS); }
     for (int i = 0; i < NS; ++i) { mbar_init(&zfull[i], 1); mbar_init(&zempty[i], WARPS); }
     mbar_fence_init();
   }
   for (int i = tid; i < DP; i += blockDim.x) il2s[i] = p.pack[i];
-  exp_table_init(etab, tid);
+  exp_table_init(etab_base, tid, blockDim.x, p.sf2);   // sf2 folded into the table
   for (int i = tid; i < XS * BM * S; i += blockDim.x) xbuf[i] = 0.0;
   fence_proxy_async();
   __syncthreads();
@@ -541,8 +543,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         double2 o0, o1;
-        o0.x = p.sf2 * exp_neg(fmin(sc[0][nb][0], 0.0), etab); o0.y = p.sf2 * exp_neg(fmin(sc[0][nb][1], 0.0), etab);
-        o1.x = p.sf2 * exp_neg(fmin(sc[1][nb][0], 0.0), etab); o1.y = p.sf2 * exp_neg(fmin(sc[1][nb][1], 0.0), etab);
+        o0.x = exp_clip_scaled(sc[0][nb][0], etab); o0.y = exp_clip_scaled(sc[0][nb][1], etab);
+        o1.x = exp_clip_scaled(sc[1][nb][0], etab); o1.y = exp_clip_scaled(sc[1][nb][1], etab);
         mu0 += fma(o0.x, c.x, o0.y * c.y); mu1 += fma(o1.x, c.x, o1.y * c.y);
         // ldk is even, so a pair starting at an even j < m is in bounds (a column == m is padding)
         if (v0 && j < p.m) *reinterpret_cast<double2*>(k0p + mt * MT + 8 * nb) = o0;
@@ -603,8 +605,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
           const double2 h = *reinterpret_cast<const double2*>(zt + MT * S + 8 * nb + 2 * t);
           k00 = s[0][nb][0] - h.x; k01 = s[0][nb][1] - h.y; k10 = s[1][nb][0] - h.x; k11 = s[1][nb][1] - h.y;
         } else {
-          k00 = p.sf2 * exp_neg(fmin(s[0][nb][0], 0.0), etab); k01 = p.sf2 * exp_neg(fmin(s[0][nb][1], 0.0), etab);
-          k10 = p.sf2 * exp_neg(fmin(s[1][nb][0], 0.0), etab); k11 = p.sf2 * exp_neg(fmin(s[1][nb][1], 0.0), etab);
+          k00 = exp_clip_scaled(s[0][nb][0], etab); k01 = exp_clip_scaled(s[0][nb][1], etab);
+          k10 = exp_clip_scaled(s[1][nb][0], etab); k11 = exp_clip_scaled(s[1][nb][1], etab);
         }
         if (p.mul && j < p.m) {
           // feature-chunked evaluation: exp(-r^2/2) factorises over blocks of features

@@ -148,8 +148,9 @@ def test_posv_reports_indefinite():
     assert int(info.cpu()[0]) == 41
 
 
-def test_eigh_twosided_variant_matches_lapack():
-    """EDRGP_JACOBI_VARIANT=4 (two-sided solver, read once per process: run in a child process)."""
+def test_eigh_general_kernel_matches_lapack():
+    """EDRGP_JACOBI_VARIANT=0 selects the general one-sided kernel also at d = 64, where the default is the
+    specialised jacobi_d64_kernel (the switch is read once per process: run in a child process)."""
     import os, subprocess, sys
     code = (
         "import numpy as np, torch\n"
@@ -165,10 +166,39 @@ def test_eigh_twosided_variant_matches_lapack():
         "    assert np.max(np.abs(cp.dot(cp.T) - np.eye(d))) < 1e-12\n"
         "    assert np.max(np.abs(cp.dot(C).dot(cp.T) - np.diag(ev))) < 1e-11 * lam[0]\n"
         "print('ok')\n")
-    env = dict(os.environ, EDRGP_JACOBI_VARIANT='4')
+    env = dict(os.environ, EDRGP_JACOBI_VARIANT='0')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["flat", "rank_deficient", "one_dominant", "tiny_scale", "zero"])
+def test_eigh_d64_spectra(kind):
+    """The default d = 64 path (specialised solver + lean rotation replay) on spectra that stress the sweep count
+    and the relative rotation test: flat (clustered), rank 5 of 64, one dominant direction, entries ~1e-200, zero."""
+    from edrgp_b200 import ops
+    d = 64
+    rng = np.random.RandomState(7)
+    if kind == "flat":
+        G = rng.standard_normal((50000, d))
+    elif kind == "rank_deficient":
+        G = rng.standard_normal((400, 5)).dot(rng.standard_normal((5, d)))
+    elif kind == "one_dominant":
+        G = 0.01 * rng.standard_normal((20000, d)); G[:, 0] += rng.standard_normal(20000)
+    elif kind == "tiny_scale":
+        G = 1e-100 * rng.standard_normal((500, d)) * np.linspace(3.0, 0.1, d)
+    else:
+        G = np.zeros((10, d))
+    C = G.T.dot(G)
+    evals, comps = ops.eigh(_dev(C))
+    evals, comps = evals.cpu().numpy(), comps.cpu().numpy()
+    lam = np.linalg.eigvalsh(C)[::-1]
+    scale = max(lam[0], 1e-300)
+    assert np.all(np.isfinite(evals)) and np.all(np.isfinite(comps))
+    assert np.max(np.abs(evals - lam)) <= 1e-12 * scale
+    assert np.max(np.abs(comps.dot(comps.T) - np.eye(d))) < 1e-12
+    assert np.max(np.abs(comps.dot(C).dot(comps.T) - np.diag(evals))) <= 1e-11 * scale
+    assert np.all(np.diff(evals) <= 1e-12 * scale)                       # descending
 
 
 def test_potrf_reports_indefinite():

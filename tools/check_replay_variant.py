@@ -1,9 +1,7 @@
-"""Validation of the lean rotation-replay kernel (EDRGP_JACOBI_REPLAY=1; written at the end of round 1 after the GPU
-budget was spent, so it is OFF by default and has not run on a GPU yet).
+"""Parity vs LAPACK and timing of the d <= 64 eigensolver (solver + rotation replay), per solver variant:
 
-    EDRGP_JACOBI_REPLAY=1 python tools/check_replay_variant.py     # parity vs LAPACK + timing
-    python tools/check_replay_variant.py                           # the default replay kernel, for comparison
-    EDRGP_JACOBI_VARIANT=5 python tools/check_replay_variant.py    # the d = 64 specialised solver (also unvalidated)
+    python tools/check_replay_variant.py                           # default: jacobi_d64_kernel at d = 64 + lean replay
+    EDRGP_JACOBI_VARIANT=0 python tools/check_replay_variant.py    # the general one-sided kernel at d = 64 too
 """
 import json, os, sys
 import numpy as np, torch
@@ -31,4 +29,4 @@ e0.record()
 for _ in range(20):
     ops.eigh(C)
 e1.record(); e1.synchronize()
-print(json.dumps({'replay_variant': os.environ.get('EDRGP_JACOBI_REPLAY', '0'), 'jacobi_variant': os.environ.get('EDRGP_JACOBI_VARIANT', '0'), 'parity': 'ok', 'eigh_d64_ms': e0.elapsed_time(e1) / 20}))
+print(json.dumps({'jacobi_variant': os.environ.get('EDRGP_JACOBI_VARIANT', 'default'), 'parity': 'ok', 'eigh_d64_ms': e0.elapsed_time(e1) / 20}))
