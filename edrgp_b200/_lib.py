@@ -22,8 +22,8 @@ SIGNATURES = {
     'edrgp_launch_count': (ctypes.c_uint64, []),
     'edrgp_fp64_probe': (_int, [_c_dp, _int, ctypes.POINTER(ctypes.c_double), _c_dp]),
     'edrgp_pack_bytes': (_sz, [_int, _int]),
-    'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _int, _int, _c_dp, _c_dp]),
-    'edrgp_kuf': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_pack_inducing': (_int, [_c_dp, _c_dp, _c_dp, _dbl, _c_dp, _int, _int, _c_dp, _c_dp]),
+    'edrgp_kuf': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_pack_tf32_bytes': (_sz, [_int, _int]),
     'edrgp_pack_inducing_tf32': (_int, [_c_dp, _c_dp, _int, _int, _c_dp, _c_dp]),
     'edrgp_kuf_tf32x3': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp]),
@@ -59,6 +59,16 @@ SIGNATURES = {
     'edrgp_standardize': (_int, [_c_dp, _i64, _int, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_project_dmma': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _c_dp, _i64, _c_dp]),
     'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
+    'edrgp_fixed_layout': (_sz, [_i64, _int, _int, _i64, _int, ctypes.POINTER(ctypes.c_int64)]),
+    'edrgp_fixed_begin': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _c_dp, _i64, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int,
+                                 _int, _c_dp, _c_dp]),
+    'edrgp_fixed_stats': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int, _int, _c_dp, _c_dp]),
+    'edrgp_fixed_posterior': (_int, [_c_dp, _i64, _i64, _int, _int, _dbl, _dbl, _dbl, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_fixed_grad': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _c_dp, _i64, _c_dp, _int, _dbl, _dbl, _c_dp, _c_dp,
+                                _i64, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_fixed_eigh': (_int, [_i64, _int, _int, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_timing_begin': (_int, []),
+    'edrgp_timing_end': (_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
 }
 
 

@@ -2,9 +2,12 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 #include "../../include/edrgp_b200.h"
 #include "common.cuh"
 #include "launch.h"
+#include "sweep.h"
 
 namespace edrgp {
 static std::atomic<uint64_t> g_launches{0};
@@ -31,6 +34,39 @@ int sm_count_cached() {
   return sms;
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- optional per-stage CUDA-event timing of the composite calls (edrgp_timing_begin / _end): the benchmark's
+// roofline needs the duration of individual kernels that one composite call launches back to back
+struct StageTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;            // reused across sessions
+  size_t used = 0;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; pool.push_back(e); }
+    return pool[used++];
+  }
+};
+StageTimer g_timer;
+std::mutex g_timer_mu;
+struct StageScope {                         // records an event pair around the launches of one stage
+  cudaStream_t st; int idx = -1;
+  StageScope(int stage, cudaStream_t s) : st(s) {
+    if (!g_timer.on) return;
+    std::lock_guard<std::mutex> lk(g_timer_mu);
+    cudaEvent_t a = g_timer.get(), b = g_timer.get();
+    if (!a || !b) return;
+    cudaEventRecord(a, st);
+    idx = (int)g_timer.spans.size();
+    g_timer.spans.push_back({stage, a, b});
+  }
+  ~StageScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_timer_mu);
+    cudaEventRecord(g_timer.spans[idx].b, st);
+  }
+};
 }  // namespace
 
 extern "C" {
@@ -55,11 +91,11 @@ size_t edrgp_pack_bytes(int m, int d) {
   return ((size_t)dp + mtiles * edrgp::pack_tile_doubles(dp)) * sizeof(double);
 }
 
-int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
-                        double* pack, void* stream) {
+int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, double coef_scale,
+                        const double* dev_scale, int m, int d, double* pack, void* stream) {
   if (!Z || !ell || !pack || m <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "pack_inducing: bad argument");
   if (!aligned16(pack)) return fail(EDRGP_ERR_ARG, "pack_inducing: pack must be 16-byte aligned");
-  cudaError_t e = edrgp::launch_pack(Z, ell, coef, coef_scale, m, d, pack, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_pack(Z, ell, coef, coef_scale, m, d, pack, (cudaStream_t)stream, dev_scale);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "pack_inducing");
 }
 
@@ -72,7 +108,8 @@ static int check_x(const char* who, const double* X, int64_t n, int d, const dou
 }
 
 int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2, double* Kfu,
-              int64_t ldk, int multiply, const double* y, double* b, double* mu, void* stream) {
+              int64_t ldk, int multiply, const double* y, double* b, double* mu, unsigned int* nonfinite_flag,
+              void* stream) {
   int rc = check_x("kuf", X, n, d, pack, m);
   if (rc) return rc;
   if (ldx < d || (ldx & 1)) return fail(EDRGP_ERR_ARG, "kuf: ldx must be even and >= d");
@@ -81,7 +118,9 @@ int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack
   if ((y == nullptr) != (b == nullptr)) return fail(EDRGP_ERR_ARG, "kuf: y and b go together");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "kuf: no CUDA device");
-  cudaError_t e = edrgp::launch_kuf(X, ldx, n, d, pack, m, sf2, Kfu, ldk, multiply, y, b, mu, sms, (cudaStream_t)stream);
+  if (!(sf2 > 0.0) || !(sf2 < 1e300)) return fail(EDRGP_ERR_ARG, "kuf: the kernel variance must be positive and finite");
+  cudaError_t e = edrgp::launch_kuf(X, ldx, n, d, pack, m, sf2, Kfu, ldk, multiply, y, b, mu, sms, (cudaStream_t)stream,
+                                    0, nonfinite_flag);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "kuf");
 }
 
@@ -389,6 +428,187 @@ int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, dou
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "project: no CUDA device");
   cudaError_t e = edrgp::launch_project(X, n, d, V, k, out, sms, (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "project");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fixed-hyper-parameter sweep composites (sweep.cu): everything between two collectives in one call
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct FixedCtx {
+  int64_t off[edrgp::FS_NREGIONS];
+  int sms;
+  double* ws;
+  double* at(int region) const { return ws + off[region]; }
+  unsigned int* flag() const { return reinterpret_cast<unsigned int*>(at(edrgp::FS_TAIL)); }
+  int* info() const { return reinterpret_cast<int*>(at(edrgp::FS_TAIL)) + 1; }
+};
+int fixed_ctx(const char* who, int64_t n, int d, int m, int64_t chunk_rows, int world, void* ws, FixedCtx* c) {
+  if (n <= 0 || d <= 0 || m <= 0 || chunk_rows <= 0 || world <= 0 || !ws) return fail(EDRGP_ERR_ARG, "%s: bad argument", who);
+  if ((d & 1) || d > 64) return fail(EDRGP_ERR_UNSUPPORTED, "%s: the composite sweep covers even d <= 64 (got %d)", who, d);
+  if (chunk_rows & 1) return fail(EDRGP_ERR_ARG, "%s: chunk_rows must be even", who);
+  if (!aligned16(ws)) return fail(EDRGP_ERR_ARG, "%s: the workspace must be 16-byte aligned", who);
+  c->sms = sm_count_cached();
+  if (c->sms <= 0) return fail(EDRGP_ERR_CUDA, "%s: no CUDA device", who);
+  edrgp::fixed_layout(n, d, m, chunk_rows, world, c->sms, c->off);
+  c->ws = (double*)ws;
+  return EDRGP_OK;
+}
+}  // namespace
+
+size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int64_t* offsets) {
+  int sms = sm_count_cached();
+  if (sms <= 0) sms = 160;
+  if (n <= 0 || d <= 0 || m <= 0 || chunk_rows <= 0 || world <= 0 || !offsets) return 0;
+  return edrgp::fixed_layout(n, d, m, chunk_rows, world, sms, offsets) * sizeof(double);
+}
+
+int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
+                      const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
+                      int world, void* workspace, void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_begin", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  if (!X || !y || !Z || !ell || !Kfu || ldx < d || (ldx & 1) || ldz != d || ldk < m || (ldk & 1) || rank < 0 || rank >= world)
+    return fail(EDRGP_ERR_ARG, "fixed_begin: bad argument");
+  if (!aligned16(X) || !aligned16(Kfu) || !aligned16(y)) return fail(EDRGP_ERR_ARG, "fixed_begin: X, y and Kfu must be 16-byte aligned");
+  if (!(sf2 > 0.0) || !(sf2 < 1e300)) return fail(EDRGP_ERR_ARG, "fixed_begin: the kernel variance must be positive and finite");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  double* scratch = c.at(edrgp::FS_SCRATCH);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 4 * c.sms);
+  // only the flag / info word: N, mean and std of an earlier normalisation stay valid when this call runs with
+  // targets that are already normalised
+  if ((e = cudaMemsetAsync(c.at(edrgp::FS_TAIL), 0, sizeof(double), st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
+  if ((e = cudaMemsetAsync(c.at(edrgp::FS_TABLE), 0, (size_t)4 * world * sizeof(double), st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
+  if ((e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
+  if ((e = edrgp::launch_pack(Z, ell, nullptr, 1.0, m, d, c.at(edrgp::FS_PACK_K), st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
+  const int64_t rows = chunk_rows < n ? chunk_rows : n;
+  // the first cross-covariance block does not need the targets: it goes first, so that the device is busy while
+  // the host walks through the rest of this call and (multi-rank) the gather of the moments table
+  {
+    StageScope t(EDRGP_STAGE_KUF, st);
+    if ((e = edrgp::launch_kuf(X, ldx, rows, d, c.at(edrgp::FS_PACK_K), m, sf2, Kfu, ldk, 0, nullptr, nullptr, nullptr, c.sms,
+                               st, 0, c.flag())) != cudaSuccess) return cuda_fail(e, "fixed_begin");
+  }
+  StageScope t(EDRGP_STAGE_TARGETS, st);
+  if ((e = edrgp::launch_target_moments(y, n, scratch, ticket, c.at(edrgp::FS_TABLE) + 4 * rank, c.sms, st)) != cudaSuccess)
+    return cuda_fail(e, "fixed_begin");
+  return EDRGP_OK;
+}
+
+int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const double* y, int m, double sf2,
+                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* workspace,
+                      void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_stats", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  if (!X || !y || !Kfu || ldx < d || (ldx & 1) || ldk < m || (ldk & 1)) return fail(EDRGP_ERR_ARG, "fixed_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  double* yt = c.at(edrgp::FS_YT);
+  {
+    StageScope t(EDRGP_STAGE_TARGETS, st);
+    e = edrgp::launch_target_standardize(c.at(edrgp::FS_TABLE), world, y, n, yt, c.at(edrgp::FS_TAIL) + 1, normalize, c.flag(),
+                                            c.sms, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "fixed_stats");
+  const double* targets = normalize ? yt : y;
+  double* P = c.at(edrgp::FS_STATS);
+  double* byy = P + (size_t)m * m;
+  for (int64_t s = 0; s < n; s += chunk_rows) {
+    const int64_t rows = n - s < chunk_rows ? n - s : chunk_rows;
+    double* Kc = Kfu + s * ldk;
+    if (s > 0) {
+      StageScope t(EDRGP_STAGE_KUF, st);
+      if ((e = edrgp::launch_kuf(X + s * ldx, ldx, rows, d, c.at(edrgp::FS_PACK_K), m, sf2, Kc, ldk, 0, nullptr, nullptr,
+                                 nullptr, c.sms, st, 0, c.flag())) != cudaSuccess) return cuda_fail(e, "fixed_stats");
+    }
+    StageScope t(EDRGP_STAGE_STATS, st);
+    if ((e = edrgp::launch_gemm_tn(Kc, ldk, m, nullptr, 0, 0, rows, 1, targets + s, P, m, byy, s > 0,
+                                   c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) return cuda_fail(e, "fixed_stats");
+  }
+  return EDRGP_OK;
+}
+
+int edrgp_fixed_posterior(const double* Z, int64_t ldz, int64_t n, int d, int m, double sf2, double jitter, double beta,
+                          int64_t chunk_rows, int world, void* workspace, void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_posterior", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  if (!Z || ldz != d || !(beta > 0.0)) return fail(EDRGP_ERR_ARG, "fixed_posterior: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  const int64_t lds = m + (m & 1);
+  StageScope t(EDRGP_STAGE_SOLVE, st);
+  double* S = c.at(edrgp::FS_S);
+  const double* P = c.at(edrgp::FS_STATS);
+  if ((e = edrgp::launch_kuf(Z, ldz, m, d, c.at(edrgp::FS_PACK_K), m, sf2, S, lds, 0, nullptr, nullptr, nullptr, c.sms, st)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_posterior");
+  if ((e = edrgp::launch_form_system(S, m, lds, sf2, jitter, beta, P, m, P + (size_t)m * m, c.at(edrgp::FS_RHS), st)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_posterior");
+  if ((e = edrgp::launch_posv(S, m, lds, c.at(edrgp::FS_L), m, c.at(edrgp::FS_RHS), c.at(edrgp::FS_ALPHA), c.info(), st)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_posterior");
+  return EDRGP_OK;
+}
+
+int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, const double* Z,
+                     int64_t ldz, const double* ell, int m, double sf2, double coef_scale, const double* dev_scale,
+                     double* G, int64_t ldg, int64_t chunk_rows, int world, void* workspace, void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_grad", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  if (!X || !Kfu || !Z || !ell || ldx < d || (ldx & 1) || ldz != d || ldk < m || (ldk & 1) || (G && (ldg < d || (ldg & 1))))
+    return fail(EDRGP_ERR_ARG, "fixed_grad: bad argument");
+  if (!aligned16(X) || !aligned16(Kfu) || (G && !aligned16(G))) return fail(EDRGP_ERR_ARG, "fixed_grad: X, Kfu and G must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  double* res = c.at(edrgp::FS_RESULT);
+  double* C = res + d + (size_t)d * d;
+  StageScope t(EDRGP_STAGE_GRAD, st);
+  if ((e = edrgp::launch_pack(Z, ell, c.at(edrgp::FS_ALPHA), coef_scale, m, d, c.at(edrgp::FS_PACK_G), st, dev_scale)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_grad");
+  if ((e = edrgp::launch_grad_gram_cached(X, ldx, n, d, Kfu, ldk, sf2, c.at(edrgp::FS_PACK_G), m, G, ldg, C,
+                                          c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) return cuda_fail(e, "fixed_grad");
+  if ((e = cudaMemcpyAsync(C + (size_t)d * d, c.at(edrgp::FS_TAIL), 4 * sizeof(double), cudaMemcpyDeviceToDevice, st)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_grad");
+  return EDRGP_OK;
+}
+
+int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_eigh", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  double* res = c.at(edrgp::FS_RESULT);
+  StageScope t(EDRGP_STAGE_EIGH, (cudaStream_t)stream);
+  cudaError_t e = edrgp::launch_eigh(res + d + (size_t)d * d, d, c.at(edrgp::FS_SCRATCH), res, res + d, nullptr,
+                                     (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "fixed_eigh");
+}
+
+int edrgp_timing_begin(void) {
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  g_timer.spans.clear();
+  g_timer.used = 0;
+  g_timer.on = true;
+  return EDRGP_OK;
+}
+
+int edrgp_timing_end(double* ms, int* count) {
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  g_timer.on = false;
+  for (int i = 0; i < EDRGP_STAGE_COUNT; ++i) { if (ms) ms[i] = 0.0; if (count) count[i] = 0; }
+  for (const auto& sp : g_timer.spans) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    if (e != cudaSuccess) return cuda_fail(e, "timing_end");
+    float t = 0.f;
+    if ((e = cudaEventElapsedTime(&t, sp.a, sp.b)) != cudaSuccess) return cuda_fail(e, "timing_end");
+    if (ms) ms[sp.stage] += (double)t;
+    if (count) count[sp.stage] += 1;
+  }
+  g_timer.spans.clear();
+  g_timer.used = 0;
+  return EDRGP_OK;
 }
 
 }  // extern "C"

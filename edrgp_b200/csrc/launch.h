@@ -8,8 +8,9 @@ namespace edrgp {
 // every kernel launch of the library is counted (edrgp_launch_count): bench.py reports it
 void count_launch();
 
+// dev_scale (optional): one double on the device multiplied into coef_scale inside the kernel
 cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
-                        double* pack, cudaStream_t st);
+                        double* pack, cudaStream_t st, const double* dev_scale = nullptr);
 bool grad_gram_fused(int d);
 cudaError_t launch_grad_gram(const double* X, int64_t n, int d, const double* pack, int m, double* G, double* C,
                              double* Cpart, int sms, cudaStream_t st);
@@ -18,7 +19,7 @@ cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int
                                     double* Cpart, int sms, cudaStream_t st);
 cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
                        double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
-                       cudaStream_t st, int linear = 0);
+                       cudaStream_t st, int linear = 0, unsigned int* nonfinite_flag = nullptr);
 
 // C (+)= A^T B (sym: B = A, upper tiles mirrored; optional y: bout[0..ka) (+)= A^T y, bout[ka] (+)= y^T y)
 size_t gemm_tn_workspace_bytes(int64_t n, int ka, int kb, int sym, int sms);

@@ -21,8 +21,10 @@ namespace edrgp {
 // pack layout:  [ il2[DP] | tile 0 | tile 1 | ... ]   tile = MT x S (z/l^2) | MT (hz) | MT (coef)
 // -------------------------------------------------------------------------------------------------
 __global__ void pack_inducing_kernel(const double* __restrict__ Z, const double* __restrict__ ell,
-                                     const double* __restrict__ coef, double coef_scale, int m, int d,
+                                     const double* __restrict__ coef, double coef_scale,
+                                     const double* __restrict__ dev_scale, int m, int d,
                                      int dp, double* __restrict__ pack) {
+  if (dev_scale != nullptr) coef_scale *= dev_scale[0];     // e.g. std(y), still on the device (no read-back)
   const int S = row_stride(dp);
   const int tile_doubles = pack_tile_doubles(dp);
   const int mtiles = (m + MT - 1) / MT;
@@ -101,6 +103,7 @@ struct PipeParams {
   int64_t ldg;         // leading dimension of G
   int mul;             // kuf: multiply the entries already in Kfu by this block's factor (feature-chunked d > 128)
   int linear;          // kuf: store the plain contraction x . z / l^2 (projection X V^T) instead of the kernel entry
+  unsigned int* flag;  // kuf: set to 1 when a row's scaled norm is not finite (NaN / Inf input: sklearn's check_X_y)
 };
 
 // Producer warp: streams the X row tiles and the inducing tiles of every row tile of this CTA.
@@ -178,7 +181,8 @@ __device__ __forceinline__ void producer_loop_cached(const PipeParams& p, double
 
 // hx[r] = -0.5 * sum_q (x_rq / l_q)^2 for the 16 rows of this warp (2 lanes per row)
 template <int DP>
-__device__ __forceinline__ void row_half_norms(const double* xw, const double* il2s, double* hxw, int lane) {
+__device__ __forceinline__ void row_half_norms(const double* xw, const double* il2s, double* hxw, int lane,
+                                               unsigned int* flag = nullptr) {
   constexpr int S = row_stride(DP);
   const int r = lane >> 1, h = lane & 1;
   const double* xr = xw + r * S + h * (DP / 2);
@@ -187,7 +191,12 @@ __device__ __forceinline__ void row_half_norms(const double* xw, const double* i
 #pragma unroll 8
   for (int q = 0; q < DP / 2; ++q) { double x = xr[q]; s = fma(x * x, il[q], s); }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (h == 0) hxw[r] = -0.5 * s;
+  if (h == 0) {
+    hxw[r] = -0.5 * s;
+    // the input scan comes for free here: a NaN or Inf anywhere in the row makes its norm non-finite (rows
+    // past the end of the matrix are zero-filled)
+    if (flag != nullptr && !(s <= 1.7976931348623157e308)) *flag = 1u;
+  }
 }
 
 // Distance GEMM for one inducing tile: s[mb][nb][e] = hx + hz + sum_q x_q z_q / l_q^2  (= -r^2/2).
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
     const int64_t row0 = tile * BM;
     double* xw = xbuf + (size_t)xs * BM * S + r0 * S;
     mbar_wait(&xfull[xs], xph);
-    row_half_norms<DP>(xw, il2s, hxs + r0, lane);
+    row_half_norms<DP>(xw, il2s, hxs + r0, lane, p.flag);
     __syncwarp();
     const double hx0 = p.linear ? 0.0 : hxs[r0 + g], hx1 = p.linear ? 0.0 : hxs[r0 + g + 8];
     const int64_t ra = row0 + r0 + g, rb = ra + 8;
@@ -697,12 +706,12 @@ static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) 
 }
 
 cudaError_t launch_pack(const double* Z, const double* ell, const double* coef, double coef_scale, int m, int d,
-                        double* pack, cudaStream_t st) {
+                        double* pack, cudaStream_t st, const double* dev_scale) {
   const int dp = padded_dim(d);
   const int mtiles = (m + MT - 1) / MT;
   const int warps_needed = mtiles * MT;
   const int blocks = (warps_needed * 32 + 255) / 256;
-  pack_inducing_kernel<<<blocks, 256, 0, st>>>(Z, ell, coef, coef_scale, m, d, dp, pack); count_launch();
+  pack_inducing_kernel<<<blocks, 256, 0, st>>>(Z, ell, coef, coef_scale, dev_scale, m, d, dp, pack); count_launch();
   return cudaGetLastError();
 }
 
@@ -763,9 +772,9 @@ cudaError_t launch_grad_gram_cached(const double* X, int64_t ldx, int64_t n, int
 
 cudaError_t launch_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
                        double* Kfu, int64_t ldk, int mul, const double* y, double* b, double* mu, int sms,
-                       cudaStream_t st, int linear) {
+                       cudaStream_t st, int linear, unsigned int* flag) {
   PipeParams p{};
-  p.ldx = ldx; p.ldg = d; p.mul = mul; p.linear = linear;
+  p.ldx = ldx; p.ldg = d; p.mul = mul; p.linear = linear; p.flag = flag;
   p.X = X; p.n = n; p.d = d; p.pack = pack; p.mtiles = (m + MT - 1) / MT;
   p.ntiles = (n + BM - 1) / BM; p.sf2 = sf2; p.Kfu = Kfu; p.ldk = ldk; p.m = m; p.y = y; p.b = b; p.mu = mu;
   const int grid = (int)(p.ntiles < sms ? p.ntiles : sms);

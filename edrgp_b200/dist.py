@@ -42,6 +42,9 @@ def allreduce_sum_(*tensors):
     """In-place sum over ranks of every tensor, packed into ONE collective."""
     if not is_distributed():
         return tensors
+    if len(tensors) == 1 and tensors[0].is_contiguous():
+        torch.distributed.all_reduce(tensors[0], op=torch.distributed.ReduceOp.SUM)   # in place, no staging copy
+        return tensors
     flat = torch.cat([t.reshape(-1) for t in tensors])
     torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
     off = 0

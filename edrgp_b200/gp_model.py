@@ -175,19 +175,24 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                   noise_var=self.noise_var, precision=getattr(self, 'precision', 'fp64'))
         from . import ops as _ops
 
-        def nonfinite_check(Xc, yc):
+        def nonfinite_check(Xc, yc, scan=True):
             """(device count of NaN / Inf entries, raiser): the model reads the count together with its
-            other deferred scalars in one transfer and calls the raiser if it is non-zero."""
-            bad = _ops.count_nonfinite(Xc, yc)          # enqueued now, read at the first host sync
+            other deferred scalars in one transfer and calls the raiser if it is non-zero.  scan=False: the
+            caller has its own evidence (the cross-covariance kernel flags non-finite rows as it goes) and
+            only wants the raiser."""
+            bad = _ops.count_nonfinite(Xc, yc) if scan else None   # enqueued now, read at the first host sync
 
             def on_bad():
                 if int(_ops.count_nonfinite(Xc).cpu()[0]) != 0:
                     raise ValueError("Input X contains NaN or infinity.")
-                raise ValueError("Input y contains NaN or infinity.")
+                if int(_ops.count_nonfinite(yc).cpu()[0]) != 0:
+                    raise ValueError("Input y contains NaN or infinity.")
+                raise ValueError("Input X contains values too large for the kernel arithmetic "
+                                 "(|x / lengthscale|^2 overflows float64).")
             return bad, on_bad
 
         if isinstance(X, torch.Tensor):
-            return _model.SparseGPRegression(X, y, pre_sync_check=lambda: nonfinite_check(X, y), **kw)
+            return _model.SparseGPRegression(X, y, pre_sync_check=lambda scan=True: nonfinite_check(X, y, scan), **kw)
         # Host rows: copy them block by block on a side stream while the statistics pass already
         # works on the blocks that have arrived; the non-finite scan (sklearn's check_X_y) runs on the
         # device once the last block is in, before the first host read-back.
@@ -234,10 +239,10 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
                 loader(0, min(n, rows))
             main.wait_event(state['y'])
 
-        def check():
+        def check(scan=True):
             loader(0, n)
             y_loader()
-            return nonfinite_check(Xd, yd)
+            return nonfinite_check(Xd, yd, scan)
 
         Xd.record_stream(copy_stream)
         yd.record_stream(copy_stream)

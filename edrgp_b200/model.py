@@ -17,6 +17,8 @@ scales with the number of points n runs as row-sharded CUDA kernels through the 
 
 There is no CPU fallback: every method needs the CUDA library and a CUDA device.
 """
+import weakref
+
 import numpy as np
 import torch
 from scipy import optimize as sopt
@@ -154,6 +156,10 @@ def _backsub_both_sides(L, X, transpose='left'):
     return tmp.t().contiguous()
 
 
+class NonFiniteInput(ValueError):
+    pass
+
+
 class SparseGPRegression(object):
     """Sparse GP regression (VFE / VarDTC, RBF kernel, Gaussian noise) on one GPU shard.
 
@@ -175,6 +181,8 @@ class SparseGPRegression(object):
         self.precision = precision
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.X = ops.pad_even(_as_device(X, self.device))          # (n_local, d_even)
+        if self.X.data_ptr() % 16:                                 # a row slice of a caller's tensor: the kernels
+            self.X = self.X.clone()                                # stream rows with 16-byte bulk copies
         self.n_local, self.d_even = self.X.shape
         # 'tf32x3' applies kernel by kernel: cross-covariance and gradients for d <= 64, the weights of the
         # hyper-parameter gradient for m <= 512; everything else runs the FP64 kernels
@@ -183,6 +191,8 @@ class SparseGPRegression(object):
         Yd = _as_device(Y, self.device).reshape(-1)
         if Yd.shape[0] != self.n_local:
             raise ValueError("X and Y row counts differ")
+        if Yd.data_ptr() % 16:
+            Yd = Yd.clone()
         # global row count: reduced together with the normaliser's first moment, read back lazily
         self._cnt_dev = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
         self._num_data = None if dist.is_distributed() else self.n_local
@@ -222,6 +232,9 @@ class SparseGPRegression(object):
         self.fix_Z = False
         self._Kcache = None
         self._need_grad = False
+        self._fixed = None                    # ops.FixedSweep of the composite fixed-hyper-parameter path
+        self._fixed_live = False              # its statistics / alpha belong to the current hyper-parameters
+        self._pack_obj = None
         self.kernel_launches = 0
         # row_loader(s, e): called once per row block, right before its first use, to enqueue the
         # host->device copy of rows s:e of X (the estimator overlaps the copy of block i + 1 with the
@@ -230,6 +243,13 @@ class SparseGPRegression(object):
         self._pre_sync_check = pre_sync_check
         self.parameters_changed()
         self._row_loader = None
+
+    _kuf_flag = None
+    _fixed = None
+    _fixed_live = False
+    _fixed_norm = False
+    _pack_obj = None
+    _pending = None
 
     def _ensure_y(self):
         """Normalised targets (GPy ``Standardize``) and the global row count, reduced over ranks."""
@@ -320,29 +340,97 @@ class SparseGPRegression(object):
             self._Kbuf = torch.empty(rows, ldk, dtype=F64, device=self.device)
         return ldk
 
+    @property
+    def _pack(self):
+        """Inducing pack with unit coefficients (cross-covariance, Kuu), built on first use."""
+        if self._pack_obj is None:
+            self._pack_obj = ops.InducingPack(self._Z_dev, self._ell_dev)
+        return self._pack_obj
+
+    def _fixed_path_ok(self, need_grad):
+        """The composite C-level sweep (``edrgp_fixed_*``) covers the fixed-hyper-parameter evaluation in FP64 for
+        even d <= 64 with the rows resident and the whole Kfu kept in HBM."""
+        return (not need_grad and self.precision == 'fp64' and self._row_loader is None
+                and self._Kcache is not None and ops.FixedSweep.supported(self.d_even, self.n_local)
+                and (self.normalizer is None or isinstance(self.normalizer, Standardize))
+                and self.chunk_rows % 2 == 0)
+
+    def _fixed_pass(self, sf2, beta):
+        """Pass 1 + posterior through the composite calls: one C call per stretch between two collectives."""
+        m = self.num_inducing
+        fs = self._fixed
+        if fs is None or (fs.n, fs.d, fs.m, fs.chunk, fs.world) != (self.n_local, self.d_even, m, self.chunk_rows,
+                                                                    dist.world_size()):
+            fs = self._fixed = ops.FixedSweep(self.n_local, self.d_even, m, self.chunk_rows, dist.rank(),
+                                              dist.world_size(), self.device)
+        if self._y_loader is not None:
+            self._y_loader()
+            self._y_loader = None
+        normalize = self._Y_normalized is None and self.normalizer is not None
+        y_in = self._Y_raw if self._Y_normalized is None else self._Y_normalized
+        fs.begin(self.X, y_in, self._Z_dev, self._ell_dev, sf2, self._Kcache)
+        dist.allreduce_sum_(fs.table)
+        fs.stats_pass(self.X, y_in, sf2, self._Kcache, normalize)
+        if self._Y_normalized is None:
+            if normalize:
+                norm = self.normalizer
+                norm._mean_dev, norm._std_dev = fs.tail[2:3], fs.tail[3:4]
+                norm._mean = norm._std = None
+                self._Y_normalized = fs.yt
+                self._fixed_norm = True
+            else:
+                self._Y_normalized = self._Y_raw
+            self._cnt_dev = fs.tail[1:2]
+        dist.allreduce_sum_(fs.stats)
+        self._stats = (fs.P, fs.byy)
+        fs.posterior(self._Z_dev, sf2, CONST_JITTER, beta)
+        self.alpha = fs.alpha
+        self._fixed_live = True
+        nblk = (self.n_local + self.chunk_rows - 1) // self.chunk_rows
+        self.kernel_launches += 6 + 3 * nblk + 4 + (m + 31) // 32
+        self._enqueue_checks()
+
     def parameters_changed(self):
         """Recompute the posterior (alpha), the VFE bound and -- while optimising -- its gradient."""
         dev = self.device
         m, d = self.num_inducing, self.input_dim
         sf2 = float(self.kern.variance)
-        ell = np.ones(self.d_even)
-        ell[:d] = self.kern.full_lengthscale()
-        self._ell_dev = _upload(ell, dev)
-        Zp = np.zeros((m, self.d_even))
+        # lengthscales and inducing inputs travel in ONE pinned upload
+        both = np.empty(self.d_even * (m + 1))
+        both[:self.d_even] = 1.0
+        both[:d] = self.kern.full_lengthscale()
+        Zp = both[self.d_even:].reshape(m, self.d_even)
         Zp[:, :d] = self.Z
-        self._Z_dev = _upload(Zp, dev)
+        if self.d_even != d:
+            Zp[:, d:] = 0.0
+        ell = both[:self.d_even]
+        both_dev = _upload(both, dev)
+        self._ell_dev = both_dev[:self.d_even]
+        self._Z_dev = both_dev[self.d_even:].view(m, self.d_even)
         beta = 1.0 / max(float(self.noise_variance), CONST_JITTER)
         need_grad = self._need_grad
         # the stored Kfu blocks are reused by the gradient passes when the whole matrix fits
         ldk = self._kbuffers(True)
+        self._pack_obj = None
+        self._fixed_live = False
+        self._beta = beta
+        self._solve = None
+        self._log_marginal_likelihood = None
+        self._woodbury_inv = None
+        self._info_dev = None
+        self._alpha_is_direct = not need_grad
+        if self._fixed_path_ok(need_grad):
+            return self._fixed_pass(sf2, beta)
 
-        self._pack = ops.InducingPack(self._Z_dev, self._ell_dev)
         # TF32-split mode: the training rows' cross-covariance (the n m d contraction) runs on the tcgen05
         # tensor cores; everything downstream (statistics, solve, gradients, eigh) stays FP64
         pack32 = ops.InducingPackTF32(self._Z_dev, self._ell_dev) \
             if (self.precision == 'tf32x3' and self.d_even <= 64) else None
         P = torch.empty(m, m, dtype=F64, device=dev)
         byy = torch.empty(m + 1, dtype=F64, device=dev)
+        # the FP64 cross-covariance kernel flags rows holding a NaN / Inf as it forms their norms: the input scan of
+        # check_X_y without another pass over X
+        self._kuf_flag = torch.zeros(1, dtype=torch.int32, device=dev) if pack32 is None else None
         for i, (s, e) in enumerate(self._chunks()):
             if self._row_loader is not None:
                 self._row_loader(s, e)
@@ -350,7 +438,7 @@ class SparseGPRegression(object):
             if pack32 is not None:
                 ops.kuf_tf32(self.X[s:e], pack32, sf2, out=Kc)
             else:
-                ops.kuf(self.X[s:e], self._pack, sf2, out=Kc)
+                ops.kuf(self.X[s:e], self._pack, sf2, out=Kc, flag=self._kuf_flag)
             y = self._ensure_y()
             ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
             self.kernel_launches += 4
@@ -359,12 +447,6 @@ class SparseGPRegression(object):
             P.zero_(); byy.zero_()
         dist.allreduce_sum_(P, byy)
         self._stats = (P, byy)
-        self._beta = beta
-        self._solve = None
-        self._log_marginal_likelihood = None
-        self._woodbury_inv = None
-        self._info_dev = None
-        self._alpha_is_direct = not need_grad
         if need_grad:
             trA, data_fit = self._full_chain()
             self._gradients(P, self._solve, beta, sf2, ell[:d], trA, data_fit, float(byy[m]), ldk)
@@ -413,19 +495,36 @@ class SparseGPRegression(object):
     def _enqueue_checks(self):
         """Host-row loader flush + deferred input validation, enqueued (nothing is read back): the
         non-finite count, the Cholesky flag, the row count and the normaliser moments are packed into
-        one small device tensor that ``_run_pre_sync_check`` fetches in ONE transfer."""
+        one small device tensor that ``_run_pre_sync_check`` fetches in ONE transfer.  On the composite path
+        the kernels have already left all of that in the workspace tail (the cross-covariance kernel flags
+        non-finite rows as it forms their norms, the target moments carry a NaN / Inf of y): nothing to enqueue."""
         check, self._pre_sync_check = getattr(self, '_pre_sync_check', None), None
-        bad, on_bad = check() if check is not None else (None, None)
+        old = self._pending
+        if self._fixed_live:
+            on_bad = check(scan=False)[1] if check is not None else None
+            if on_bad is None and old is not None:
+                on_bad = old[1]
+            self._pending = (self._fixed, on_bad, None)
+            return
+        norm = self.normalizer if isinstance(getattr(self, 'normalizer', None), Standardize) else None
+        flag = getattr(self, '_kuf_flag', None)
+        if check is None:
+            bad, on_bad = None, None
+        elif flag is not None and self.n_local > 0:
+            # X was scanned by the cross-covariance kernel; the targets show in their own moments (Standardize:
+            # checked when the moments are read) or get their own small scan
+            on_bad = check(scan=False)[1]
+            bad = flag.to(F64) if norm is not None else flag.to(F64) + ops.count_nonfinite(self._Y_raw).to(F64)
+        else:
+            bad, on_bad = check()
         if getattr(self, '_Y_raw', None) is not None:
             self._ensure_y()
-        norm = self.normalizer if isinstance(getattr(self, 'normalizer', None), Standardize) else None
         need_norm = norm is not None and norm._mean is None
         info = getattr(self, '_info_dev', None)
         self._info_dev = None
         if bad is None and info is None and not need_norm and self._num_data is not None:
             return
-        old = getattr(self, '_pending', None)
-        if old is not None:                       # flags of an earlier, still unread evaluation stay armed
+        if old is not None and isinstance(old[0], torch.Tensor):   # flags of an earlier, still unread evaluation stay armed
             prev, prev_on_bad, _ = old
             bad = prev[0:1] if bad is None else bad.to(F64) + prev[0:1]
             on_bad = on_bad or prev_on_bad
@@ -442,15 +541,31 @@ class SparseGPRegression(object):
         """Fetch what ``_enqueue_checks`` packed (at most ONE read-back, which also brings the row count
         and the normaliser moments to the host); returns the Cholesky flag."""
         self._enqueue_checks()
-        pending, self._pending = getattr(self, '_pending', None), None
+        pending, self._pending = self._pending, None
         if pending is None:
             return 0
         flat, on_bad, norm = pending
+        if isinstance(flat, ops.FixedSweep):
+            # composite path: the tail travels behind the eigen-decomposition when that has been read already
+            fs = flat
+            tail = fs.host[-4:] if fs.host is not None else fs.tail.cpu().numpy()
+            flag, info, count, mean, std = ops.FixedSweep.decode_tail(tail)
+            self._num_data = int(round(count))
+            norm = self.normalizer
+            if self._fixed_norm and isinstance(norm, Standardize) and norm._mean is None:
+                norm._mean, norm._std = mean, std
+            if flag != 0 or (self._fixed_norm and not (np.isfinite(mean) and np.isfinite(std))):
+                if on_bad is not None:
+                    on_bad()
+                raise NonFiniteInput("Input contains NaN or infinity.")
+            return info
         v = flat.cpu()
         self._num_data = int(round(float(v[2])))
+        bad = float(v[0]) != 0.0
         if norm is not None and norm._mean is None:
             norm._mean, norm._std = float(v[3]), float(v[4])
-        if float(v[0]) != 0.0 and on_bad is not None:
+            bad = bad or not (np.isfinite(norm._mean) and np.isfinite(norm._std))
+        if bad and on_bad is not None:
             on_bad()
         return int(v[1])
 
@@ -695,7 +810,21 @@ class SparseGPRegression(object):
             return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
         use_cache = X is None and getattr(self, '_Kcache', None) is not None
         sf2 = float(self.kern.variance)
-        if use_cache and self.d_even <= 64 and self.precision == 'tf32x3':
+        if use_cache and self._fixed_live and self.d_even <= 64 and self.precision == 'fp64':
+            # composite path: coefficient pack (std(y) applied on the device), gradients from the stored Kfu and
+            # their Gram matrix in one call; C is a view of the result block the eigensolver writes next to
+            fs = self._fixed
+            G = None
+            if want_G:
+                G = G_out if (G_out is not None and G_out.shape[1] == self.d_even) else \
+                    torch.empty(Xd.shape[0], self.d_even, dtype=F64, device=self.device)
+            if isinstance(scale, torch.Tensor):
+                C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, 1.0, scale, G)
+            else:
+                C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, float(scale), None, G)
+            C._edrgp_fixed = weakref.ref(fs)
+            self.kernel_launches += 3
+        elif use_cache and self.d_even <= 64 and self.precision == 'tf32x3':
             # TF32-split mode: W Z and the row sums as one tcgen05 contraction over the stored Kfu; the
             # Gram matrix of the gradients stays on the FP64 reduction
             coef, cs = self._grad_coef(scale)

@@ -38,18 +38,32 @@ class _Timed(object):
         return False
 
 
+_STAGES = ('kuf', 'targets', 'inducing_stats', 'solve', 'grad_gram_cached', 'eigh')      # EDRGP_STAGE_* order
+
+
 def start_timing():
-    """Begin collecting CUDA-event pairs around the contraction ops on the current stream."""
+    """Begin collecting CUDA-event pairs around the contraction ops on the current stream (the composite
+    calls of the fixed sweep bracket their stages themselves: edrgp_timing_begin)."""
     global _TIMING
     _TIMING = {}
+    _lib.check(_lib.load().edrgp_timing_begin(), 'edrgp_timing_begin')
 
 
 def stop_timing():
     """Stop collecting; returns {op name: (total ms, launches)} (synchronises)."""
+    import ctypes
     global _TIMING
     t, _TIMING = _TIMING, None
     torch.cuda.synchronize()
-    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (t or {}).items()}
+    out = {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (t or {}).items()}
+    ms = (ctypes.c_double * len(_STAGES))()
+    cnt = (ctypes.c_int * len(_STAGES))()
+    _lib.check(_lib.load().edrgp_timing_end(ms, cnt), 'edrgp_timing_end')
+    for name, a, c in zip(_STAGES, ms, cnt):
+        if c:
+            prev = out.get(name, (0.0, 0))
+            out[name] = (prev[0] + a, prev[1] + c)
+    return out
 
 
 def _need_cuda(*ts):
@@ -75,8 +89,8 @@ class InducingPack(object):
     exp(-r^2/2) factorises over the blocks and the gradient of a feature only needs its own block.
     """
 
-    def __init__(self, Z, ell, coef=None, coef_scale=1.0, block=128):
-        _need_cuda(Z, ell, coef)
+    def __init__(self, Z, ell, coef=None, coef_scale=1.0, block=128, dev_scale=None):
+        _need_cuda(Z, ell, coef, dev_scale)
         self.m, d = Z.shape
         if d % 2:
             Z = pad_even(Z)
@@ -95,21 +109,23 @@ class InducingPack(object):
             buf = torch.empty(lib.edrgp_pack_bytes(self.m, dc) // 8, dtype=F64, device=Z.device)
             self.blocks.append((c0, dc, Zb, eb, buf))
         self.buf = self.blocks[0][4]
-        self.set_coef(coef, coef_scale)
+        self.set_coef(coef, coef_scale, dev_scale)
 
-    def set_coef(self, coef, coef_scale=1.0):
+    def set_coef(self, coef, coef_scale=1.0, dev_scale=None):
+        """coef * coef_scale [* dev_scale[0], a 1-element device tensor: no read-back, no extra kernel]."""
         lib = _lib.load()
-        _need_cuda(coef)
+        _need_cuda(coef, dev_scale)
         for c0, dc, Zb, eb, buf in self.blocks:
-            _lib.check(lib.edrgp_pack_inducing(_ptr(Zb), _ptr(eb), _ptr(coef), float(coef_scale), self.m, dc,
-                                               _ptr(buf), _stream()), 'edrgp_pack_inducing')
+            _lib.check(lib.edrgp_pack_inducing(_ptr(Zb), _ptr(eb), _ptr(coef), float(coef_scale), _ptr(dev_scale),
+                                               self.m, dc, _ptr(buf), _stream()), 'edrgp_pack_inducing')
         return self
 
 
-def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
+def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False, flag=None):
     """Kfu (n, m) and, if y is given, b = Kfu^T y.  want_mu: returns (K, b, mu) with
     mu = Kfu @ coef (the coefficients stored in the pack).  Any feature count: more than 128
-    features are evaluated block by block into the same buffer (multiply mode)."""
+    features are evaluated block by block into the same buffer (multiply mode).  flag: 1-element int32
+    device tensor set to 1 when a row of X holds a NaN / Inf (the scan of check_X_y for free)."""
     lib = _lib.load()
     X = pad_even(X)
     _need_cuda(X, y)
@@ -129,7 +145,7 @@ def kuf(X, pack, sf2, y=None, out=None, want_K=True, want_mu=False):
             _lib.check(lib.edrgp_kuf(X.data_ptr() + 8 * c0, ldx, n, dc, _ptr(buf), pack.m,
                                      float(sf2) if last else 1.0, _ptr(K), ldk, int(i > 0),
                                      _ptr(y) if last else 0, _ptr(b) if last else 0, _ptr(mu) if last else 0,
-                                     _stream()), 'edrgp_kuf')
+                                     _ptr(flag), _stream()), 'edrgp_kuf')
     if not want_K:
         K = None
     if K is not None and ldk != pack.m:
@@ -523,6 +539,90 @@ def project(X, V):
     with _Timed('project'):
         _lib.check(lib.edrgp_project(_ptr(X), n, d, _ptr(V), k, _ptr(out), _stream()), 'edrgp_project')
     return out
+
+
+class FixedSweep(object):
+    """The composite calls of the fixed-hyper-parameter sweep (``edrgp_fixed_*``) over ONE workspace tensor.
+
+    Everything between two collectives is one C call; the regions a multi-rank caller all-reduces in place
+    (``table``, ``stats``, ``C``) and the results (``alpha``, ``tail``, ``result``) are views of the workspace."""
+
+    REGIONS = ('pack_k', 'pack_g', 'yt', 'stats', 'table', 'S', 'L', 'rhs', 'alpha', 'scratch', 'tail', 'result')
+
+    @staticmethod
+    def supported(d_even, n_local):
+        return d_even % 2 == 0 and d_even <= 64 and n_local > 0
+
+    def __init__(self, n_local, d, m, chunk_rows, rank, world, device):
+        import ctypes
+        lib = _lib.load()
+        self.n, self.d, self.m, self.chunk, self.rank, self.world = int(n_local), int(d), int(m), int(chunk_rows), rank, world
+        off = (ctypes.c_int64 * len(self.REGIONS))()
+        nbytes = lib.edrgp_fixed_layout(self.n, self.d, self.m, self.chunk, self.world, off)
+        if nbytes == 0:
+            raise _lib.EdrgpError("edrgp_fixed_layout rejected the shape")
+        self.ws = torch.empty(nbytes // 8, dtype=F64, device=device)
+        self.off = dict(zip(self.REGIONS, [int(o) for o in off]))
+        m, d = self.m, self.d
+        o = self.off
+        self.table = self.ws[o['table']:o['table'] + 4 * world]
+        self.stats = self.ws[o['stats']:o['stats'] + m * m + m + 1]
+        self.P = self.stats[:m * m].view(m, m)
+        self.byy = self.stats[m * m:]
+        self.yt = self.ws[o['yt']:o['yt'] + self.n]
+        self.alpha = self.ws[o['alpha']:o['alpha'] + m]
+        self.L = self.ws[o['L']:o['L'] + m * m].view(m, m)
+        self.tail = self.ws[o['tail']:o['tail'] + 4]
+        self.result = self.ws[o['result']:o['result'] + d + 2 * d * d + 4]
+        self.C = self.result[d + d * d:d + 2 * d * d].view(d, d)
+        self.host = None                     # the result block once it has been read back (one transfer)
+
+    def _common(self):
+        return self.chunk, self.world, _ptr(self.ws), _stream()
+
+    def begin(self, X, y, Z, ell, sf2, Kfu):
+        lib = _lib.load()
+        _need_cuda(X, y, Z, ell, Kfu)
+        _lib.check(lib.edrgp_fixed_begin(_ptr(X), X.shape[1], self.n, self.d, _ptr(y), _ptr(Z), Z.shape[1], _ptr(ell),
+                                         self.m, float(sf2), self.chunk, _ptr(Kfu), Kfu.shape[1], self.rank, self.world,
+                                         _ptr(self.ws), _stream()), 'edrgp_fixed_begin')
+        self.host = None
+
+    def stats_pass(self, X, y, sf2, Kfu, normalize):
+        lib = _lib.load()
+        _lib.check(lib.edrgp_fixed_stats(_ptr(X), X.shape[1], self.n, self.d, _ptr(y), self.m, float(sf2), self.chunk,
+                                         _ptr(Kfu), Kfu.shape[1], int(bool(normalize)), self.world, _ptr(self.ws),
+                                         _stream()), 'edrgp_fixed_stats')
+
+    def posterior(self, Z, sf2, jitter, beta):
+        lib = _lib.load()
+        _lib.check(lib.edrgp_fixed_posterior(_ptr(Z), Z.shape[1], self.n, self.d, self.m, float(sf2), float(jitter),
+                                             float(beta), *self._common()), 'edrgp_fixed_posterior')
+
+    def grad(self, X, Kfu, Z, ell, sf2, coef_scale=1.0, dev_scale=None, G=None):
+        """C = G^T G (view of the result block, NOT reduced over ranks) of the gradients with coefficients
+        alpha * coef_scale [* dev_scale[0]]; G (n, ldg) is filled when given."""
+        lib = _lib.load()
+        _need_cuda(G, dev_scale)
+        _lib.check(lib.edrgp_fixed_grad(_ptr(X), X.shape[1], self.n, self.d, _ptr(Kfu), Kfu.shape[1], _ptr(Z), Z.shape[1],
+                                        _ptr(ell), self.m, float(sf2), float(coef_scale), _ptr(dev_scale), _ptr(G),
+                                        0 if G is None else G.shape[1], *self._common()), 'edrgp_fixed_grad')
+        self.host = None
+        return self.C
+
+    def eigh(self):
+        """eigh of the (all-reduced) C inside the result block, then ONE read-back of evals | components | C | tail."""
+        lib = _lib.load()
+        _lib.check(lib.edrgp_fixed_eigh(self.n, self.d, self.m, *self._common()), 'edrgp_fixed_eigh')
+        self.host = self.result.cpu().numpy()
+        return self.host
+
+    @staticmethod
+    def decode_tail(tail4):
+        """(non-finite flag, Cholesky info, N, mean, std) from the four tail doubles (numpy)."""
+        import numpy as np
+        ints = np.frombuffer(np.ascontiguousarray(tail4[:1]).tobytes(), dtype=np.int32)
+        return int(ints[0]), int(ints[1]), float(tail4[1]), float(tail4[2]), float(tail4[3])
 
 
 def launch_count():

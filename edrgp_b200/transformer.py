@@ -53,15 +53,24 @@ class GramEighTransformer(BaseEstimator, TransformerMixin):
 
     def fit_gram(self, C, n_samples=None):
         """Fit from C = G^T G (d, d), already summed over all rows (and ranks)."""
-        if not isinstance(C, torch.Tensor):
-            C = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64), device='cuda')
-        d = C.shape[0]
-        evals, comps = ops.eigh(C)
-        # one read-back for eigenvalues, eigenvectors and the Gram matrix itself
-        host = torch.cat([evals, comps.reshape(-1), C.reshape(-1)]).cpu().numpy()
+        fixed = getattr(C, '_edrgp_fixed', None)
+        fixed = fixed() if fixed is not None else None
+        if fixed is not None and C.data_ptr() == fixed.C.data_ptr():
+            # C is the Gram slot of a composite sweep's result block (SparseGPRegression.gradient_gram): the
+            # eigensolver writes next to it and ONE read-back brings eigenvalues, components, C and the sweep's
+            # deferred-check words to the host
+            d = fixed.d
+            host = fixed.eigh()
+        else:
+            if not isinstance(C, torch.Tensor):
+                C = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64), device='cuda')
+            d = C.shape[0]
+            evals, comps = ops.eigh(C)
+            # one read-back for eigenvalues, eigenvectors and the Gram matrix itself
+            host = torch.cat([evals, comps.reshape(-1), C.reshape(-1)]).cpu().numpy()
         S2 = np.clip(host[:d], 0.0, np.inf)
         comps = host[d:d + d * d].reshape(d, d)
-        gram = host[d + d * d:].reshape(d, d)
+        gram = host[d + d * d:d + 2 * d * d].reshape(d, d)
         total = S2.sum()
         ratio = S2 / total if total > 0 else np.zeros_like(S2)
         nc = self.n_components

@@ -58,8 +58,10 @@ int edrgp_fp64_probe(double* scratch, int iters, double* flops, void* stream);
  * the gradient kernel).
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_pack_bytes(int m, int d);
+/* dev_scale (may be NULL): one double ON THE DEVICE multiplied into coef_scale inside the kernel -- std(y) of
+ * the target normaliser, which newer GPy multiplies into the Jacobian, without reading it back first. */
 int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, double coef_scale,
-                        int m, int d, double* pack, void* stream);
+                        const double* dev_scale, int m, int d, double* pack, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  cross-covariance  Kfu = sf2 * exp(-0.5 * clip(|x/l|^2 + |z/l|^2 - 2 (x/l).(z/l), 0)).
@@ -74,10 +76,13 @@ int edrgp_pack_inducing(const double* Z, const double* ell, const double* coef, 
  * entries already in Kfu by this call's factor: exp(-r^2/2) factorises over feature blocks, which is
  * how d > 128 is evaluated (every block but the first with multiply = 1; the variance sf2, y, b
  * and mu only on the last block, the others with sf2 = 1).
+ * nonfinite_flag (device, may be NULL) is set to 1 when a row holds a NaN or an Inf -- its scaled norm, which
+ * the kernel forms anyway, is then not finite: the non-finite scan of sklearn's check_X_y
+ * (edrgp/gp_model/base.py:87) at no extra pass over X.  The caller zeroes it.
  * ------------------------------------------------------------------------------------------- */
 int edrgp_kuf(const double* X, int64_t ldx, int64_t n, int d, const double* pack, int m, double sf2,
               double* Kfu, int64_t ldk, int multiply, const double* y, double* b, double* mu,
-              void* stream);
+              unsigned int* nonfinite_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1 in the TF32-split mode ("tf32x3"): the same cross-covariance as edrgp_kuf -- GPy RBF.K(X, Z),
@@ -243,9 +248,9 @@ int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* str
  * Replaces np.linalg.svd(G) in SVDTransformer.fit (edrgp/utils.py:140): comps rows are the right
  * singular vectors of G, evals = S^2, descending.  C is left intact.
  * workspace: edrgp_eigh_workspace_bytes(d).  sweeps (device int, may be NULL) receives the number of
- * Jacobi sweeps used.  d <= 116 runs as one CTA in shared memory and only enqueues; larger d runs
- * one kernel per round-robin step over all SMs and SYNCHRONISES the stream once per sweep to read
- * the convergence flag (the one exception to "enqueue only").
+ * Jacobi sweeps used.  d <= 116 runs as one CTA in shared memory (d <= 64: the solver records its rotations and a
+ * second kernel replays them on V across SMs); larger d runs all sweeps inside one persistent multi-SM kernel
+ * with a grid barrier per round-robin step.  Every size only enqueues.
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_eigh_workspace_bytes(int d);
 int edrgp_eigh(double* C, int d, double* evals, double* comps, int* sweeps, void* workspace,
@@ -276,6 +281,59 @@ int edrgp_standardize(const double* X, int64_t n, int d, const double* mean, con
                       double* out, void* stream);
 int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, double* out,
                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fixed-hyper-parameter EDR sweep as composite calls: everything between two collectives is
+ * enqueued by ONE call (a rank whose row shard takes a few milliseconds must not wait for its host
+ * between kernels).  Together they replace one estimator.fit + predict_gradient + SVDTransformer.fit
+ * of the reference loop (edrgp/base.py:435-466; edrgp/gp_model/base.py:46-70,208-222;
+ * edrgp/utils.py:123-157) at fixed hyper-parameters, for even d <= 64 with the whole Kfu (n, ldk)
+ * kept in HBM.  All calls share one workspace of edrgp_fixed_layout(...) bytes whose regions
+ * (offsets in doubles, written to offsets[EDRGP_FS_NREGIONS]) the caller may read -- and all-reduce in
+ * place, which is the only thing a multi-rank caller does between the calls:
+ *
+ *   edrgp_fixed_begin      pack(Z, l) -> Kfu block 0 (no targets needed: the device is busy at once)
+ *                          -> this rank's [n_r, pivot, S1, S2] of the targets into row `rank` of TABLE
+ *       [sum TABLE over ranks: every rank fills only its own row]
+ *   edrgp_fixed_stats      mean / std(y) over all ranks (GPy Standardize; normalize = 0: y is used as it is and only
+ *                          N is refreshed), TAIL = [flags | N | mean | std], then P, b, y^T y over all row blocks
+ *                          into STATS
+ *       [sum STATS over ranks]
+ *   edrgp_fixed_posterior  S = Kuu + jitter I + beta P;  alpha = S^-1 beta b  (Cholesky; info -> TAIL)
+ *   edrgp_fixed_grad       pack(Z, l, alpha * coef_scale [* dev_scale[0], e.g. std(y) = TAIL[3]]) -> gradients from the stored Kfu
+ *                          (G (n, ldg) optional) -> C = G^T G into RESULT, TAIL copied behind it
+ *       [sum C over ranks]
+ *   edrgp_fixed_eigh       eigh(C): RESULT = evals (d) | components (d x d) | C (d x d) | TAIL copy (4)
+ *
+ * TAIL word 0 holds two 32-bit integers: the non-finite flag of edrgp_kuf and the info of edrgp_posv.
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  EDRGP_FS_PACK_K = 0, EDRGP_FS_PACK_G, EDRGP_FS_YT, EDRGP_FS_STATS, EDRGP_FS_TABLE, EDRGP_FS_S, EDRGP_FS_L,
+  EDRGP_FS_RHS, EDRGP_FS_ALPHA, EDRGP_FS_SCRATCH, EDRGP_FS_TAIL, EDRGP_FS_RESULT, EDRGP_FS_NREGIONS
+};
+size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int64_t* offsets);
+int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
+                      const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
+                      int world, void* workspace, void* stream);
+int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const double* y, int m, double sf2,
+                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* workspace,
+                      void* stream);
+int edrgp_fixed_posterior(const double* Z, int64_t ldz, int64_t n, int d, int m, double sf2, double jitter, double beta,
+                          int64_t chunk_rows, int world, void* workspace, void* stream);
+int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, const double* Z,
+                     int64_t ldz, const double* ell, int m, double sf2, double coef_scale, const double* dev_scale,
+                     double* G, int64_t ldg, int64_t chunk_rows, int world, void* workspace, void* stream);
+int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream);
+
+/* Optional per-stage timing of the composite calls (measurement aid; nothing on the product path needs it):
+ * between edrgp_timing_begin and edrgp_timing_end every stage a composite call launches is bracketed by a pair of
+ * CUDA events on the caller's stream; _end waits for them and adds up milliseconds and launch groups per stage
+ * (ms[EDRGP_STAGE_COUNT], count[EDRGP_STAGE_COUNT]).  EDRGP_STAGE_STATS spans exactly one launch of the symmetric
+ * reduction P = Kfu^T Kfu per row block, which is what bench.py's roofline divides by. */
+enum { EDRGP_STAGE_KUF = 0, EDRGP_STAGE_TARGETS, EDRGP_STAGE_STATS, EDRGP_STAGE_SOLVE, EDRGP_STAGE_GRAD, EDRGP_STAGE_EIGH,
+       EDRGP_STAGE_COUNT };
+int edrgp_timing_begin(void);
+int edrgp_timing_end(double* ms, int* count);
 
 #ifdef __cplusplus
 }

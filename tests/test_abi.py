@@ -49,7 +49,7 @@ def test_version_and_error_calls_work_without_gpu():
     assert lib.edrgp_version() >= 100
     assert lib.edrgp_pack_bytes(512, 64) == (64 + 16 * 32 * (64 + 2 + 2)) * 8
     # argument errors are reported before any CUDA call
-    rc = lib.edrgp_kuf(0, 4, 10, 4, 0, 3, 1.0, 0, 4, 0, 0, 0, 0, 0)
+    rc = lib.edrgp_kuf(0, 4, 10, 4, 0, 3, 1.0, 0, 4, 0, 0, 0, 0, 0, 0)
     assert rc == -1
     assert b'kuf' in lib.edrgp_last_error()
 
