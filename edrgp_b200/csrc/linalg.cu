@@ -829,6 +829,25 @@ static int jacobi_variant() {
   return v;
 }
 
+// Power-of-two factor that brings the largest diagonal entry of C into [1, 2): the solvers iterate on a scaled
+// copy (rotations do not depend on the scale; eigenvalues are Rayleigh quotients against the caller's C), so that
+// the squares and products of column norms they compare stay inside the double range for matrices whose entries are
+// anywhere between ~1e-300 and ~1e+300.  The whole CTA calls this (one barrier); 1.0 for a zero or non-finite diagonal.
+__device__ __forceinline__ double jacobi_input_scale(const double* __restrict__ C, int d, int tid, int nt) {
+  __shared__ unsigned long long mxbits;
+  if (tid == 0) mxbits = 0ull;
+  __syncthreads();
+  unsigned long long mine = 0ull;
+  for (int i = tid; i < d; i += nt) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(C[(int64_t)i * d + i]));
+    mine = b > mine ? b : mine;
+  }
+  if (mine) atomicMax(&mxbits, mine);
+  __syncthreads();
+  const int e = (int)((mxbits >> 52) & 0x7ffull);
+  return (e == 0 || e == 0x7ff) ? 1.0 : __hiloint2double((2046 - e) << 20, 0);
+}
+
 // Eigenvalues and output for the vectors V (column i at V + i * ds, shared or global memory): lam is
 // d doubles of shared scratch; the whole CTA calls this after a barrier.
 __device__ __forceinline__ void jacobi_finish(const double* __restrict__ C, int d, const double* V, int ds, double* lam,
@@ -912,9 +931,10 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
   __shared__ int rotated;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int dd = d + (d & 1), np = dd / 2;
+  const double in_scale = jacobi_input_scale(C, d, tid, nt);
   for (int i = tid; i < d * d; i += nt) {
     const int c = i / d, r = i - c * d;
-    W[c * ds + r] = C[(int64_t)r * d + c];
+    W[c * ds + r] = C[(int64_t)r * d + c] * in_scale;
     if (!LOGV) V[c * ds + r] = r == c ? 1.0 : 0.0;
   }
   __syncthreads();
@@ -1050,9 +1070,10 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
   __shared__ unsigned short sched[PER * NP];  // p | q << 8 of slot k at step s
   __shared__ int rotated;
   const int tid = threadIdx.x;
+  const double in_scale = jacobi_input_scale(C, D, tid, 512);
   for (int i = tid; i < D * D; i += 512) {
     const int c = i >> 6, r = i & 63;
-    W[c * DS + r] = C[(int64_t)r * D + c];
+    W[c * DS + r] = C[(int64_t)r * D + c] * in_scale;
   }
   for (int i = tid; i < PER * NP; i += 512) {
     const int step = i >> 5, k = i & 31;
@@ -1254,10 +1275,11 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
 // nothing synchronises the stream.
 // ---------------------------------------------------------------------------------------------
 __global__ void eig_init_kernel(const double* __restrict__ C, int d, double* __restrict__ W, double* __restrict__ V) {
+  const double in_scale = jacobi_input_scale(C, d, threadIdx.x, blockDim.x);     // every CTA derives the same factor
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)d * d) return;
   const int c = (int)(i / d), r = (int)(i - (int64_t)c * d);
-  W[i] = C[(int64_t)r * d + c];
+  W[i] = C[(int64_t)r * d + c] * in_scale;
   V[i] = r == c ? 1.0 : 0.0;
 }
 
@@ -1443,13 +1465,18 @@ static cudaError_t launch_eigh_large(const double* C, int d, double* ws, double*
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   int grid = (np + 7) / 8;                       // 8 warps (pairs) per CTA; every CTA must be resident: <= one per SM
   if (grid > sms) grid = sms;
-  if (d <= 128) eig_persistent_kernel<4><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
-  else if (d <= 256) eig_persistent_kernel<8><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
-  else if (d <= 512) eig_persistent_kernel<16><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
-  else eig_persistent_kernel<0><<<grid, 256, 0, st>>>(W, V, d, 60, ctrl);
+  // The kernel synchronises its CTAs with its own spin barrier, which is only safe when every CTA is resident at
+  // the same time: a COOPERATIVE launch makes the driver guarantee that (or fail the launch with
+  // cudaErrorCooperativeLaunchTooLarge) even when another stream, an NCCL kernel or another process holds SMs.
+  int max_sweeps = 60;
+  void* args[] = {(void*)&W, (void*)&V, (void*)&d, (void*)&max_sweeps, (void*)&ctrl};
+  const void* kern = d <= 128 ? (const void*)eig_persistent_kernel<4>
+                   : d <= 256 ? (const void*)eig_persistent_kernel<8>
+                   : d <= 512 ? (const void*)eig_persistent_kernel<16> : (const void*)eig_persistent_kernel<0>;
+  if ((e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, 0, st)) != cudaSuccess) return e;
   count_launch();
-  if (sweeps) {
-    e = cudaMemcpyAsync(sweeps, ctrl + 3, sizeof(int), cudaMemcpyDeviceToDevice, st);
+  if (sweeps) {      // [0] sweeps done, [1] status: the barrier's time-out flag (0 = clean)
+    e = cudaMemcpyAsync(sweeps, ctrl + 3, 2 * sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
   }
   eig_rayleigh_kernel<<<(d + 7) / 8, 256, 0, st>>>(C, V, d, lam); count_launch();

@@ -55,6 +55,13 @@ def allreduce_sum_(*tensors):
     return tensors
 
 
+def allreduce_max_(tensor):
+    """In-place maximum over ranks (failure flags)."""
+    if is_distributed():
+        torch.distributed.all_reduce(tensor, op=torch.distributed.ReduceOp.MAX)
+    return tensor
+
+
 def broadcast_(tensor, src=0):
     if is_distributed():
         torch.distributed.broadcast(tensor, src=src)

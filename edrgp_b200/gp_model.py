@@ -8,7 +8,6 @@ Only what the hot path needs is provided: the RBF kernel (ARD or not) with a Gau
 Other GPy kernels, sums of kernels, uncertain inputs and mean functions raise
 ``NotImplementedError`` instead of silently doing something else.
 """
-import pickle
 from copy import deepcopy
 
 import numpy as np
@@ -109,25 +108,41 @@ class _BaseGP(BaseEstimator):
         return self.estimator_.predictive_gradients(X)[0][:, :, 0]
 
     def save(self, model_path):
-        """Save the fitted model to ``model_path`` (+ '.pickle'), edrgp/gp_model/base.py:224-239.
-        The file holds plain arrays (hyper-parameters, Z, alpha, Cholesky factors)."""
+        """Save the fitted model to ``model_path`` (+ '.pickle', the reference's file name convention,
+        edrgp/gp_model/base.py:224-239).  The CONTENT is not a GPy pickle: it is a NumPy ``.npz`` archive of plain
+        arrays (hyper-parameters, Z, alpha, Cholesky factors, normaliser moments) that loads without executing
+        anything (``allow_pickle=False``); files written by the reference cannot be read and vice versa."""
         check_is_fitted(self, 'estimator_')
         if not model_path.endswith('.pickle'):
             model_path += '.pickle'
+        state = self.estimator_.state_dict()
+        arrays = {'format': np.array('edrgp_b200/2'), 'n_features_': np.array(self.n_features_)}
+        arrays.update({'state_' + k: np.asarray(v) for k, v in state.items()})
         with open(model_path, 'wb') as f:
-            pickle.dump({'format': 'edrgp_b200/1', 'state': self.estimator_.state_dict(),
-                         'n_features_': self.n_features_}, f)
+            np.savez(f, **arrays)
 
     def load(self, model_path):
-        """Load a model saved by ``save`` (edrgp/gp_model/base.py:242-257)."""
+        """Load a model saved by ``save`` (edrgp/gp_model/base.py:242-257).  The restored estimator predicts
+        (``predict``, ``predict_variance``, ``predict_gradient``); it holds no training rows."""
         if not model_path.endswith('.pickle'):
             model_path += '.pickle'
-        with open(model_path, 'rb') as f:
-            blob = pickle.load(f)
-        if not isinstance(blob, dict) or blob.get('format') != 'edrgp_b200/1':
-            raise ValueError("not an edrgp_b200 model file")
-        self.estimator_ = _model.FittedSparseGP(blob['state'])
-        self.n_features_ = blob['n_features_']
+        try:
+            with np.load(model_path, allow_pickle=False) as blob:
+                if 'format' not in blob.files or str(blob['format']) != 'edrgp_b200/2':
+                    raise ValueError("not an edrgp_b200 model file")
+                state = {k[6:]: blob[k] for k in blob.files if k.startswith('state_')}
+                n_features = int(blob['n_features_'])
+        except (OSError, ValueError) as e:
+            raise ValueError("not an edrgp_b200 model file (%s); GPy pickles written by the reference are not "
+                             "supported" % (e,))
+        for k in ('variance', 'noise_variance', 'log_likelihood', 'y_mean', 'y_std'):
+            if k in state:
+                state[k] = float(state[k])
+        for k in ('input_dim', 'num_data'):
+            state[k] = int(state[k])
+        state['ARD'] = bool(state['ARD'])
+        self.estimator_ = _model.FittedSparseGP(state)
+        self.n_features_ = n_features
 
 
 class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
@@ -170,6 +185,8 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
     def _get_model(self, X, y, kernel):
         import torch
+        if self.Y_metadata is not None:
+            raise NotImplementedError("Y_metadata is outside the B200 path (Gaussian likelihood only)")
         kw = dict(kernel=kernel, Z=self.Z, num_inducing=self.num_inducing, X_variance=self.X_variance,
                   mean_function=self.mean_function, normalizer=self.normalizer, chunk_rows=self.chunk_rows,
                   noise_var=self.noise_var, precision=getattr(self, 'precision', 'fp64'))
@@ -183,12 +200,13 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
             bad = _ops.count_nonfinite(Xc, yc) if scan else None   # enqueued now, read at the first host sync
 
             def on_bad():
+                bad_input = _model.NonFiniteInput         # a ValueError, as sklearn's validators raise
                 if int(_ops.count_nonfinite(Xc).cpu()[0]) != 0:
-                    raise ValueError("Input X contains NaN or infinity.")
+                    raise bad_input("Input X contains NaN or infinity.")
                 if int(_ops.count_nonfinite(yc).cpu()[0]) != 0:
-                    raise ValueError("Input y contains NaN or infinity.")
-                raise ValueError("Input X contains values too large for the kernel arithmetic "
-                                 "(|x / lengthscale|^2 overflows float64).")
+                    raise bad_input("Input y contains NaN or infinity.")
+                raise bad_input("Input contains NaN or infinity on another rank, or values too large for the "
+                                "kernel arithmetic (|x / lengthscale|^2 overflows float64).")
             return bad, on_bad
 
         if isinstance(X, torch.Tensor):

@@ -79,12 +79,11 @@ class Standardize(object):
     def scale_by_device(self, y_dev, cnt_dev):
         """cnt_dev: 1-element device tensor holding this rank's row count; it is summed over ranks
         in the same collective as the first moment (and left holding the global count)."""
-        s1, _ = ops.col_moments(y_dev)
-        s1 = s1.clone()
+        empty = y_dev.numel() == 0                 # a rank without rows still joins both collectives
+        s1 = torch.zeros(1, dtype=F64, device=cnt_dev.device) if empty else ops.col_moments(y_dev)[0].clone()
         dist.allreduce_sum_(s1, cnt_dev)
         mean = s1 / cnt_dev
-        _, s2 = ops.col_moments(y_dev, shift=mean)
-        s2 = s2.clone()
+        s2 = torch.zeros(1, dtype=F64, device=cnt_dev.device) if empty else ops.col_moments(y_dev, shift=mean)[1].clone()
         dist.allreduce_sum_(s2)
         self._mean_dev, self._std_dev = mean, torch.sqrt(s2 / cnt_dev)
         self._mean = self._std = None
@@ -113,6 +112,8 @@ class Standardize(object):
         self._std = float(v)
 
     def normalize_device(self, y_dev):
+        if y_dev.numel() == 0:
+            return y_dev
         return ops.standardize(y_dev, self._mean_dev, self._std_dev)
 
     def inverse_mean(self, X):
@@ -194,7 +195,7 @@ class SparseGPRegression(object):
         if Yd.data_ptr() % 16:
             Yd = Yd.clone()
         # global row count: reduced together with the normaliser's first moment, read back lazily
-        self._cnt_dev = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
+        self._cnt_dev_t = None
         self._num_data = None if dist.is_distributed() else self.n_local
         if normalizer is True:
             self.normalizer = Standardize()
@@ -243,6 +244,20 @@ class SparseGPRegression(object):
         self._pre_sync_check = pre_sync_check
         self.parameters_changed()
         self._row_loader = None
+
+    _cnt_dev_t = None
+
+    @property
+    def _cnt_dev(self):
+        """1-element device tensor with this rank's row count (summed over ranks by the normaliser's collective);
+        created on first use -- the composite path takes the global count from its own moments table."""
+        if self._cnt_dev_t is None:
+            self._cnt_dev_t = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
+        return self._cnt_dev_t
+
+    @_cnt_dev.setter
+    def _cnt_dev(self, t):
+        self._cnt_dev_t = t
 
     _kuf_flag = None
     _fixed = None
@@ -335,8 +350,8 @@ class SparseGPRegression(object):
                     self._Kcache = torch.empty(self.n_local, ldk, dtype=F64, device=self.device)
                 except torch.cuda.OutOfMemoryError:
                     self._Kcache = None                       # one reusable block instead (recompute path)
-        if getattr(self, '_Kbuf', None) is None or self._Kbuf.shape[1] != ldk:
-            rows = min(self.chunk_rows, self.n_local)
+        if self._Kcache is None and (getattr(self, '_Kbuf', None) is None or self._Kbuf.shape[1] != ldk):
+            rows = min(self.chunk_rows, self.n_local)                 # one reusable block (recompute path)
             self._Kbuf = torch.empty(rows, ldk, dtype=F64, device=self.device)
         return ldk
 
@@ -361,8 +376,9 @@ class SparseGPRegression(object):
         fs = self._fixed
         if fs is None or (fs.n, fs.d, fs.m, fs.chunk, fs.world) != (self.n_local, self.d_even, m, self.chunk_rows,
                                                                     dist.world_size()):
-            fs = self._fixed = ops.FixedSweep(self.n_local, self.d_even, m, self.chunk_rows, dist.rank(),
-                                              dist.world_size(), self.device)
+            fs = self._fixed = ops.FixedSweep.acquire(self.n_local, self.d_even, m, self.chunk_rows, dist.rank(),
+                                                      dist.world_size(), self.device)
+            weakref.finalize(self, ops.FixedSweep.release, fs)
         if self._y_loader is not None:
             self._y_loader()
             self._y_loader = None
@@ -529,6 +545,9 @@ class SparseGPRegression(object):
             bad = prev[0:1] if bad is None else bad.to(F64) + prev[0:1]
             on_bad = on_bad or prev_on_bad
             info = prev[1:2] if info is None else info            # the latest factorisation's flag wins
+        if bad is not None and dist.is_distributed():
+            bad = bad.to(F64).clone()
+            dist.allreduce_sum_(bad)               # every rank raises when any rank's rows are bad
         zero = None
         if bad is None or info is None:
             zero = torch.zeros(1, dtype=F64, device=self.device)
@@ -558,6 +577,9 @@ class SparseGPRegression(object):
                 if on_bad is not None:
                     on_bad()
                 raise NonFiniteInput("Input contains NaN or infinity.")
+            if info != 0 and fs.world > 1 and not np.isfinite(float(fs.byy[-1])):
+                # a NaN / Inf in another rank's rows reaches this rank through the all-reduced statistics
+                raise NonFiniteInput("Input contains NaN or infinity (rows of another rank).")
             return info
         v = flat.cpu()
         self._num_data = int(round(float(v[2])))
@@ -691,22 +713,36 @@ class SparseGPRegression(object):
     _allowed_failures = 10
 
     def _objective_grads(self, x):
+        fail = 0
+        obj, grads = np.inf, None
         try:
             self._set_optimizer_array(x)
             obj = -float(np.sum(self.log_likelihood()))
             grads = -self._transformed_gradients()
-            self._fail_count = 0
+        except NonFiniteInput:
+            raise                                  # bad input is not a failed evaluation: it surfaces as it is
         except (np.linalg.LinAlgError, ZeroDivisionError, ValueError, FloatingPointError):
+            fail = 1
+        if dist.is_distributed():
+            # every rank must walk the same L-BFGS trajectory and stay in the same collectives: a failure on
+            # any rank is a failure everywhere, and (f, g) are rank 0's
+            buf = torch.zeros(2 + x.size, dtype=F64, device=self.device)
+            if not fail:
+                buf[1:] = torch.as_tensor(np.concatenate([[obj], grads]), device=self.device)
+            buf[0] = float(fail)
+            flag = buf[0:1].clone()
+            dist.allreduce_max_(flag)
+            dist.broadcast_(buf, 0)
+            host = buf.cpu().numpy()
+            fail = int(round(float(flag.cpu()[0])))
+            obj, grads = float(host[1]), host[2:]
+        if fail:
             if self._fail_count >= self._allowed_failures:
-                raise
+                raise np.linalg.LinAlgError("the objective could not be evaluated %d times in a row "
+                                            "(not positive definite)" % (self._fail_count + 1))
             self._fail_count += 1
             return np.inf, np.clip(np.zeros_like(x), -1e10, 1e10)
-        if dist.is_distributed():
-            # every rank must walk the same L-BFGS trajectory: take rank 0's view of (f, g)
-            buf = torch.as_tensor(np.concatenate([[obj], grads]), device=self.device)
-            dist.broadcast_(buf, 0)
-            buf = buf.cpu().numpy()
-            obj, grads = float(buf[0]), buf[1:]
+        self._fail_count = 0
         return obj, np.clip(grads, -1e10, 1e10)
 
     def optimize(self, optimizer=None, start=None, messages=False, max_iters=1000, **kwargs):
@@ -716,6 +752,9 @@ class SparseGPRegression(object):
         x0 = self._get_optimizer_array() if start is None else np.asarray(start, dtype=np.float64)
         if max_iters <= 0 or x0.size == 0:
             return self
+        # deferred input validation surfaces HERE, once and on every rank alike (the non-finite count is summed
+        # over ranks), not as a "failed evaluation" inside the optimiser
+        self._run_pre_sync_check()
         self._need_grad = True
         try:
             x_opt, f_opt, info = sopt.fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters, maxiter=max_iters)
@@ -822,6 +861,9 @@ class SparseGPRegression(object):
                 C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, 1.0, scale, G)
             else:
                 C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, float(scale), None, G)
+            # the caller gets its own copy (it may sum it over ranks in place, keep it, call again); the tag lets
+            # GramEighTransformer.fit_gram run the eigensolver inside the block and read everything back at once
+            C = C.clone()
             C._edrgp_fixed = weakref.ref(fs)
             self.kernel_launches += 3
         elif use_cache and self.d_even <= 64 and self.precision == 'tf32x3':

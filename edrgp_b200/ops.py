@@ -410,9 +410,13 @@ def trsm(L, B, trans=False):
     return B
 
 
-def eigh(C):
+EIGH_MAX_SWEEPS = 60
+
+
+def eigh(C, return_status=False):
     """Descending eigen-decomposition of a symmetric (d, d) matrix: (evals, comps) with comps rows
-    = eigenvectors.  C is not modified."""
+    = eigenvectors.  C is not modified.  return_status: also the device int32 pair [sweeps, barrier time-out]
+    for ``check_eigh_status`` once it has reached the host (callers read it with the eigenvalues)."""
     lib = _lib.load()
     _need_cuda(C)
     d = C.shape[0]
@@ -420,9 +424,18 @@ def eigh(C):
     evals = torch.empty(d, dtype=F64, device=C.device)
     comps = torch.empty(d, d, dtype=F64, device=C.device)
     ws = torch.empty(max(1, lib.edrgp_eigh_workspace_bytes(d) // 8), dtype=F64, device=C.device)
+    status = torch.zeros(2, dtype=torch.int32, device=C.device) if return_status else None
     with _Timed('eigh'):
-        _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), 0, _ptr(ws), _stream()), 'edrgp_eigh')
-    return evals, comps
+        _lib.check(lib.edrgp_eigh(_ptr(A), d, _ptr(evals), _ptr(comps), _ptr(status), _ptr(ws), _stream()), 'edrgp_eigh')
+    return (evals, comps, status) if return_status else (evals, comps)
+
+
+def check_eigh_status(sweeps, timed_out):
+    """Raise instead of handing out half-rotated eigenvectors."""
+    if int(timed_out) != 0:
+        raise _lib.EdrgpError("edrgp_eigh: the multi-SM Jacobi solver's grid barrier timed out (a CTA was not resident)")
+    if int(sweeps) >= EIGH_MAX_SWEEPS:
+        raise _lib.EdrgpError("edrgp_eigh: no convergence within %d Jacobi sweeps" % EIGH_MAX_SWEEPS)
 
 
 def col_moments(X, shift=None, weight=None, out=None, accumulate=False):
@@ -549,9 +562,34 @@ class FixedSweep(object):
 
     REGIONS = ('pack_k', 'pack_g', 'yt', 'stats', 'table', 'S', 'L', 'rhs', 'alpha', 'scratch', 'tail', 'result')
 
+    _POOL = {}            # shape key -> workspaces of models that no longer exist, ready for reuse
+    _POOL_DEPTH = 2
+
     @staticmethod
     def supported(d_even, n_local):
         return d_even % 2 == 0 and d_even <= 64 and n_local > 0
+
+    @classmethod
+    def acquire(cls, n_local, d, m, chunk_rows, rank, world, device):
+        """A workspace for one model: a recycled one of the same shape when a previous model has been dropped
+        (building the views costs more host time than the kernels of a small shard leave room for)."""
+        key = (torch.device(device).index, int(n_local), int(d), int(m), int(chunk_rows), int(rank), int(world))
+        free = cls._POOL.get(key)
+        if free:
+            fs = free.pop()
+            fs.host = None
+            return fs
+        fs = cls(n_local, d, m, chunk_rows, rank, world, device)
+        fs.key = key
+        return fs
+
+    @classmethod
+    def release(cls, fs):
+        """Called when the owning model is collected (weakref.finalize): nothing the model handed out aliases the
+        workspace (``gradient_gram`` returns a copy of C), so it can serve the next model of the same shape."""
+        free = cls._POOL.setdefault(fs.key, [])
+        if len(free) < cls._POOL_DEPTH:
+            free.append(fs)
 
     def __init__(self, n_local, d, m, chunk_rows, rank, world, device):
         import ctypes
@@ -576,6 +614,7 @@ class FixedSweep(object):
         self.result = self.ws[o['result']:o['result'] + d + 2 * d * d + 4]
         self.C = self.result[d + d * d:d + 2 * d * d].view(d, d)
         self.host = None                     # the result block once it has been read back (one transfer)
+        self.key = None
 
     def _common(self):
         return self.chunk, self.world, _ptr(self.ws), _stream()
@@ -610,9 +649,13 @@ class FixedSweep(object):
         self.host = None
         return self.C
 
-    def eigh(self):
-        """eigh of the (all-reduced) C inside the result block, then ONE read-back of evals | components | C | tail."""
+    def eigh(self, C=None):
+        """eigh of the (all-reduced) Gram matrix inside the result block, then ONE read-back of
+        evals | components | C | tail.  C: the caller's copy of the matrix (possibly summed over ranks since
+        ``grad`` returned it); it is put back into the block first."""
         lib = _lib.load()
+        if C is not None and C.data_ptr() != self.C.data_ptr():
+            self.C.copy_(C)
         _lib.check(lib.edrgp_fixed_eigh(self.n, self.d, self.m, *self._common()), 'edrgp_fixed_eigh')
         self.host = self.result.cpu().numpy()
         return self.host

@@ -55,19 +55,20 @@ class GramEighTransformer(BaseEstimator, TransformerMixin):
         """Fit from C = G^T G (d, d), already summed over all rows (and ranks)."""
         fixed = getattr(C, '_edrgp_fixed', None)
         fixed = fixed() if fixed is not None else None
-        if fixed is not None and C.data_ptr() == fixed.C.data_ptr():
-            # C is the Gram slot of a composite sweep's result block (SparseGPRegression.gradient_gram): the
-            # eigensolver writes next to it and ONE read-back brings eigenvalues, components, C and the sweep's
+        if fixed is not None and tuple(C.shape) == (fixed.d, fixed.d):
+            # C came from a composite sweep (SparseGPRegression.gradient_gram): the eigensolver runs inside the
+            # sweep's result block and ONE read-back brings eigenvalues, components, C and the sweep's
             # deferred-check words to the host
             d = fixed.d
-            host = fixed.eigh()
+            host = fixed.eigh(C)
         else:
             if not isinstance(C, torch.Tensor):
                 C = torch.as_tensor(np.ascontiguousarray(C, dtype=np.float64), device='cuda')
             d = C.shape[0]
-            evals, comps = ops.eigh(C)
-            # one read-back for eigenvalues, eigenvectors and the Gram matrix itself
-            host = torch.cat([evals, comps.reshape(-1), C.reshape(-1)]).cpu().numpy()
+            evals, comps, status = ops.eigh(C, return_status=True)
+            # one read-back for eigenvalues, eigenvectors, the Gram matrix itself and the solver's status
+            host = torch.cat([evals, comps.reshape(-1), C.reshape(-1), status.to(F64)]).cpu().numpy()
+            ops.check_eigh_status(host[-2], host[-1])
         S2 = np.clip(host[:d], 0.0, np.inf)
         comps = host[d:d + d * d].reshape(d, d)
         gram = host[d + d * d:d + 2 * d * d].reshape(d, d)
@@ -126,9 +127,11 @@ class DevicePCA(BaseEstimator, TransformerMixin):
         else:
             C = torch.zeros(d, d, dtype=F64, device=Xd.device)
         dist.allreduce_sum_(C)
-        evals, comps = ops.eigh(C)
-        lam = np.clip(evals.cpu().numpy(), 0.0, np.inf)
-        comps = comps.cpu().numpy()
+        evals, comps, status = ops.eigh(C, return_status=True)
+        host = torch.cat([evals, comps.reshape(-1), status.to(F64)]).cpu().numpy()
+        ops.check_eigh_status(host[-2], host[-1])
+        lam = np.clip(host[:d], 0.0, np.inf)
+        comps = host[d:d + d * d].reshape(d, d)
         nc = self.n_components
         if nc is None:
             k = min(d, int(n))

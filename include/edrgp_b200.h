@@ -247,8 +247,9 @@ int edrgp_trsm(const double* L, int m, double* B, int nrhs, int trans, void* str
  * (one-sided cyclic Jacobi on W = C V; eigenvalues as Rayleigh quotients).
  * Replaces np.linalg.svd(G) in SVDTransformer.fit (edrgp/utils.py:140): comps rows are the right
  * singular vectors of G, evals = S^2, descending.  C is left intact.
- * workspace: edrgp_eigh_workspace_bytes(d).  sweeps (device int, may be NULL) receives the number of
- * Jacobi sweeps used.  d <= 116 runs as one CTA in shared memory (d <= 64: the solver records its rotations and a
+ * workspace: edrgp_eigh_workspace_bytes(d).  sweeps (TWO device ints, may be NULL; the caller zeroes them):
+ * [0] receives the number of Jacobi sweeps used (60 = the limit: not converged), [1] a status word that is
+ * non-zero when the multi-SM solver's grid barrier timed out (results are then unusable).  d <= 116 runs as one CTA in shared memory (d <= 64: the solver records its rotations and a
  * second kernel replays them on V across SMs); larger d runs all sweeps inside one persistent multi-SM kernel
  * with a grid barrier per round-robin step.  Every size only enqueues.
  * ------------------------------------------------------------------------------------------- */

@@ -172,10 +172,12 @@ def test_eigh_general_kernel_matches_lapack():
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("kind", ["flat", "rank_deficient", "one_dominant", "tiny_scale", "zero"])
+@pytest.mark.parametrize("kind", ["flat", "rank_deficient", "one_dominant", "tiny_scale", "huge_scale", "zero"])
 def test_eigh_d64_spectra(kind):
     """The default d = 64 path (specialised solver + lean rotation replay) on spectra that stress the sweep count
-    and the relative rotation test: flat (clustered), rank 5 of 64, one dominant direction, entries ~1e-200, zero."""
+    and the relative rotation test: flat (clustered), rank 5 of 64, one dominant direction, entries ~1e-200 (the
+    solver iterates on a copy scaled by a power of two, or the products of column norms it compares would underflow),
+    zero."""
     from edrgp_b200 import ops
     d = 64
     rng = np.random.RandomState(7)
@@ -187,6 +189,8 @@ def test_eigh_d64_spectra(kind):
         G = 0.01 * rng.standard_normal((20000, d)); G[:, 0] += rng.standard_normal(20000)
     elif kind == "tiny_scale":
         G = 1e-100 * rng.standard_normal((500, d)) * np.linspace(3.0, 0.1, d)
+    elif kind == "huge_scale":
+        G = 1e120 * rng.standard_normal((500, d)) * np.linspace(3.0, 0.1, d)
     else:
         G = np.zeros((10, d))
     C = G.T.dot(G)

@@ -83,8 +83,10 @@ def test_gradient_cache_and_recompute_agree():
         mod._need_grad = True
         mod.parameters_changed()
     assert a._Kcache is None and b._Kcache is not None
-    assert np.array_equal(a.grad_Z, b.grad_Z)
-    assert a.grad_variance == b.grad_variance
+    # same kernels on the same entries; the two models standardise their targets by different routes (the cached
+    # one went through the composite sweep's one-pass moments first), which differ in the last bits
+    assert _relerr(a.grad_Z, b.grad_Z) < 1e-10
+    assert abs(a.grad_variance - b.grad_variance) < 1e-10 * abs(b.grad_variance)
 
 
 def test_optimize_improves_bound_like_the_oracle():

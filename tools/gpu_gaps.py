@@ -1,35 +1,55 @@
-"""GPU-side idle gaps between the timed ops of one sweep on a 500k-row shard (8-GPU share of C3)."""
-import sys, time
-import numpy as np, torch
+"""Where one sweep on a 500k-row shard (the 8-GPU share of C3) spends its time: CUDA-event total of the sweep
+through the public classes, the stage times the library brackets itself (edrgp_timing_begin / _end) and what is left
+over -- the rank-replicated, latency-bound remainder R = total - (kuf + stats + gradients) that limits strong scaling."""
+import json
+import sys
+import numpy as np
+import torch
 sys.path.insert(0, '.')
 import edrgp_b200 as eb
 from edrgp_b200 import model as emodel, ops
-n, d, m = 500_000, 64, 512
+
+n, d, m = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (500_000, 64, 512)))
 g = torch.Generator(device='cuda').manual_seed(0)
 X = torch.randn(n, d, dtype=torch.float64, device='cuda', generator=g)
-y = torch.randn(n, dtype=torch.float64, device='cuda', generator=g)
+B = torch.as_tensor(np.linalg.qr(np.random.RandomState(0).standard_normal((d, 3)))[0], device='cuda')
+y = torch.tanh(X @ B).sum(1) + 0.05 * torch.randn(n, dtype=torch.float64, device='cuda', generator=g)
 Z = X[:m].cpu().numpy()
 ell = np.sqrt(d) * (1 + 0.5 * np.random.RandomState(1).uniform(size=d))
-order = []
-class T(ops._Timed):
-    def __enter__(self):
-        self.e0 = torch.cuda.Event(enable_timing=True); self.e0.record()
-    def __exit__(self, *a):
-        e1 = torch.cuda.Event(enable_timing=True); e1.record(); order.append((self.name, self.e0, e1)); return False
-ops._Timed = T
+
+
 def sweep():
-    est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True, method='fixed', noise_var=0.1, chunk_rows=524288, deferred_checks=True).fit(X, y)
+    est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True,
+                                            method='fixed', noise_var=0.1, chunk_rows=524288, deferred_checks=True).fit(X, y)
     _, C = est.estimator_.gradient_gram(want_G=False, check=False)
     tr = eb.GramEighTransformer(n_components=3).fit_gram(C, n)
     est.estimator_.finish_checks()
     return tr.components_
-for _ in range(3): sweep()
-torch.cuda.synchronize(); order.clear()
-s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-s0.record(); sweep(); s1.record(); torch.cuda.synchronize()
-print('total %.3f ms' % s0.elapsed_time(s1))
-prev = s0; pname = 'start'
-for name, a, b in order:
-    print('gap %-16s -> %-16s %.3f ms   | %-16s %.3f ms' % (pname, name, prev.elapsed_time(a), name, a.elapsed_time(b)))
-    prev, pname = b, name
-print('gap %-16s -> end %.3f ms' % (pname, prev.elapsed_time(s1)))
+
+
+for _ in range(5):
+    sweep()
+torch.cuda.synchronize()
+reps = 20
+ops.start_timing()
+s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s0.record()
+for _ in range(reps):
+    sweep()
+s1.record()
+torch.cuda.synchronize()
+st = ops.stop_timing()
+total = s0.elapsed_time(s1) / reps
+out = {'n': n, 'd': d, 'm': m, 'total_ms': total, 'stages_ms': {k: v[0] / reps for k, v in st.items()}}
+scal = sum(out['stages_ms'].get(k, 0.0) for k in ('kuf', 'inducing_stats', 'grad_gram_cached'))
+out['scalable_ms'] = scal
+out['replicated_R_ms'] = total - scal
+out['unattributed_ms'] = total - sum(out['stages_ms'].values())
+# the same without the event pairs (they cost a little themselves)
+s0.record()
+for _ in range(reps):
+    sweep()
+s1.record()
+torch.cuda.synchronize()
+out['total_ms_untimed'] = s0.elapsed_time(s1) / reps
+print(json.dumps(out))
