@@ -39,6 +39,12 @@ METRIC = "EDR fit points/sec at n=4M,d=64,m=512"
 UNIT = "points/s"
 N_TOTAL, D, M, K_TRUE = 4_000_000, 64, 512, 3
 NOISE, SF2 = 0.1, 1.0
+# BASELINE.json configs: name -> (n, d, m, chained PCA preprocessor).  The driver's default
+# run is C3, the configuration the metric is quoted on; the others are run on request (--config) and their lines are
+# kept under profiles/.
+CONFIGS = {'C1': (500, 10, 20, False), 'C2': (100_000, 32, 256, False), 'C3': (N_TOTAL, D, M, False),
+           'C4': (1_000_000, 512, 1024, False), 'C5': (16_000_000, 128, 2048, True)}
+CPU_SAMPLE_ROWS = 131072          # rows per CPU sweep of both CPU legs (cpu_baseline and --impl reference)
 
 
 def _hbm_peak_gbs():
@@ -176,30 +182,48 @@ def time_cpu(rows, d, m, steps, warmup):
     return rows / (sum(times) / len(times)), sum(times) / len(times)
 
 
+CPU_NOTE = ("CPU port of the reference path (GPy is not installable here): oracle/pipeline.py, row-chunked NumPy / "
+            "OpenBLAS in GEMM form on all host threads.  It is FASTER than the reference itself would be: GPy "
+            "evaluates the gradient with a per-dimension loop over n x m temporaries and also builds an n x n "
+            "variance-gradient term that edr-gp discards, and the reference's SVDTransformer forms an n x n U "
+            "(BASELINE.md section 2) -- neither runs at this n.")
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rows = args.cpu_rows or 131072
+    rows = min(args.cpu_rows or CPU_SAMPLE_ROWS, args.n)
     use_all_host_threads()
     cores = cpu_threads()
     pts, sec = time_cpu(rows, args.d, args.m, args.steps, args.warmup)
-    sample = "%d rows of the same generator per step (n=%d named shape), all host BLAS threads" % (rows, args.n)
-    line = {"impl": "reference", "metric": METRIC, "value": pts, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    sample = ("%d rows of the same generator per step (a bounded sample of the n=%d named shape; throughput in rows/s "
+              "is what is compared), all host BLAS threads" % (rows, args.n))
+    line = {"impl": "reference", "metric": metric_name(args), "value": pts, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "n": args.n, "d": args.d, "m": args.m,
-                       "hyperparameters": "fixed", "note": "CPU port of the reference path (GPy not installable): "
-                       "oracle/pipeline.py chunked NumPy/OpenBLAS; O(n^2) steps of the reference replaced as BASELINE.md section 2"},
+                       "rows_per_step": rows, "hyperparameters": "fixed", "note": CPU_NOTE},
             "cpu_baseline": {"value": pts, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pts, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+def metric_name(args):
+    """BASELINE.json's metric string for the configuration it is quoted on (C3); the same metric at the shape
+    actually run otherwise."""
+    if (args.n, args.d, args.m) == (N_TOTAL, D, M) and not args.pca:
+        return METRIC
+    return "EDR fit points/sec at n=%d,d=%d,m=%d%s" % (args.n, args.d, args.m, " (PCA-chained)" if args.pca else "")
+
+
 def workload_name(args):
-    return ("C3 headline: n=%d d=%d m=%d ARD-RBF sparse-GP EDR sweep at fixed hyper-parameters "
-            "(stats + solve + posterior gradients + GtG + eigh), rows sharded over ranks" % (args.n, args.d, args.m))
+    name = args.config or next((k for k, v in CONFIGS.items() if v[:3] == (args.n, args.d, args.m)), 'custom')
+    return ("%s%s: n=%d d=%d m=%d ARD-RBF sparse-GP EDR sweep at fixed hyper-parameters (%sstats + solve + posterior "
+            "gradients + GtG + eigh), rows sharded over ranks"
+            % (name, " headline" if name == 'C3' else "", args.n, args.d, args.m,
+               "StandardScaler + PCA preprocessor + " if args.pca else ""))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,10 +274,25 @@ def run_ours(args):
                                                  method='fixed', noise_var=NOISE, chunk_rows=args.chunk_rows,
                                                  deferred_checks=True, precision=precision or args.precision)
 
+    def preprocess(Xin):
+        """C5: the front of the chain on the device (edrgp/edr.py:142-176 with preprocessor=PCA): column moments
+        + standardise, centred Gram matrix on the DMMA reduction + eigh + projection (DevicePCA), all-reduced."""
+        Xd = Xin if isinstance(Xin, torch.Tensor) else torch.as_tensor(Xin, device=dev)
+        cnt = torch.tensor([float(Xd.shape[0])], dtype=torch.float64, device=dev)
+        s1 = ops.col_moments(Xd)[0].clone()
+        edist.allreduce_sum_(s1, cnt)
+        mean = s1 / cnt
+        s2 = ops.col_moments(Xd, shift=mean)[1].clone()
+        edist.allreduce_sum_(s2)
+        Xs = ops.standardize(Xd, mean, torch.sqrt(s2 / cnt))
+        return eb.DevicePCA(n_components=d).fit_transform_device(Xs)
+
     def sweep(Xin, yin, precision=None):
         """One fixed-hyper-parameter EDR sweep through the public classes.  The input validation and
         the Cholesky flag are computed on the device inside the sweep and read (and raised) once, after
         the directions have been read back: no host round trip between the row passes."""
+        if args.pca:
+            Xin = preprocess(Xin)
         est = make_estimator(precision).fit(Xin, yin)
         _, C = est.estimator_.gradient_gram(want_G=False, check=False)
         edist.allreduce_sum_(C)
@@ -308,21 +347,23 @@ def run_ours(args):
     # ---- the fused Kuf + gradient + GtG kernel on its own (north-star pipeline roofline).  The sweep
     # above feeds the gradient pass from the Kfu blocks of the statistics pass when they fit in HBM;
     # the recompute kernel is what runs for new rows and when they do not.
-    est0 = make_estimator().fit(X, y)
-    gpack = est0.estimator_._grad_pack(1.0)
-    for _ in range(2):
-        ops.grad_gram(est0.estimator_.X, gpack, want_G=False)
-    ops.start_timing()
-    for _ in range(3):
-        ops.grad_gram(est0.estimator_.X, gpack, want_G=False)
-    pa = ops.stop_timing()
-    pipe_alone_ms, pipe_alone_n = pa.get('grad_gram', (0.0, 1))
-    del est0, gpack
+    pipe_alone_ms, pipe_alone_n = 0.0, 1
+    if d + (d & 1) <= 64 and not args.pca:
+        est0 = make_estimator().fit(X, y)
+        gpack = est0.estimator_._grad_pack(1.0)
+        for _ in range(2):
+            ops.grad_gram(est0.estimator_.X, gpack, want_G=False)
+        ops.start_timing()
+        for _ in range(3):
+            ops.grad_gram(est0.estimator_.X, gpack, want_G=False)
+        pa = ops.stop_timing()
+        pipe_alone_ms, pipe_alone_n = pa.get('grad_gram', (0.0, 1))
+        del est0, gpack
 
     # ---- the same sweep in the TF32-split mode (informational; the headline above is FP64): the training
     # rows' cross-covariance on the tcgen05 tensor cores, everything downstream unchanged
     tf32_mode = None
-    if d + (d & 1) <= 64 and args.precision == 'fp64' and not args.no_tf32:
+    if d + (d & 1) <= 64 and args.precision == 'fp64' and not args.no_tf32 and not args.pca:
         for _ in range(2):
             sweep(X, y, 'tf32x3')
         ops.start_timing()
@@ -377,6 +418,20 @@ def run_ours(args):
     h2d = (n * d + n) * 8
     d2h = (K_TRUE * d + d + d * d) * 8 + 64
 
+    # ---- the same end-to-end arm from PAGEABLE NumPy arrays (what an sklearn user passes): the estimator stages
+    # them through its ring of pinned blocks (native host threads), one cudaMemcpyAsync per block
+    e2e_pageable = None
+    if not args.no_pageable:
+        Xpg, ypg = np.array(Xnp), np.array(ynp)             # plain malloc'ed copies
+        for _ in range(2):
+            sweep(Xpg, ypg)
+        pg_steps = max(1, min(args.steps, 5))
+        pg_ms, _ = timed(lambda: sweep(Xpg, ypg), pg_steps)
+        e2e_pageable = {"value": n / (pg_ms / pg_steps * 1e-3), "unit": UNIT, "ms_per_step": pg_ms / pg_steps,
+                        "steps": pg_steps, "ratio_to_pinned": (e2e_ms / e2e_steps) / (pg_ms / pg_steps),
+                        "note": "host rows in ordinary (pageable) NumPy arrays"}
+        del Xpg, ypg
+
     # ---- the public orchestrator with the reference's full semantics (informational, N = 1 only):
     # EffectiveDimensionalityReduction.fit = StandardScaler + GP fit + gradients + eigh + projection +
     # the second GP fit on the projected rows (edrgp/base.py:172-200), from the same host rows
@@ -416,11 +471,13 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        rows = args.cpu_rows or 524288
-        pts, sec = time_cpu(rows, d, m, 1, 1)
+        rows = min(args.cpu_rows or CPU_SAMPLE_ROWS, n)
+        cpu_steps = 5
+        pts, sec = time_cpu(rows, d, m, cpu_steps, 1)
         cpu = {"value": pts, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-               "sample": "%d rows of the same generator, one sweep after one warm-up (%.1f s); oracle/pipeline.py "
-                         "chunked NumPy/OpenBLAS on all host threads" % (rows, sec)}
+               "sample": "%d rows of the same generator per sweep (the sample --impl reference uses), %d sweeps after "
+                         "one warm-up (%.2f s each); oracle/pipeline.py chunked NumPy/OpenBLAS on all host threads"
+                         % (rows, cpu_steps, sec), "note": CPU_NOTE}
 
     # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of a launch of the
     # same size (524288 rows); null when the launch size differs or the capture is absent
@@ -434,7 +491,7 @@ def run_ours(args):
         pass
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if args.precision == 'fp64' else "f64 (cross-covariance contraction: tf32 x 3)", "data": "synthetic",
         "config": {"workload": workload_name(args), "n": n, "d": d, "m": m, "rows_per_rank": n_local,
@@ -446,26 +503,29 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                 "api": "SparseGaussianProcessRegressor(method='fixed').fit(X_host, y_host) -> gradient_gram -> "
-                       "GramEighTransformer.fit_gram -> components_ (host)"},
+                       "GramEighTransformer.fit_gram -> components_ (host)",
+                "host_memory": "pinned", "pageable": e2e_pageable},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (P = Kfu^T Kfu, b, yy; symmetric DMMA reduction)",
-                     "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
+                     "achieved": syrk_tf_exec, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf_exec / peak if peak else None,
+                     "flops_counted": "EXECUTED by the kernel: the upper triangle of P only (full 128 x 128 tiles above "
+                                      "the diagonal, 8 x 8 blocks on it) = %.1f %% of the algorithmic 2 m^2 + 2 m per row; "
+                                      "this is the pipe-utilisation figure ncu's sm__pipe_tensor_subpipe_dmma reports"
+                                      % (100.0 * fl['syrk_executed'] / fl['syrk']),
+                     "achieved_algorithmic": syrk_tf, "frac_algorithmic": syrk_tf / peak if peak else None,
+                     "algorithmic_note": "SURVEY 8d counts 2 m^2 + 2 m flops per row with the symmetric half NOT "
+                                         "discounted; against that count the kernel reads above 1 by construction",
                      "traffic": traffic,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 524288-row launch (ncu --set full, "
-                                     "profiles/r01_ncu_top_kernels_final.txt); algorithmic bytes per launch = 2.15 GB (the Kfu "
-                                     "block once): each column slab is read by several tiles, L2 absorbs about half of the re-reads",
-                     "achieved_executed": syrk_tf_exec, "frac_executed": syrk_tf_exec / peak if peak else None,
+                     "traffic_source": "recorded: dram__bytes_read.sum + dram__bytes_write.sum of one 524288-row launch "
+                                       "(ncu --set full, profiles/r01_ncu_top_kernels_final.txt); null when this run's "
+                                       "launch size differs.  Algorithmic bytes per launch = 2.15 GB (the Kfu block "
+                                       "once): each column slab is read by several tiles, L2 absorbs about half",
                      "peak_live": peak_live, "peak_recorded": peak_recorded,
                      "peak_source": "measured FP64 DMMA (mma.sync m8n8k4 f64) peak of this pool's B200: the larger of "
                                     "the live probe in this process (edrgp_fp64_probe, CUDA events) and the standalone "
                                     "microbenchmark recorded in profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has "
                                     "no FP64 figure",
-                     "note": "achieved counts the ALGORITHMIC 2 m^2 + 2 m flops per row as SURVEY 8d prescribes "
-                             "(symmetry NOT discounted), so frac exceeds 1 by construction: the kernel computes only "
-                             "the upper triangle (full tiles above the diagonal, 8 x 8 blocks on it) = 50.9 % of those "
-                             "flops at m = 512; achieved_executed / frac_executed count the DMMA flops actually "
-                             "issued and are the pipe-utilisation figure (ncu sm__pipe_tensor_subpipe_dmma)",
                      "avg_launch_ms": syrk_avg_ms, "launches": syrk_n, "share_of_step": syrk_ms / total_ms},
         "roofline_pipeline": {"bound": "tensor", "kernel": "grad_gram_kernel (fused Kuf + gradient + GtG)",
                               "achieved": pipe_tf, "peak": peak, "unit": "TFLOP/s",
@@ -514,9 +574,15 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-edr', action='store_true')
     ap.add_argument('--no-tf32', action='store_true', help="skip the informational TF32-split arm")
+    ap.add_argument('--no-pageable', action='store_true', help="skip the pageable-host-memory end-to-end leg")
+    ap.add_argument('--config', default=None, choices=sorted(CONFIGS), help="a BASELINE.json configuration (default: C3)")
+    ap.add_argument('--pca', action='store_true', help="run the StandardScaler + DevicePCA front of the chain inside the step")
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32x3'],
                     help="arithmetic of the cross-covariance pass (the headline is fp64)")
     args = ap.parse_args()
+    if args.config:
+        args.n, args.d, args.m, pca = CONFIGS[args.config]
+        args.pca = args.pca or pca
     if args.impl == 'reference':
         run_reference(args)
     else:

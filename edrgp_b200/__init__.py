@@ -9,5 +9,5 @@ __version__ = '0.1.0'
 
 from .gp_model import SparseGaussianProcessRegressor          # noqa: F401
 from .transformer import GramEighTransformer, DevicePCA       # noqa: F401
-from .edr import EffectiveDimensionalityReduction, EDR        # noqa: F401
+from .edr import EffectiveDimensionalityReduction, EDR, BlockEDR   # noqa: F401
 from .utils import discrepancy, subspace_variance_ratio_from_gram   # noqa: F401

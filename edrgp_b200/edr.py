@@ -321,9 +321,52 @@ class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):
     # ------------------------------------------------------------------------------------------
     @property
     def _first_gradients_(self):
+        """Host copy of the first iteration's gradients (edrgp/base.py:161).  With several ranks every rank holds
+        only ITS rows: that is what this returns, with a warning -- use ``first_gradients_rows`` for rows of the
+        whole data set, or ``refit``, which gathers what it needs."""
         if getattr(self, '_first_gradients_dev', None) is None:
             raise AttributeError("first gradients were not kept (keep_gradients=False)")
+        if dist.is_distributed():
+            warnings.warn("_first_gradients_ holds this rank's %d rows only (the gradients are sharded over %d ranks); "
+                          "first_gradients_rows(rows) gathers rows of the whole data set"
+                          % (self._first_gradients_dev.shape[0], dist.world_size()), RuntimeWarning)
         return self._first_gradients_dev.cpu().numpy()
+
+    def _row_offsets(self):
+        """(first global row of this rank, global row count) of the row-sharded gradients."""
+        sizes = torch.zeros(dist.world_size(), dtype=F64, device='cuda')
+        sizes[dist.rank()] = float(self._n_local)
+        dist.allreduce_sum_(sizes)
+        sizes = sizes.cpu().numpy()
+        return int(round(sizes[:dist.rank()].sum())), int(round(sizes.sum()))
+
+    def first_gradients_rows(self, rows=None, max_rows=None, seed=0):
+        """Rows of the first iteration's gradients by GLOBAL row index, gathered to every rank as a host array
+        (k, d).  ``rows=None``: all rows, or -- when ``max_rows`` is given and smaller -- a seeded uniform subsample
+        without replacement (sorted).  Returns ``(G_rows, rows)``.  Collective: every rank calls it alike."""
+        if getattr(self, '_first_gradients_dev', None) is None:
+            raise AttributeError("first gradients were not kept (keep_gradients=False)")
+        G = self._first_gradients_dev
+        lo, n = (0, G.shape[0]) if not dist.is_distributed() else self._row_offsets()
+        if rows is None:
+            rows = np.arange(n)
+            if max_rows is not None and n > max_rows:
+                rows = np.sort(np.random.RandomState(seed).choice(n, size=int(max_rows), replace=False))
+        else:
+            rows = np.asarray(rows)
+            if rows.dtype == bool:
+                rows = np.nonzero(rows)[0]
+            rows = np.where(rows < 0, rows + n, rows)
+        if not dist.is_distributed():
+            idx = torch.as_tensor(rows, device=G.device)
+            return G[idx].cpu().numpy(), rows
+        out = torch.zeros(len(rows), G.shape[1], dtype=F64, device=G.device)
+        local = rows - lo
+        mine = np.nonzero((local >= 0) & (local < G.shape[0]))[0]
+        if mine.size:
+            out[torch.as_tensor(mine, device=G.device)] = G[torch.as_tensor(local[mine], device=G.device)]
+        dist.allreduce_sum_(out)                      # every row is owned by exactly one rank
+        return out.cpu().numpy(), rows
 
     @property
     def subspace_gradients_(self):
@@ -338,22 +381,39 @@ class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):
     def _recovered_gradients_(self):
         return np.dot(self.subspace_gradients_, self._components_fit_space)
 
-    def refit(self, refit_transformer, rows=None):
+    def refit(self, refit_transformer, rows=None, max_rows=1_000_000):
         """New components from the gradients kept at fit time (edrgp/edr.py:115-140,
-        edrgp/base.py:202-239).  ``refit_transformer`` is any host transformer (e.g. SparsePCA)."""
+        edrgp/base.py:202-239).  ``refit_transformer`` is any transformer with ``fit`` + ``components_``.
+
+        * A transformer with ``fit_gram`` (``GramEighTransformer``) and ``rows=None`` is fitted from the Gram matrix of
+          ALL gradients, which the fit has already reduced over rows and ranks: nothing is gathered.
+        * A host transformer (e.g. ``SparsePCA``) needs rows: ``rows`` (global indices) if given, all rows if they are
+          at most ``max_rows``, else a seeded uniform subsample of ``max_rows`` rows -- announced by a warning.  With
+          several ranks the rows are gathered to every rank and every rank fits the same transformer (so give it a
+          ``random_state``); the subspace variance is always taken against the rows the transformer saw."""
         check_is_fitted(self, 'components_')
-        index = slice(None) if rows is None else rows
-        grads = self._first_gradients_[index, :]
         self.refit_transformer_ = clone(refit_transformer)
         if hasattr(self.refit_transformer_, 'fit_gram') and rows is None:
-            self.refit_transformer_.fit_gram(self._first_gram_, grads.shape[0])
+            cnt = torch.tensor([float(self._n_local)], dtype=F64, device='cuda')
+            dist.allreduce_sum_(cnt)
+            self.refit_transformer_.fit_gram(self._first_gram_, int(round(float(cnt[0]))))
+            C = self._first_gram_
         else:
+            grads, used = self.first_gradients_rows(rows, max_rows=max_rows if rows is None else None)
+            if rows is None and dist.is_distributed():
+                total = self._row_offsets()[1]
+            else:
+                total = self._first_gradients_dev.shape[0]
+            if rows is None and len(used) < total:
+                warnings.warn("refit: the host transformer is fitted on a seeded subsample of %d of %d gradient rows "
+                              "(max_rows=%d)" % (len(used), total, max_rows), RuntimeWarning)
+            self.refit_rows_ = used
             self.refit_transformer_.fit(grads)
+            C = grads.T.dot(grads)
         self._check_transformer(self.refit_transformer_)
         comps = deepcopy(self.refit_transformer_.components_)
         comps = _l2_normalize(comps, axis=1)
         comps = self._remove_zero_components(comps)
-        C = self._first_gram_ if rows is None else grads.T.dot(grads)
         (self.refit_subspace_variance_,
          self.refit_subspace_variance_ratio_) = subspace_variance_ratio_from_gram(C, comps.T)
         self.refit_components_ = np.dot(comps, self._reverse_scaling_) if self.normalize else comps
@@ -408,3 +468,131 @@ class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):
 
 
 EDR = EffectiveDimensionalityReduction
+
+
+class BlockEDR(EffectiveDimensionalityReduction):
+    """Block effective dimensionality reduction (``edrgp.base.BlockEDR``, edrgp/base.py:520-766): one transformer
+    per block of features, fitted on the block's columns of the gradients, merged into block-diagonal components.
+
+    The gradients of a block's columns have the Gram matrix ``C[cols, cols]``, so with a ``fit_gram`` transformer
+    (``GramEighTransformer``) every block is a small eigenproblem on a diagonal block of the d x d Gram matrix the
+    fused gradient kernel has already reduced over rows and ranks; other transformers are
+    fitted on the gathered gradient rows.  Like the reference class it is one-shot (no ``step``) and works on the
+    rows as given (no scaling, no preprocessor).
+
+    Parameters: ``estimator``, ``transformer``, ``n_components`` (None, an int, or a list with one entry per
+    block), ``blocks`` (list of lists of column indices; None = one block of all columns)."""
+
+    def __init__(self, estimator=None, transformer=None, n_components=None, blocks=None, keep_gradients=True):
+        self.estimator = estimator
+        self.transformer = transformer
+        self.n_components = n_components
+        self.blocks = blocks
+        self.keep_gradients = keep_gradients
+
+    # the parent's fit machinery reads these (``transformer`` is a read-only alias there; here it is the parameter)
+    transformer = None
+    dr_transformer = property(lambda self: self.transformer)
+    step = None
+    normalize = False
+    preprocessor = None
+
+    def _check_init(self, n_features):
+        if self.estimator is None:
+            raise ValueError("Estimator should be speciified")
+        if self.transformer is None:
+            raise ValueError("transformer should be specified")
+        self.n_components_ = n_features if self.n_components is None else self.n_components
+
+    def _make_blocks(self, n_features):                       # edrgp/base.py:735-766
+        if self.blocks is None:
+            if isinstance(self.n_components_, (int, np.integer)):
+                self.blocks_ = [{'columns': np.arange(n_features), 'n_components': int(self.n_components_)}]
+            else:
+                raise ValueError("blocks should be specified if n_components is list")
+        elif isinstance(self.blocks, list):
+            if isinstance(self.n_components_, list):
+                self.blocks_ = [{'columns': np.asarray(b), 'n_components': k}
+                                for b, k in zip(self.blocks, self.n_components_)]
+            else:
+                # (the reference takes max(n_components, len(block)): an int keeps every direction of every block)
+                self.blocks_ = [{'columns': np.asarray(b), 'n_components': max(int(self.n_components_), len(b))}
+                                for b in self.blocks]
+        else:
+            raise ValueError("blocks should be None or a list of lists of column indices")
+        return self
+
+    def _fit_block(self, transformer, C, block, grads=None):
+        transformer.set_params(n_components=block['n_components'])
+        cols = block['columns']
+        if hasattr(transformer, 'fit_gram'):
+            transformer.fit_gram(C[np.ix_(cols, cols)], self._n_total)
+        else:
+            transformer.fit(grads[:, cols])
+        self._check_transformer(transformer)
+        return transformer.components_.T
+
+    def _merge_components(self, components, n_features):      # edrgp/base.py:654-680
+        eff = sum(c.shape[1] for c in components)
+        out = np.zeros((n_features, eff))
+        start = 0
+        for blk, comp in zip(self.blocks_, components):
+            stop = start + comp.shape[1]
+            out[blk['columns'], start:stop] = comp
+            blk['components'] = np.arange(start, stop)
+            start = stop
+        return out.T
+
+    def _fit_iterations(self, Xp, yd, **opt_kws):
+        n_features = Xp.shape[1]
+        self._check_init(n_features)
+        self._make_blocks(n_features)
+        self.components_ = None
+        self.num_iter = 0
+        self._first_gram_ = None
+        self._first_gradients_dev = None
+        cnt = torch.tensor([float(self._n_local)], dtype=F64, device='cuda')
+        dist.allreduce_sum_(cnt)
+        self._n_total = int(round(float(cnt[0])))
+        self._fit_estimator(Xp, yd, **opt_kws)
+        fused = hasattr(self.transformer, 'fit_gram')
+        G, C = self._gradient_gram(self.keep_gradients or not fused)
+        self._first_gram_ = C
+        self._first_gradients_dev = G if self.keep_gradients else None
+        grads = None
+        if not fused:
+            self._first_gradients_dev = G
+            grads = self.first_gradients_rows(None)[0]
+            if not self.keep_gradients:
+                self._first_gradients_dev = None
+        self.transformer_ = clone(self.transformer)
+        comps = [self._fit_block(clone(self.transformer), C, blk, grads) for blk in self.blocks_]
+        self.components_ = self._merge_components(comps, n_features)
+        X_proj = self._project_rows(Xp)
+        self.num_iter += 1
+        self._last_fit(X_proj, yd, **opt_kws)
+
+    def refit(self, refit_transformer, rows=None, params=None, max_rows=1_000_000):
+        """Per-block refit on the kept gradients (edrgp/base.py:682-733); ``params``: one dict of extra transformer
+        parameters per block."""
+        check_is_fitted(self, 'components_')
+        self._make_blocks(self._first_gram_.shape[0])
+        self.refit_transformer_ = clone(refit_transformer)
+        fused = hasattr(refit_transformer, 'fit_gram') and rows is None
+        if fused:
+            grads, C = None, self._first_gram_
+        else:
+            grads, self.refit_rows_ = self.first_gradients_rows(rows, max_rows=max_rows if rows is None else None)
+            C = grads.T.dot(grads)
+        comps = []
+        for i, blk in enumerate(self.blocks_):
+            tr = clone(refit_transformer)
+            if params is not None and params[i] is not None:
+                tr.set_params(**params[i])
+                blk = dict(blk, n_components=params[i].get('n_components', blk['n_components']))
+            comps.append(self._fit_block(tr, C, blk, grads))
+        merged = _l2_normalize(self._merge_components(comps, C.shape[0]))
+        self.refit_components_ = self._remove_zero_components(merged)
+        (self.refit_subspace_variance_,
+         self.refit_subspace_variance_ratio_) = subspace_variance_ratio_from_gram(C, self.refit_components_.T)
+        return self

@@ -152,3 +152,41 @@ def test_cuda_edr_surface_matches_reference_values(path):
     _check_fit(edr, g, c)
     _check_refit(edr, g, c, lambda k: eb.GramEighTransformer(n_components=k))
     _check_refit(edr, g, c, lambda k: EconomySVDTransformer(n_components=k))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("transformer", ["gram", "host"])
+def test_block_edr_matches_reference_block_edr(reference_edrgp, transformer):
+    """``BlockEDR`` (eigh on diagonal blocks of the reduced Gram matrix) against the UNMODIFIED reference class
+    (edrgp/base.py:520-766) driven with the oracle estimator and the reference's SVDTransformer."""
+    import numpy.matlib  # noqa: F401  (the reference calls np.matlib.repmat without importing it)
+    import edrgp_b200 as eb
+    from edrgp.base import BlockEDR as ReferenceBlockEDR
+    from edrgp.utils import SVDTransformer as ReferenceSVD
+    from oracle.estimator import SparseGaussianProcessRegressor as OracleSGPR
+    from oracle.reference_loop import EconomySVDTransformer
+    g = np.load([p for p in GOLDEN if 'small_adaptive' in p][0])
+    X, y = g['X'], g['y']                                    # (300, 6)
+    blocks, ncomp = [[0, 1, 2], [3, 4, 5]], [1, 2]
+    np.random.seed(21)
+    ref = ReferenceBlockEDR(OracleSGPR('RBF', {'ARD': True}, num_inducing=15), ReferenceSVD(), n_components=ncomp,
+                            blocks=[list(b) for b in blocks])
+    ref.fit(X, y, max_iters=0)
+    np.random.seed(21)
+    tr = eb.GramEighTransformer() if transformer == "gram" else EconomySVDTransformer()
+    edr = eb.BlockEDR(eb.SparseGaussianProcessRegressor('RBF', {'ARD': True}, num_inducing=15), tr, n_components=ncomp,
+                      blocks=[list(b) for b in blocks])
+    edr.fit(X, y, max_iters=0)
+    assert edr.components_.shape == ref.components_.shape == (3, 6)
+    assert np.all(edr.components_[0, 3:] == 0) and np.all(edr.components_[1:, :3] == 0)      # block diagonal
+    assert _same_up_to_row_signs(edr.components_, ref.components_, 1e-6)
+    assert np.allclose(edr.subspace_variance_ratio_, ref.subspace_variance_ratio_, rtol=1e-7)
+    assert np.allclose(edr.subspace_variance_, ref.subspace_variance_, rtol=1e-7)
+    assert _rel(edr._first_gradients_, ref._first_gradients_) < 1e-8
+    ll, ll_ref = (float(e.estimator_.estimator_.log_likelihood()[0, 0]) for e in (edr, ref))
+    assert abs(ll - ll_ref) < 1e-8 * abs(ll_ref)
+    # per-block refit
+    ref.refit(ReferenceSVD())
+    edr.refit(eb.GramEighTransformer() if transformer == "gram" else EconomySVDTransformer())
+    assert _same_up_to_row_signs(edr.refit_components_, ref.refit_components_, 1e-6)
+    assert np.allclose(edr.refit_subspace_variance_ratio_, ref.refit_subspace_variance_ratio_, rtol=1e-7)
