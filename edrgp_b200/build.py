@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libedrgp_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared']
 
 
 def sources():

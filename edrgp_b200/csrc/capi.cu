@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "launch.h"
 #include "sweep.h"
+#include "h2d.h"
 
 namespace edrgp {
 static std::atomic<uint64_t> g_launches{0};
@@ -584,6 +585,32 @@ int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, voi
   cudaError_t e = edrgp::launch_eigh(res + d + (size_t)d * d, d, c.at(edrgp::FS_SCRATCH), res, res + d, nullptr,
                                      (cudaStream_t)stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "fixed_eigh");
+}
+
+void* edrgp_h2d_open(const void* host, void* dev, int64_t rows, size_t row_bytes, size_t dst_pitch, int64_t block_rows,
+                     int threads, int slots, void* order_after_stream) {
+  if (!host || !dev || rows <= 0 || row_bytes == 0 || dst_pitch < row_bytes || block_rows <= 0) {
+    fail(EDRGP_ERR_ARG, "h2d_open: bad argument");
+    return nullptr;
+  }
+  cudaError_t e = cudaSuccess;
+  edrgp::H2DTransfer* t = edrgp::h2d_open(host, dev, rows, row_bytes, dst_pitch, block_rows, threads, slots,
+                                          (cudaStream_t)order_after_stream, &e);
+  if (!t) cuda_fail(e, "h2d_open");
+  return t;
+}
+
+int edrgp_h2d_wait(void* handle, int64_t upto_row, int64_t ahead_rows, void* consumer_stream) {
+  if (!handle) return fail(EDRGP_ERR_ARG, "h2d_wait: bad argument");
+  cudaError_t e = edrgp::h2d_wait((edrgp::H2DTransfer*)handle, upto_row, ahead_rows, (cudaStream_t)consumer_stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "h2d_wait");
+}
+
+int edrgp_h2d_staged(void* handle) { return handle && edrgp::h2d_staged((const edrgp::H2DTransfer*)handle) ? 1 : 0; }
+
+int edrgp_h2d_close(void* handle) {
+  edrgp::h2d_close((edrgp::H2DTransfer*)handle);
+  return EDRGP_OK;
 }
 
 int edrgp_timing_begin(void) {

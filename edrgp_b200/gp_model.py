@@ -20,6 +20,22 @@ from . import model as _model
 _KERNELS = {'RBF': _model.RBF, 'rbf': _model.RBF}
 
 
+def _host_copy_threads():
+    """Host threads that stage pageable rows into pinned blocks: the CPUs this process may use, shared fairly
+    between the ranks of this node, one left for the thread that drives the GPU; at most 8 (memcpy saturates the
+    memory channels well before that)."""
+    import os
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cpus = os.cpu_count() or 1
+    local = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    env = os.environ.get('EDRGP_H2D_THREADS')
+    if env:
+        return max(1, int(env))
+    return max(1, min(8, cpus // local - 1))
+
+
 class _BaseGP(BaseEstimator):
     """Common estimator logic (mirrors ``edrgp/gp_model/base.py:_BaseGP``)."""
 
@@ -211,61 +227,70 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
 
         if isinstance(X, torch.Tensor):
             return _model.SparseGPRegression(X, y, pre_sync_check=lambda scan=True: nonfinite_check(X, y, scan), **kw)
-        # Host rows: copy them block by block on a side stream while the statistics pass already
-        # works on the blocks that have arrived; the non-finite scan (sklearn's check_X_y) runs on the
-        # device once the last block is in, before the first host read-back.
+        # Host rows: the library's streamer (edrgp_h2d_*) moves them block by block while the statistics pass already
+        # works on the blocks that have arrived -- straight from the caller's buffer when it is pinned, through a ring
+        # of pinned blocks filled by host threads when it is ordinary (pageable) memory; the non-finite scan
+        # (sklearn's check_X_y) runs on the device, before the first host read-back.
+        from . import _lib
+        lib = _lib.load()
         n, d = X.shape
         dev = torch.device('cuda', torch.cuda.current_device())
         de = d + (d & 1)
         Xd = torch.zeros(n, de, dtype=torch.float64, device=dev) if de != d else \
             torch.empty(n, d, dtype=torch.float64, device=dev)
-        Xh = torch.from_numpy(X)
-        yh = torch.from_numpy(y)
-        yd = torch.empty(yh.shape, dtype=torch.float64, device=dev)
-        copy_stream = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)                       # Xd's allocation / zero fill
+        yd = torch.empty(y.shape, dtype=torch.float64, device=dev)
+        main = torch.cuda.current_stream(dev).cuda_stream
         # copy granularity: a quarter of chunk_rows (the size of the statistics blocks while the rows are
-        # arriving, see SparseGPRegression._chunks); the look-ahead below stays one full chunk_rows
+        # arriving, see SparseGPRegression._chunks); a pinned source is enqueued one chunk_rows ahead of its consumer
         rows = int(max(1024, min(self.chunk_rows // 4 if self.chunk_rows >= 65536 else self.chunk_rows, max(n, 1))))
         rows &= ~1
         ahead = int(max(rows, min(self.chunk_rows, max(n, 1))))
-        events = []                                         # (end row, event), in row order
-        state = {'next': 0, 'y': None}
+        threads = _host_copy_threads()
+        state = {'x': None, 'y': None, 'closed': False}
+
+        def start():
+            # opened at the first request, i.e. AFTER the model has uploaded its hyper-parameters and inducing
+            # inputs: the copy engine serves its queue in order
+            if state['x'] is None and not state['closed']:
+                state['x'] = lib.edrgp_h2d_open(X.ctypes.data, Xd.data_ptr(), n, d * 8, de * 8, rows, threads, 3, main)
+                if not state['x']:
+                    raise _lib.EdrgpError("edrgp_h2d_open failed: %s" % lib.edrgp_last_error().decode())
+                # the targets travel right behind the first X block
+                state['y'] = lib.edrgp_h2d_open(y.ctypes.data, yd.data_ptr(), n, 8, 8, n, max(1, threads // 4), 2, main)
+                if not state['y']:
+                    raise _lib.EdrgpError("edrgp_h2d_open failed: %s" % lib.edrgp_last_error().decode())
 
         def loader(s, e):
-            # enqueue copies up to one chunk_rows beyond e, then make the compute stream wait for rows < e
-            while state['next'] < n and state['next'] < e + ahead:
-                s0 = state['next']
-                e0 = min(n, s0 + rows)
-                with torch.cuda.stream(copy_stream):
-                    Xd[s0:e0, :d].copy_(Xh[s0:e0], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                events.append((s0, ev))
-                state['next'] = e0
-                if state['y'] is None:                      # the targets travel right behind the first X block
-                    with torch.cuda.stream(copy_stream):
-                        yd.copy_(yh, non_blocking=True)
-                        state['y'] = torch.cuda.Event()
-                        state['y'].record(copy_stream)
-            while events and events[0][0] < e:
-                main.wait_event(events.pop(0)[1])
+            if state['closed']:
+                return
+            start()
+            _lib.check(lib.edrgp_h2d_wait(state['x'], e, ahead, main), 'edrgp_h2d_wait')
 
         def y_loader():
-            if state['y'] is None:
-                loader(0, min(n, rows))
-            main.wait_event(state['y'])
+            if state['closed']:
+                return
+            start()
+            _lib.check(lib.edrgp_h2d_wait(state['y'], n, 0, main), 'edrgp_h2d_wait')
+
+        def close():
+            if not state['closed']:
+                state['closed'] = True
+                for k in ('x', 'y'):
+                    if state[k]:
+                        lib.edrgp_h2d_close(state[k])         # joins the copy threads, waits for the DMA
+                        state[k] = None
 
         def check(scan=True):
             loader(0, n)
             y_loader()
+            close()
             return nonfinite_check(Xd, yd, scan)
 
-        Xd.record_stream(copy_stream)
-        yd.record_stream(copy_stream)
-        return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check,
-                                         y_loader=y_loader, **kw)
+        try:
+            return _model.SparseGPRegression(Xd, yd, input_dim=d, row_loader=loader, pre_sync_check=check,
+                                             y_loader=y_loader, **kw)
+        finally:
+            close()                                  # (a no-op after a normal construction: check() has run)
 
     def _check_data(self, X, y):
         """Validation of ``check_X_y`` (edrgp/gp_model/base.py:72-91) split so that the O(n d) part

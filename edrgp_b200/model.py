@@ -252,7 +252,7 @@ class SparseGPRegression(object):
         """1-element device tensor with this rank's row count (summed over ranks by the normaliser's collective);
         created on first use -- the composite path takes the global count from its own moments table."""
         if self._cnt_dev_t is None:
-            self._cnt_dev_t = torch.tensor([float(self.n_local)], dtype=F64, device=self.device)
+            self._cnt_dev_t = torch.full((1,), float(self.n_local), dtype=F64, device=self.device)   # (a fill: no H2D)
         return self._cnt_dev_t
 
     @_cnt_dev.setter

@@ -326,6 +326,29 @@ int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const doubl
                      double* G, int64_t ldg, int64_t chunk_rows, int world, void* workspace, void* stream);
 int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host rows -> device in blocks, overlapped with the kernels that consume them.  Replaces the implicit
+ * "the arrays are already where the arithmetic runs" of the reference's fit(X, y) (edrgp/gp_model/base.py:46-91:
+ * check_X_y hands GPy a C-contiguous float64 host ndarray).
+ *   edrgp_h2d_open   starts the transfer of `rows` rows of `row_bytes` from `host` (contiguous) to `dev` (row pitch
+ *                    dst_pitch >= row_bytes) in blocks of block_rows rows, ordered after the work already enqueued on
+ *                    order_after_stream.  A pinned / registered source is copied with one cudaMemcpyAsync per block;
+ *                    an ordinary (pageable) source is staged by `threads` host threads through a ring of `slots`
+ *                    pinned blocks (kept for the next transfer), each block's DMA enqueued by the thread that
+ *                    completes it.  Returns a handle, or NULL (edrgp_last_error).
+ *   edrgp_h2d_wait   blocks the calling host thread until the blocks covering rows [0, upto_row) have been ENQUEUED,
+ *                    then makes consumer_stream wait for them (no device synchronisation).  A pinned source is
+ *                    enqueued here, up to ahead_rows beyond upto_row (the copy engine serves its queue in order: a
+ *                    transfer enqueued all at once would delay every small upload the caller makes next).
+ *   edrgp_h2d_staged 1 when the source was pageable and goes through the ring.
+ *   edrgp_h2d_close  joins the threads, waits for the copies and releases the handle; `host` must stay valid until then.
+ * ------------------------------------------------------------------------------------------- */
+void* edrgp_h2d_open(const void* host, void* dev, int64_t rows, size_t row_bytes, size_t dst_pitch, int64_t block_rows,
+                     int threads, int slots, void* order_after_stream);
+int edrgp_h2d_wait(void* handle, int64_t upto_row, int64_t ahead_rows, void* consumer_stream);
+int edrgp_h2d_staged(void* handle);
+int edrgp_h2d_close(void* handle);
+
 /* Optional per-stage timing of the composite calls (measurement aid; nothing on the product path needs it):
  * between edrgp_timing_begin and edrgp_timing_end every stage a composite call launches is bracketed by a pair of
  * CUDA events on the caller's stream; _end waits for them and adds up milliseconds and launch groups per stage

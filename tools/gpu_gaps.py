@@ -2,19 +2,28 @@
 through the public classes, the stage times the library brackets itself (edrgp_timing_begin / _end) and what is left
 over -- the rank-replicated, latency-bound remainder R = total - (kuf + stats + gradients) that limits strong scaling."""
 import json
+import os
 import sys
 import numpy as np
 import torch
 sys.path.insert(0, '.')
 import edrgp_b200 as eb
-from edrgp_b200 import model as emodel, ops
+from edrgp_b200 import dist as edist, model as emodel, ops
 
+# under torchrun: every rank holds a shard of n rows (weak: n is PER RANK here) and the collectives are live
+world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+if world > 1:
+    torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', torch.cuda.current_device()))
 n, d, m = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (500_000, 64, 512)))
-g = torch.Generator(device='cuda').manual_seed(0)
+g = torch.Generator(device='cuda').manual_seed(rank)
 X = torch.randn(n, d, dtype=torch.float64, device='cuda', generator=g)
 B = torch.as_tensor(np.linalg.qr(np.random.RandomState(0).standard_normal((d, 3)))[0], device='cuda')
 y = torch.tanh(X @ B).sum(1) + 0.05 * torch.randn(n, dtype=torch.float64, device='cuda', generator=g)
-Z = X[:m].cpu().numpy()
+Z0 = X[:m].clone()
+if world > 1:
+    torch.distributed.broadcast(Z0, 0)
+Z = Z0.cpu().numpy()
 ell = np.sqrt(d) * (1 + 0.5 * np.random.RandomState(1).uniform(size=d))
 
 
@@ -22,7 +31,8 @@ def sweep():
     est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True,
                                             method='fixed', noise_var=0.1, chunk_rows=524288, deferred_checks=True).fit(X, y)
     _, C = est.estimator_.gradient_gram(want_G=False, check=False)
-    tr = eb.GramEighTransformer(n_components=3).fit_gram(C, n)
+    edist.allreduce_sum_(C)
+    tr = eb.GramEighTransformer(n_components=3).fit_gram(C, n * world)
     est.estimator_.finish_checks()
     return tr.components_
 
@@ -52,4 +62,26 @@ for _ in range(reps):
 s1.record()
 torch.cuda.synchronize()
 out['total_ms_untimed'] = s0.elapsed_time(s1) / reps
-print(json.dumps(out))
+out['world'], out['rank'] = world, rank
+if world > 1:
+    # the collectives of a sweep on their own: CUDA events around back-to-back all-reduces of the three payloads
+    coll = {}
+    for name, count in (('table', 4 * world), ('stats', m * m + m + 1), ('gram', d * d)):
+        t = torch.zeros(count, dtype=torch.float64, device='cuda')
+        for _ in range(5):
+            torch.distributed.all_reduce(t)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(50):
+            torch.distributed.all_reduce(t)
+        s1.record()
+        torch.cuda.synchronize()
+        coll[name] = s0.elapsed_time(s1) / 50
+    out['allreduce_ms_back_to_back'] = coll
+for r in range(world):
+    if r == rank:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+if world > 1:
+    torch.distributed.destroy_process_group()
