@@ -61,13 +61,15 @@ SIGNATURES = {
     'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_fixed_layout': (_sz, [_i64, _int, _int, _i64, _int, ctypes.POINTER(ctypes.c_int64)]),
     'edrgp_fixed_begin': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _c_dp, _i64, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int,
-                                 _int, _c_dp, _c_dp]),
-    'edrgp_fixed_stats': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int, _int, _c_dp, _c_dp]),
+                                 _int, _c_dp, _i64, _c_dp, _c_dp]),
+    'edrgp_fixed_stats': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int, _int, _c_dp, _i64,
+                                 _c_dp, _c_dp]),
     'edrgp_fixed_posterior': (_int, [_c_dp, _i64, _i64, _int, _int, _dbl, _dbl, _dbl, _i64, _int, _c_dp, _c_dp]),
     'edrgp_fixed_grad': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _c_dp, _i64, _c_dp, _int, _dbl, _dbl, _c_dp, _c_dp,
                                 _i64, _i64, _int, _c_dp, _c_dp]),
     'edrgp_fixed_eigh': (_int, [_i64, _int, _int, _i64, _int, _c_dp, _c_dp]),
-    'edrgp_h2d_open': (ctypes.c_void_p, [_c_dp, _c_dp, _i64, _sz, _sz, _i64, _int, _int, _c_dp]),
+    'edrgp_h2d_open': (ctypes.c_void_p, [_c_dp, _c_dp, _i64, _sz, _sz, _i64, _int, _int, _c_dp, _c_dp, _c_dp, _sz]),
+    'edrgp_h2d_wait_side': (_int, [_c_dp, _c_dp]),
     'edrgp_h2d_wait': (_int, [_c_dp, _i64, _i64, _c_dp]),
     'edrgp_h2d_staged': (_int, [_c_dp]),
     'edrgp_h2d_close': (_int, [_c_dp]),

@@ -466,7 +466,7 @@ size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world
 
 int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
                       const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
-                      int world, void* workspace, void* stream) {
+                      int world, void* h2d, int64_t h2d_ahead, void* workspace, void* stream) {
   FixedCtx c;
   int rc = fixed_ctx("fixed_begin", n, d, m, chunk_rows, world, workspace, &c);
   if (rc) return rc;
@@ -487,11 +487,14 @@ int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const doub
   const int64_t rows = chunk_rows < n ? chunk_rows : n;
   // the first cross-covariance block does not need the targets: it goes first, so that the device is busy while
   // the host walks through the rest of this call and (multi-rank) the gather of the moments table
+  // rows (and targets) still on their way from the host: the stream waits for the blocks this call touches
+  if (h2d && (e = edrgp::h2d_wait((edrgp::H2DTransfer*)h2d, rows, h2d_ahead, st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
   {
     StageScope t(EDRGP_STAGE_KUF, st);
     if ((e = edrgp::launch_kuf(X, ldx, rows, d, c.at(edrgp::FS_PACK_K), m, sf2, Kfu, ldk, 0, nullptr, nullptr, nullptr, c.sms,
                                st, 0, c.flag())) != cudaSuccess) return cuda_fail(e, "fixed_begin");
   }
+  if (h2d && (e = edrgp::h2d_wait_side((edrgp::H2DTransfer*)h2d, st)) != cudaSuccess) return cuda_fail(e, "fixed_begin");
   StageScope t(EDRGP_STAGE_TARGETS, st);
   if ((e = edrgp::launch_target_moments(y, n, scratch, ticket, c.at(edrgp::FS_TABLE) + 4 * rank, c.sms, st)) != cudaSuccess)
     return cuda_fail(e, "fixed_begin");
@@ -499,8 +502,8 @@ int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const doub
 }
 
 int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const double* y, int m, double sf2,
-                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* workspace,
-                      void* stream) {
+                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* h2d, int64_t h2d_ahead,
+                      void* workspace, void* stream) {
   FixedCtx c;
   int rc = fixed_ctx("fixed_stats", n, d, m, chunk_rows, world, workspace, &c);
   if (rc) return rc;
@@ -520,6 +523,8 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
   for (int64_t s = 0; s < n; s += chunk_rows) {
     const int64_t rows = n - s < chunk_rows ? n - s : chunk_rows;
     double* Kc = Kfu + s * ldk;
+    if (s > 0 && h2d && (e = edrgp::h2d_wait((edrgp::H2DTransfer*)h2d, s + rows, h2d_ahead, st)) != cudaSuccess)
+      return cuda_fail(e, "fixed_stats");
     if (s > 0) {
       StageScope t(EDRGP_STAGE_KUF, st);
       if ((e = edrgp::launch_kuf(X + s * ldx, ldx, rows, d, c.at(edrgp::FS_PACK_K), m, sf2, Kc, ldk, 0, nullptr, nullptr,
@@ -588,14 +593,15 @@ int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, voi
 }
 
 void* edrgp_h2d_open(const void* host, void* dev, int64_t rows, size_t row_bytes, size_t dst_pitch, int64_t block_rows,
-                     int threads, int slots, void* order_after_stream) {
+                     int threads, int slots, void* order_after_stream, const void* side_host, void* side_dev,
+                     size_t side_bytes) {
   if (!host || !dev || rows <= 0 || row_bytes == 0 || dst_pitch < row_bytes || block_rows <= 0) {
     fail(EDRGP_ERR_ARG, "h2d_open: bad argument");
     return nullptr;
   }
   cudaError_t e = cudaSuccess;
   edrgp::H2DTransfer* t = edrgp::h2d_open(host, dev, rows, row_bytes, dst_pitch, block_rows, threads, slots,
-                                          (cudaStream_t)order_after_stream, &e);
+                                          (cudaStream_t)order_after_stream, side_host, side_dev, side_bytes, &e);
   if (!t) cuda_fail(e, "h2d_open");
   return t;
 }
@@ -604,6 +610,12 @@ int edrgp_h2d_wait(void* handle, int64_t upto_row, int64_t ahead_rows, void* con
   if (!handle) return fail(EDRGP_ERR_ARG, "h2d_wait: bad argument");
   cudaError_t e = edrgp::h2d_wait((edrgp::H2DTransfer*)handle, upto_row, ahead_rows, (cudaStream_t)consumer_stream);
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "h2d_wait");
+}
+
+int edrgp_h2d_wait_side(void* handle, void* consumer_stream) {
+  if (!handle) return fail(EDRGP_ERR_ARG, "h2d_wait_side: bad argument");
+  cudaError_t e = edrgp::h2d_wait_side((edrgp::H2DTransfer*)handle, (cudaStream_t)consumer_stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "h2d_wait_side");
 }
 
 int edrgp_h2d_staged(void* handle) { return handle && edrgp::h2d_staged((const edrgp::H2DTransfer*)handle) ? 1 : 0; }

@@ -83,6 +83,14 @@ struct H2DTransfer {
   std::condition_variable cv;
   int issued = 0;                  // blocks whose DMA and event record have been enqueued (in order)
   cudaError_t error = cudaSuccess;
+  // side payload (the targets): one contiguous buffer that travels on the SAME copy stream right behind block 0 --
+  // on a stream of its own it was served after the whole row transfer (the copy engine drained the rows' queue first)
+  const char* side_src = nullptr;
+  char* side_dst = nullptr;
+  size_t side_bytes = 0;
+  bool side_pinned = false;
+  PinnedSlot side_slot;
+  cudaEvent_t side_ev = nullptr;
 
   int64_t rows_of(int b) const { return std::min(block_rows, rows - (int64_t)b * block_rows); }
 
@@ -93,7 +101,14 @@ struct H2DTransfer {
     if (dst_pitch == row_bytes) e = cudaMemcpyAsync(to, from, (size_t)r * row_bytes, cudaMemcpyHostToDevice, copy_stream);
     else e = cudaMemcpy2DAsync(to, dst_pitch, from, row_bytes, row_bytes, (size_t)r, cudaMemcpyHostToDevice, copy_stream);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(ev[b], copy_stream);
+    if ((e = cudaEventRecord(ev[b], copy_stream)) != cudaSuccess) return e;
+    if (b == 0 && side_bytes) {
+      const void* sfrom = side_src;
+      if (!side_pinned) { std::memcpy(side_slot.ptr, side_src, side_bytes); sfrom = side_slot.ptr; }
+      if ((e = cudaMemcpyAsync(side_dst, sfrom, side_bytes, cudaMemcpyHostToDevice, copy_stream)) != cudaSuccess) return e;
+      e = cudaEventRecord(side_ev, copy_stream);
+    }
+    return e;
   }
 
   void mark_issued(int b, cudaError_t e) {
@@ -134,8 +149,17 @@ struct H2DTransfer {
   }
 };
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+  cudaGetLastError();                                   // an unregistered pointer may leave an error code behind
+  return pinned;
+}
+
 H2DTransfer* h2d_open(const void* src, void* dst, int64_t rows, size_t row_bytes, size_t dst_pitch, int64_t block_rows,
-                      int threads, int slots, cudaStream_t order_after, cudaError_t* err) {
+                      int threads, int slots, cudaStream_t order_after, const void* side_src, void* side_dst,
+                      size_t side_bytes, cudaError_t* err) {
   *err = cudaSuccess;
   auto* t = new H2DTransfer();
   t->src = (const char*)src; t->dst = (char*)dst; t->rows = rows; t->row_bytes = row_bytes; t->dst_pitch = dst_pitch;
@@ -154,10 +178,16 @@ H2DTransfer* h2d_open(const void* src, void* dst, int64_t rows, size_t row_bytes
   t->ev.resize(t->nblocks);
   for (int b = 0; b < t->nblocks && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&t->ev[b], cudaEventDisableTiming);
   if (e != cudaSuccess) { *err = e; h2d_close(t); return nullptr; }
-  cudaPointerAttributes attr{};
-  const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
-                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-  cudaGetLastError();                                   // an unregistered pointer may leave a sticky-less error behind
+  const bool pinned = is_pinned(src);
+  if (side_src && side_dst && side_bytes) {
+    t->side_src = (const char*)side_src; t->side_dst = (char*)side_dst; t->side_bytes = side_bytes;
+    t->side_pinned = is_pinned(side_src);
+    if ((e = cudaEventCreateWithFlags(&t->side_ev, cudaEventDisableTiming)) != cudaSuccess) { *err = e; h2d_close(t); return nullptr; }
+    if (!t->side_pinned) {
+      t->side_slot = g_pool.take(side_bytes);
+      if (!t->side_slot.ptr) { *err = cudaErrorMemoryAllocation; h2d_close(t); return nullptr; }
+    }
+  }
   // (a small pageable source is not worth threads: the driver's own bounce buffer moves it in microseconds)
   t->staged = !pinned && (size_t)rows * row_bytes > ((size_t)4 << 20);
   // A pinned source is enqueued by h2d_wait itself, a bounded number of rows ahead of the consumer: the copy engine
@@ -201,6 +231,13 @@ cudaError_t h2d_wait(H2DTransfer* t, int64_t upto_row, int64_t ahead_rows, cudaS
   return cudaStreamWaitEvent(consumer, t->ev[last], 0);   // the copy stream is in order: earlier blocks are covered
 }
 
+cudaError_t h2d_wait_side(H2DTransfer* t, cudaStream_t consumer) {
+  if (!t->side_bytes) return cudaSuccess;
+  cudaError_t e = h2d_wait(t, 1, 0, consumer);            // the side payload is enqueued with block 0
+  if (e != cudaSuccess) return e;
+  return cudaStreamWaitEvent(consumer, t->side_ev, 0);
+}
+
 bool h2d_staged(const H2DTransfer* t) { return t->staged; }
 
 void h2d_close(H2DTransfer* t) {
@@ -209,6 +246,8 @@ void h2d_close(H2DTransfer* t) {
   // slots go back to the pool only once their last DMA has drained
   if (!t->slots.empty() && t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   for (auto& s : t->slots) g_pool.give(s);
+  if (t->side_slot.ptr) { if (t->copy_stream) cudaStreamSynchronize(t->copy_stream); g_pool.give(t->side_slot); }
+  if (t->side_ev) cudaEventDestroy(t->side_ev);
   for (auto& e : t->ev) if (e) cudaEventDestroy(e);
   if (t->copy_stream) {
     cudaStreamSynchronize(t->copy_stream);              // a pinned source must stay valid until its copies are done

@@ -1249,6 +1249,10 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     const size_t smem = (size_t)d * ds * sizeof(double);
     // (a two-sided solver on the matrix itself was tried here: same time per step, fewer sweeps on flat spectra,
     // but its absolute rotation test does not terminate cleanly on numerically rank-deficient matrices)
+    // (the same solver on a cluster of 2 or 4 SMs -- every block owning a share of the pairs, full column copies
+    // kept coherent through distributed shared memory, one cluster barrier per step -- was built and measured in
+    // round 2: 0.88 / 0.84 ms against 0.48 ms on one SM; a cluster barrier costs ~1 600 cycles, as much as the
+    // whole step it was meant to shorten: profiles/r02_jacobi_variants.txt)
     if (jacobi_variant() < 0 && d == 64)
       jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl);
     else

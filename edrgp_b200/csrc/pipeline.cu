@@ -13,6 +13,7 @@
 // accumulators (16 x 32 per inducing tile) are turned into W in registers and fed straight back as
 // the A operand of the second GEMM by permuting its k index, so nothing but X and (optionally) G
 // touches HBM.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace edrgp {
@@ -488,6 +489,13 @@ __global__ void reduce_gram_kernel(const double* __restrict__ Cpart, int nparts,
 // -------------------------------------------------------------------------------------------------
 // K1 (+ b = Kuf y): cross-covariance tiles written to HBM
 // -------------------------------------------------------------------------------------------------
+// What keeps this kernel at ~62 % of the DMMA peak was looked for in round 2 and NOT found (profiles/r02_kuf_study.txt):
+// the data-dependent exp-table lookups were made bank-conflict free (the 40 M "bank conflicts" ncu still counts are
+// the TMA writes of the inducing tiles, not LDS wavefronts: per-instruction excess wavefronts are 3 % of the total),
+// the FP64 instruction count of the exponential went from 13 to 10, a variant with sixteen warps of 8 rows (four
+// warps per scheduler, 92 registers) ran at 60.6 % against 62.2 %, and a register-only microbenchmark shows that two
+// warps per scheduler saturate the pipe even with ONE accumulator chain each (tools/dmma_chain.cu), so neither
+// occupancy nor accumulator dependencies are the limiter.  DMMA + FP64 pipe time add up to 74 % of the cycles.
 // SIMPLE: entries are stored, nothing is multiplied in and no Kfu^T y is accumulated -- the statistics
 // pass.  Its tile loop is software pipelined: the exp + store of inducing tile t is interleaved, at
 // source level and branch-free, with the distance contraction of tile t + 1, so that the DMMA pipe

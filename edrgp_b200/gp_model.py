@@ -246,18 +246,16 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
         rows &= ~1
         ahead = int(max(rows, min(self.chunk_rows, max(n, 1))))
         threads = _host_copy_threads()
-        state = {'x': None, 'y': None, 'closed': False}
+        state = {'x': None, 'closed': False}
 
         def start():
             # opened at the first request, i.e. AFTER the model has uploaded its hyper-parameters and inducing
-            # inputs: the copy engine serves its queue in order
+            # inputs (the copy engine serves its queue in order); the targets travel on the same copy stream right
+            # behind the first block of rows
             if state['x'] is None and not state['closed']:
-                state['x'] = lib.edrgp_h2d_open(X.ctypes.data, Xd.data_ptr(), n, d * 8, de * 8, rows, threads, 3, main)
+                state['x'] = lib.edrgp_h2d_open(X.ctypes.data, Xd.data_ptr(), n, d * 8, de * 8, rows, threads, 3, main,
+                                                y.ctypes.data, yd.data_ptr(), n * 8)
                 if not state['x']:
-                    raise _lib.EdrgpError("edrgp_h2d_open failed: %s" % lib.edrgp_last_error().decode())
-                # the targets travel right behind the first X block
-                state['y'] = lib.edrgp_h2d_open(y.ctypes.data, yd.data_ptr(), n, 8, 8, n, max(1, threads // 4), 2, main)
-                if not state['y']:
                     raise _lib.EdrgpError("edrgp_h2d_open failed: %s" % lib.edrgp_last_error().decode())
 
         def loader(s, e):
@@ -266,19 +264,25 @@ class SparseGaussianProcessRegressor(_BaseGP, RegressorMixin):
             start()
             _lib.check(lib.edrgp_h2d_wait(state['x'], e, ahead, main), 'edrgp_h2d_wait')
 
+        def handle():
+            """The streamer's handle for the composite sweep calls, which wait block by block themselves."""
+            start()
+            return state['x']
+
+        loader.handle, loader.rows, loader.ahead = handle, rows, ahead
+
         def y_loader():
             if state['closed']:
                 return
             start()
-            _lib.check(lib.edrgp_h2d_wait(state['y'], n, 0, main), 'edrgp_h2d_wait')
+            _lib.check(lib.edrgp_h2d_wait_side(state['x'], main), 'edrgp_h2d_wait_side')
 
         def close():
             if not state['closed']:
                 state['closed'] = True
-                for k in ('x', 'y'):
-                    if state[k]:
-                        lib.edrgp_h2d_close(state[k])         # joins the copy threads, waits for the DMA
-                        state[k] = None
+                if state['x']:
+                    lib.edrgp_h2d_close(state['x'])           # joins the copy threads, waits for the DMA
+                    state['x'] = None
 
         def check(scan=True):
             loader(0, n)

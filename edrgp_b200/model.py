@@ -365,7 +365,8 @@ class SparseGPRegression(object):
     def _fixed_path_ok(self, need_grad):
         """The composite C-level sweep (``edrgp_fixed_*``) covers the fixed-hyper-parameter evaluation in FP64 for
         even d <= 64 with the rows resident and the whole Kfu kept in HBM."""
-        return (not need_grad and self.precision == 'fp64' and self._row_loader is None
+        loader = self._row_loader                 # host rows still arriving: fine if the loader exposes the native handle
+        return (not need_grad and self.precision == 'fp64' and (loader is None or hasattr(loader, 'handle'))
                 and self._Kcache is not None and ops.FixedSweep.supported(self.d_even, self.n_local)
                 and (self.normalizer is None or isinstance(self.normalizer, Standardize))
                 and self.chunk_rows % 2 == 0)
@@ -374,19 +375,21 @@ class SparseGPRegression(object):
         """Pass 1 + posterior through the composite calls: one C call per stretch between two collectives."""
         m = self.num_inducing
         fs = self._fixed
-        if fs is None or (fs.n, fs.d, fs.m, fs.chunk, fs.world) != (self.n_local, self.d_even, m, self.chunk_rows,
-                                                                    dist.world_size()):
-            fs = self._fixed = ops.FixedSweep.acquire(self.n_local, self.d_even, m, self.chunk_rows, dist.rank(),
+        # rows still arriving from the host (the estimator's streamer): the calls wait for them block by block, in
+        # blocks of the streamer's own size (a quarter of chunk_rows: the first kernel starts after the first block)
+        loader = self._row_loader
+        chunk = self.chunk_rows if loader is None else min(self.chunk_rows, max(2, loader.rows & ~1))
+        h2d, ahead = (loader.handle(), loader.ahead) if loader is not None else (None, 0)
+        if fs is None or (fs.n, fs.d, fs.m, fs.chunk, fs.world) != (self.n_local, self.d_even, m, chunk, dist.world_size()):
+            fs = self._fixed = ops.FixedSweep.acquire(self.n_local, self.d_even, m, chunk, dist.rank(),
                                                       dist.world_size(), self.device)
             weakref.finalize(self, ops.FixedSweep.release, fs)
-        if self._y_loader is not None:
-            self._y_loader()
-            self._y_loader = None
+        self._y_loader = None                      # (the calls wait for the targets themselves)
         normalize = self._Y_normalized is None and self.normalizer is not None
         y_in = self._Y_raw if self._Y_normalized is None else self._Y_normalized
-        fs.begin(self.X, y_in, self._Z_dev, self._ell_dev, sf2, self._Kcache)
+        fs.begin(self.X, y_in, self._Z_dev, self._ell_dev, sf2, self._Kcache, h2d, ahead)
         dist.allreduce_sum_(fs.table)
-        fs.stats_pass(self.X, y_in, sf2, self._Kcache, normalize)
+        fs.stats_pass(self.X, y_in, sf2, self._Kcache, normalize, h2d, ahead)
         if self._Y_normalized is None:
             if normalize:
                 norm = self.normalizer
@@ -402,7 +405,7 @@ class SparseGPRegression(object):
         fs.posterior(self._Z_dev, sf2, CONST_JITTER, beta)
         self.alpha = fs.alpha
         self._fixed_live = True
-        nblk = (self.n_local + self.chunk_rows - 1) // self.chunk_rows
+        nblk = (self.n_local + chunk - 1) // chunk
         self.kernel_launches += 6 + 3 * nblk + 4 + (m + 31) // 32
         self._enqueue_checks()
 

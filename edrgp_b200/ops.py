@@ -619,19 +619,20 @@ class FixedSweep(object):
     def _common(self):
         return self.chunk, self.world, _ptr(self.ws), _stream()
 
-    def begin(self, X, y, Z, ell, sf2, Kfu):
+    def begin(self, X, y, Z, ell, sf2, Kfu, h2d=None, h2d_ahead=0):
+        """h2d: an edrgp_h2d_open handle when X / y are still arriving from the host (the calls wait block by block)."""
         lib = _lib.load()
         _need_cuda(X, y, Z, ell, Kfu)
         _lib.check(lib.edrgp_fixed_begin(_ptr(X), X.shape[1], self.n, self.d, _ptr(y), _ptr(Z), Z.shape[1], _ptr(ell),
                                          self.m, float(sf2), self.chunk, _ptr(Kfu), Kfu.shape[1], self.rank, self.world,
-                                         _ptr(self.ws), _stream()), 'edrgp_fixed_begin')
+                                         h2d, int(h2d_ahead), _ptr(self.ws), _stream()), 'edrgp_fixed_begin')
         self.host = None
 
-    def stats_pass(self, X, y, sf2, Kfu, normalize):
+    def stats_pass(self, X, y, sf2, Kfu, normalize, h2d=None, h2d_ahead=0):
         lib = _lib.load()
         _lib.check(lib.edrgp_fixed_stats(_ptr(X), X.shape[1], self.n, self.d, _ptr(y), self.m, float(sf2), self.chunk,
-                                         _ptr(Kfu), Kfu.shape[1], int(bool(normalize)), self.world, _ptr(self.ws),
-                                         _stream()), 'edrgp_fixed_stats')
+                                         _ptr(Kfu), Kfu.shape[1], int(bool(normalize)), self.world, h2d, int(h2d_ahead),
+                                         _ptr(self.ws), _stream()), 'edrgp_fixed_stats')
 
     def posterior(self, Z, sf2, jitter, beta):
         lib = _lib.load()

@@ -307,6 +307,8 @@ int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, dou
  *   edrgp_fixed_eigh       eigh(C): RESULT = evals (d) | components (d x d) | C (d x d) | TAIL copy (4)
  *
  * TAIL word 0 holds two 32-bit integers: the non-finite flag of edrgp_kuf and the info of edrgp_posv.
+ * h2d (may be NULL): an edrgp_h2d_open handle whose rows / side payload are X / y still on their way from the host;
+ * begin and stats then make the stream wait for each row block (chunk_rows rows) right before the kernels that read it.
  * ------------------------------------------------------------------------------------------- */
 enum {
   EDRGP_FS_PACK_K = 0, EDRGP_FS_PACK_G, EDRGP_FS_YT, EDRGP_FS_STATS, EDRGP_FS_TABLE, EDRGP_FS_S, EDRGP_FS_L,
@@ -315,10 +317,10 @@ enum {
 size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int64_t* offsets);
 int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
                       const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
-                      int world, void* workspace, void* stream);
+                      int world, void* h2d, int64_t h2d_ahead, void* workspace, void* stream);
 int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const double* y, int m, double sf2,
-                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* workspace,
-                      void* stream);
+                      int64_t chunk_rows, double* Kfu, int64_t ldk, int normalize, int world, void* h2d, int64_t h2d_ahead,
+                      void* workspace, void* stream);
 int edrgp_fixed_posterior(const double* Z, int64_t ldz, int64_t n, int d, int m, double sf2, double jitter, double beta,
                           int64_t chunk_rows, int world, void* workspace, void* stream);
 int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const double* Kfu, int64_t ldk, const double* Z,
@@ -335,7 +337,9 @@ int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, voi
  *                    order_after_stream.  A pinned / registered source is copied with one cudaMemcpyAsync per block;
  *                    an ordinary (pageable) source is staged by `threads` host threads through a ring of `slots`
  *                    pinned blocks (kept for the next transfer), each block's DMA enqueued by the thread that
- *                    completes it.  Returns a handle, or NULL (edrgp_last_error).
+ *                    completes it.  side_host / side_dev / side_bytes (may be NULL / 0): one more contiguous buffer
+ *                    -- the targets -- that travels on the same copy stream right behind the first block
+ *                    (edrgp_h2d_wait_side makes a stream wait for it).  Returns a handle, or NULL (edrgp_last_error).
  *   edrgp_h2d_wait   blocks the calling host thread until the blocks covering rows [0, upto_row) have been ENQUEUED,
  *                    then makes consumer_stream wait for them (no device synchronisation).  A pinned source is
  *                    enqueued here, up to ahead_rows beyond upto_row (the copy engine serves its queue in order: a
@@ -344,7 +348,9 @@ int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, voi
  *   edrgp_h2d_close  joins the threads, waits for the copies and releases the handle; `host` must stay valid until then.
  * ------------------------------------------------------------------------------------------- */
 void* edrgp_h2d_open(const void* host, void* dev, int64_t rows, size_t row_bytes, size_t dst_pitch, int64_t block_rows,
-                     int threads, int slots, void* order_after_stream);
+                     int threads, int slots, void* order_after_stream, const void* side_host, void* side_dev,
+                     size_t side_bytes);
+int edrgp_h2d_wait_side(void* handle, void* consumer_stream);
 int edrgp_h2d_wait(void* handle, int64_t upto_row, int64_t ahead_rows, void* consumer_stream);
 int edrgp_h2d_staged(void* handle);
 int edrgp_h2d_close(void* handle);

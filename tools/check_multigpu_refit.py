@@ -18,7 +18,27 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import edrgp_b200 as eb                                   # noqa: E402
 from edrgp_b200 import dist, model                        # noqa: E402
 from edrgp_b200.utils import principal_angle              # noqa: E402
-from oracle.reference_loop import EconomySVDTransformer   # noqa: E402  (a host transformer; checker-side only)
+
+
+class EconomySVDTransformer(object):
+    """Any host transformer with fit + components_ (here: uncentred PCA by economy SVD, sklearn-clonable)."""
+
+    def __init__(self, n_components=None):
+        self.n_components = n_components
+
+    def get_params(self, deep=True):
+        return {'n_components': self.n_components}
+
+    def set_params(self, **params):
+        for key, v in params.items():
+            setattr(self, key, v)
+        return self
+
+    def fit(self, G, y=None):
+        _, _, Vh = np.linalg.svd(np.asarray(G, dtype=np.float64), full_matrices=False)
+        self.components_ = Vh[:self.n_components or Vh.shape[0]]
+        return self
+
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
