@@ -29,6 +29,8 @@
 
 namespace edrgp {
 
+void host_copy_streaming(void* dst, const void* src, size_t n);      // hostcopy.cpp: non-temporal stores
+
 namespace {
 
 struct PinnedSlot { void* ptr = nullptr; size_t bytes = 0; };
@@ -104,7 +106,7 @@ struct H2DTransfer {
     if ((e = cudaEventRecord(ev[b], copy_stream)) != cudaSuccess) return e;
     if (b == 0 && side_bytes) {
       const void* sfrom = side_src;
-      if (!side_pinned) { std::memcpy(side_slot.ptr, side_src, side_bytes); sfrom = side_slot.ptr; }
+      if (!side_pinned) { host_copy_streaming(side_slot.ptr, side_src, side_bytes); sfrom = side_slot.ptr; }
       if ((e = cudaMemcpyAsync(side_dst, sfrom, side_bytes, cudaMemcpyHostToDevice, copy_stream)) != cudaSuccess) return e;
       e = cudaEventRecord(side_ev, copy_stream);
     }
@@ -136,7 +138,7 @@ struct H2DTransfer {
       const size_t stripe = ((bytes + nworkers - 1) / nworkers + 63) & ~(size_t)63;
       const size_t lo = std::min(bytes, stripe * w), hi = std::min(bytes, lo + stripe);
       char* slot = (char*)slots[b % nslots].ptr;
-      if (hi > lo) std::memcpy(slot + lo, src + (size_t)b * block_rows * row_bytes + lo, hi - lo);
+      if (hi > lo) host_copy_streaming(slot + lo, src + (size_t)b * block_rows * row_bytes + lo, hi - lo);
       if (arrived[b].fetch_add(1, std::memory_order_acq_rel) == nworkers - 1) {
         // last stripe in: this worker hands the block to the copy engine
         {

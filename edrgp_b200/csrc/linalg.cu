@@ -1063,7 +1063,7 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
 // the default for d = 64, EDRGP_JACOBI_VARIANT=0 selects the general kernel.
 __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restrict__ C, int max_sweeps,
                                                          int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
-                                                         int* __restrict__ nlog) {
+                                                         int* __restrict__ nlog, const double* __restrict__ V0) {
   constexpr int D = 64, DS = 66, NP = 32, PER = 63, L = 16, R = 4;
   extern __shared__ double sh[];
   double* W = sh;                             // [D][DS] column-major
@@ -1071,9 +1071,25 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
   __shared__ int rotated;
   const int tid = threadIdx.x;
   const double in_scale = jacobi_input_scale(C, D, tid, 512);
-  for (int i = tid; i < D * D; i += 512) {
-    const int c = i >> 6, r = i & 63;
-    W[c * DS + r] = C[(int64_t)r * D + c] * in_scale;
+  if (V0 == nullptr) {
+    for (int i = tid; i < D * D; i += 512) {
+      const int c = i >> 6, r = i & 63;
+      W[c * DS + r] = C[(int64_t)r * D + c] * in_scale;
+    }
+  } else {
+    // warm start from an orthogonal V0 (vector c at V0 + c D: the single-precision pre-solve below): W = C V0.
+    // A thread owns one component r of eight vectors; C is symmetric, so row r is read along the warp.
+    const int r = tid & 63, c0 = (tid >> 6) * 8;
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double crk = C[(int64_t)k * D + r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fma(crk, V0[(c0 + j) * D + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) W[(c0 + j) * DS + r] = acc[j] * in_scale;
   }
   for (int i = tid; i < PER * NP; i += 512) {
     const int step = i >> 5, k = i & 31;
@@ -1157,9 +1173,11 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
 // profiles/r02_jacobi_variants.txt).  Index logic emulated lane by lane on the CPU in tests/test_replay_logic.py.
 constexpr int JV_WARPS = 8;
 constexpr int JV_AHEAD = 16;
+// V0 (may be null = identity; may alias Vt: a warp reads its own row before it writes it): the vectors the log
+// continues from; finish = 0 leaves Vt as the result (an intermediate stage of the two-stage d = 64 solver).
 __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
     const double* __restrict__ C, int d, const double2* __restrict__ rotlog, int* ctrl, double* Vt,
-    double* __restrict__ evals, double* __restrict__ comps) {
+    double* __restrict__ evals, double* __restrict__ comps, const double* V0, int finish) {
   __shared__ double lam[64];
   __shared__ int last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1179,8 +1197,13 @@ __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
     double va, vb;
     {
       const int a0 = lane == 0 ? per : lane, b0 = lane == 0 ? 0 : per - lane;
-      va = (act && a0 == row) ? 1.0 : 0.0;
-      vb = (act && b0 == row) ? 1.0 : 0.0;
+      if (V0 == nullptr) {
+        va = (act && a0 == row) ? 1.0 : 0.0;
+        vb = (act && b0 == row) ? 1.0 : 0.0;
+      } else {
+        va = (act && a0 < d) ? V0[(size_t)a0 * d + row] : 0.0;
+        vb = (act && b0 < d) ? V0[(size_t)b0 * d + row] : 0.0;
+      }
     }
     const bool is0 = lane == 0, isl = np > 1 && lane == np - 1, ring = np > 1;
     const double2* lp = rotlog + (act ? lane : 0);
@@ -1223,6 +1246,7 @@ __global__ void __launch_bounds__(JV_WARPS * 32) jacobi_vectors_lean_kernel(
   }
   __threadfence();
   __syncthreads();
+  if (!finish) return;
   if (tid == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(ctrl + 1), 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
@@ -1253,12 +1277,17 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     // kept coherent through distributed shared memory, one cluster barrier per step -- was built and measured in
     // round 2: 0.88 / 0.84 ms against 0.48 ms on one SM; a cluster barrier costs ~1 600 cycles, as much as the
     // whole step it was meant to shorten: profiles/r02_jacobi_variants.txt)
+    const int nrep = (d + JV_WARPS - 1) / JV_WARPS;
+    // (a single-precision pre-solve in front of the FP64 solver -- float copy of the matrix, rotations renormalised in
+    // FP64 and logged, the FP64 solver warm-started from W = C V1 so that it needs two sweeps instead of eight -- was
+    // built and measured in round 2: 0.487 ms against 0.486 ms.  A float step is not shorter: the step is a chain of
+    // ~10 dependent stages (load, products, four shuffle levels, parameters, store, barrier), not FP64 issue.)
     if (jacobi_variant() < 0 && d == 64)
-      jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl);
+      jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl, nullptr);
     else
       jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
     count_launch();
-    jacobi_vectors_lean_kernel<<<(d + JV_WARPS - 1) / JV_WARPS, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps);
+    jacobi_vectors_lean_kernel<<<nrep, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps, nullptr, 1);
     count_launch();
     return cudaGetLastError();
   }
