@@ -566,9 +566,9 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--n', type=int, default=N_TOTAL)
-    ap.add_argument('--d', type=int, default=D)
-    ap.add_argument('--m', type=int, default=M)
+    ap.add_argument('--n', type=int, default=None, help="rows (default: the configuration's)")
+    ap.add_argument('--d', type=int, default=None)
+    ap.add_argument('--m', type=int, default=None)
     ap.add_argument('--chunk-rows', type=int, default=524288)
     ap.add_argument('--cpu-rows', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
@@ -580,9 +580,9 @@ def main():
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'tf32x3'],
                     help="arithmetic of the cross-covariance pass (the headline is fp64)")
     args = ap.parse_args()
-    if args.config:
-        args.n, args.d, args.m, pca = CONFIGS[args.config]
-        args.pca = args.pca or pca
+    cn, cd, cm, pca = CONFIGS[args.config or 'C3']
+    args.n, args.d, args.m = args.n or cn, args.d or cd, args.m or cm      # explicit sizes override the configuration's
+    args.pca = args.pca or (pca and args.config is not None)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -560,8 +560,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
         const int j = mt * MT + 8 * nb + 2 * t;
         const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         double2 o0, o1;
-        o0.x = exp_clip_scaled(sc[0][nb][0], etab); o0.y = exp_clip_scaled(sc[0][nb][1], etab);
-        o1.x = exp_clip_scaled(sc[1][nb][0], etab); o1.y = exp_clip_scaled(sc[1][nb][1], etab);
+        if (p.linear == 2) {       // tuning aid (EDRGP_KUF_DEBUG=1): raw exponents, no exp -- how fast is the loop without it?
+          o0.x = sc[0][nb][0]; o0.y = sc[0][nb][1]; o1.x = sc[1][nb][0]; o1.y = sc[1][nb][1];
+        } else {
+          o0.x = exp_clip_scaled(sc[0][nb][0], etab); o0.y = exp_clip_scaled(sc[0][nb][1], etab);
+          o1.x = exp_clip_scaled(sc[1][nb][0], etab); o1.y = exp_clip_scaled(sc[1][nb][1], etab);
+        }
         mu0 += fma(o0.x, c.x, o0.y * c.y); mu1 += fma(o1.x, c.x, o1.y * c.y);
         // ldk is even, so a pair starting at an even j < m is in bounds (a column == m is padding)
         if (v0 && j < p.m) *reinterpret_cast<double2*>(k0p + mt * MT + 8 * nb) = o0;
@@ -710,6 +714,8 @@ template <int DP, int XS, int NS>
 static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) {
   // the pipelined variant needs DP / 16 divisible by 4 (64, 128) to split the next tile's contraction
   const bool simple = p.Kfu != nullptr && !p.mul && !p.linear && p.b == nullptr && (DP % 64 == 0);
+  static const int dbg = [] { const char* e = getenv("EDRGP_KUF_DEBUG"); return e ? atoi(e) : 0; }();
+  if (simple && dbg == 1) { PipeParams q = p; q.linear = 2; return launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(q, grid, st); }
   return simple ? launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(p, grid, st) : launch_kuf_s<DP, XS, NS, false>(p, grid, st);
 }
 

@@ -70,3 +70,29 @@ def test_product_never_imports_the_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+
+
+def test_fixed_sweep_layout_and_tail_decoding():
+    """The composite sweep's workspace layout (no GPU needed: sizes only) and the packing of the two 32-bit check
+    words into the first tail double."""
+    import ctypes
+    import numpy as np
+    from edrgp_b200 import _lib, ops
+    lib = _lib.load()
+    names = ops.FixedSweep.REGIONS
+    off = (ctypes.c_int64 * len(names))()
+    nbytes = lib.edrgp_fixed_layout(500000, 64, 512, 524288, 8, off)
+    assert nbytes > 0 and nbytes % 16 == 0
+    o = dict(zip(names, list(off)))
+    assert all(v % 2 == 0 for v in o.values())                       # 16-byte aligned regions
+    order = sorted(o.values())
+    assert order == [o[k] for k in names]                              # laid out in declaration order
+    assert o['stats'] - o['yt'] >= 500000 and o['table'] - o['stats'] >= 512 * 512 + 512 + 1
+    assert o['S'] - o['table'] >= 4 * 8
+    assert nbytes // 8 - o['result'] >= 64 + 2 * 64 * 64 + 4
+    assert lib.edrgp_fixed_layout(0, 64, 512, 524288, 1, off) == 0    # rejected shapes
+    tail = np.zeros(4)
+    tail[:1] = np.array([3, 41], dtype=np.int32).view(np.float64)
+    tail[1:] = [4e6, 0.25, 1.75]
+    assert ops.FixedSweep.decode_tail(tail) == (3, 41, 4e6, 0.25, 1.75)
+    assert ops.FixedSweep.supported(64, 10) and not ops.FixedSweep.supported(66, 10) and not ops.FixedSweep.supported(64, 0)

@@ -38,3 +38,26 @@ def test_default_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.strip().startswith('{') and '"value"' in l]
+
+
+def test_config_selection_and_metric_names():
+    """--config picks a BASELINE.json shape, explicit sizes override it, and only the headline shape carries
+    BASELINE's metric string."""
+    import importlib
+    import types
+    bench = importlib.import_module('bench')
+    def args(**kw):
+        a = types.SimpleNamespace(config=None, n=None, d=None, m=None, pca=False)
+        a.__dict__.update(kw)
+        cn, cd, cm, pca = bench.CONFIGS[a.config or 'C3']
+        a.n, a.d, a.m = a.n or cn, a.d or cd, a.m or cm
+        a.pca = a.pca or (pca and a.config is not None)
+        return a
+    assert bench.metric_name(args()) == bench.METRIC
+    a = args(config='C4')
+    assert (a.n, a.d, a.m, a.pca) == (1_000_000, 512, 1024, False) and 'n=1000000,d=512,m=1024' in bench.metric_name(a)
+    a = args(config='C5', n=2_000_000)
+    assert (a.n, a.d, a.m, a.pca) == (2_000_000, 128, 2048, True) and 'PCA-chained' in bench.metric_name(a)
+    assert 'C5' in bench.workload_name(a) and 'PCA preprocessor' in bench.workload_name(a)
+    fl = bench.flops_per_point(64, 512)
+    assert fl['syrk'] == 2 * 512 * 512 + 2 * 512 and 0.5 < fl['syrk_executed'] / fl['syrk'] < 0.52

@@ -40,6 +40,30 @@ def _worker(rank, world, port, out):
         z = torch.full((4,), float(rank), dtype=torch.float64)
         dist.broadcast_(z, 0)
         assert torch.equal(z, torch.zeros(4, dtype=torch.float64))
+        # a single contiguous tensor is reduced in place (no staging copy); a failure flag by maximum
+        one = torch.full((6,), float(rank + 1), dtype=torch.float64)
+        view = one[1:5]
+        dist.allreduce_sum_(view)
+        assert one.tolist() == [rank + 1.0, 3.0, 3.0, 3.0, 3.0, rank + 1.0]
+        flag = torch.tensor([float(rank == 1)], dtype=torch.float64)
+        dist.allreduce_max_(flag)
+        assert float(flag[0]) == 1.0
+        # the targets' moments table of the composite sweep (csrc/sweep.cu): every rank fills its own row
+        # [n_r, pivot_r, sum (y - pivot_r), sum (y - pivot_r)^2]; one summed table gives the GLOBAL mean and std
+        rng = np.random.RandomState(7)
+        y_all = 1e3 + 2.5 * rng.standard_normal(5001)
+        lo_y, hi_y = dist.shard_bounds(y_all.size)
+        ys_ = y_all[lo_y:hi_y]
+        table = torch.zeros(world, 4, dtype=torch.float64)
+        piv = ys_[0]
+        table[rank] = torch.tensor([ys_.size, piv, np.sum(ys_ - piv), np.sum((ys_ - piv) ** 2)])
+        dist.allreduce_sum_(table)
+        t = table.numpy()
+        N = t[:, 0].sum()
+        mean = np.sum(t[:, 0] * t[:, 1] + t[:, 2]) / N
+        m2 = np.sum(t[:, 3] + 2 * (t[:, 1] - mean) * t[:, 2] + t[:, 0] * (t[:, 1] - mean) ** 2)
+        assert abs(mean - y_all.mean()) < 1e-13 * abs(y_all.mean())
+        assert abs(np.sqrt(m2 / N) - y_all.std()) < 1e-12 * y_all.std()
 
         n, d, m = 3001, 6, 25
         w = op.make_workload(n, d, m, seed=2, k_true=2)
