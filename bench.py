@@ -293,6 +293,8 @@ def run_ours(args):
         the directions have been read back: no host round trip between the row passes."""
         if args.pca:
             Xin = preprocess(Xin)
+            if not isinstance(yin, torch.Tensor):
+                yin = torch.as_tensor(yin, device=dev)
         est = make_estimator(precision).fit(Xin, yin)
         _, C = est.estimator_.gradient_gram(want_G=False, check=False)
         edist.allreduce_sum_(C)
