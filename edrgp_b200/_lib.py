@@ -40,6 +40,8 @@ SIGNATURES = {
     'edrgp_syrk_workspace_bytes': (_sz, [_i64, _int]),
     'edrgp_syrk': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
     'edrgp_inducing_stats': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _c_dp, _i64, _c_dp, _int, _c_dp, _c_dp]),
+    'edrgp_inducing_stats_i8_workspace_bytes': (_sz, [_i64, _int]),
+    'edrgp_inducing_stats_i8': (_int, [_c_dp, _i64, _int, _i64, _c_dp, _dbl, _c_dp, _i64, _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_gemm_tn_workspace_bytes': (_sz, [_i64, _int, _int]),
     'edrgp_gemm_tn': (_int, [_c_dp, _i64, _int, _c_dp, _i64, _int, _i64, _c_dp, _i64, _int, _c_dp, _c_dp]),
     'edrgp_kmm': (_int, [_c_dp, _i64, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _int, _int, _c_dp]),

@@ -285,6 +285,27 @@ int edrgp_inducing_stats(const double* Kfu, int64_t n, int m, int64_t ldk, const
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "inducing_stats");
 }
 
+size_t edrgp_inducing_stats_i8_workspace_bytes(int64_t n, int m) {
+  int sms = sm_count_cached();
+  if (sms <= 0) sms = 160;
+  if (n <= 0 || m <= 0 || m > 2048) return 0;
+  return edrgp::inducing_stats_i8_workspace_bytes(n, m, sms);
+}
+
+int edrgp_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2, double* P,
+                            int64_t ldp, double* b_yy, int accumulate, void* workspace, void* stream) {
+  if (!Kfu || n <= 0 || m <= 0 || ldk < m || !P || ldp < m || !workspace) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: bad argument");
+  if (m > 2048) return fail(EDRGP_ERR_UNSUPPORTED, "inducing_stats_i8: m=%d > 2048", m);
+  if ((y == nullptr) != (b_yy == nullptr)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: y and b_yy go together");
+  if (!(sf2 > 0.0) || !(sf2 < 1e150)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: the kernel variance must be positive and finite");
+  if (!aligned16(workspace)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: the workspace must be 16-byte aligned");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(EDRGP_ERR_CUDA, "inducing_stats_i8: no CUDA device");
+  cudaError_t e = edrgp::launch_inducing_stats_i8(Kfu, n, m, ldk, y, sf2, P, ldp, b_yy, accumulate, workspace, sms,
+                                                  (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "inducing_stats_i8");
+}
+
 size_t edrgp_gemm_tn_workspace_bytes(int64_t n, int ka, int kb) {
   int sms = sm_count_cached();
   if (sms <= 0) sms = 160;

@@ -70,6 +70,12 @@ cudaError_t launch_weights_tf32(const double* K, int64_t n, int m, int64_t ldk, 
                                 const double* alpha, double c_ya, double* T, int64_t ldt, double* rowsum, int sms,
                                 cudaStream_t st);
 
+// exact-product INT8 symmetric reduction (tcgen05 kind::i8): i8syrk.cu
+size_t inducing_stats_i8_workspace_bytes(int64_t n, int m, int sms);
+cudaError_t launch_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2,
+                                     double* P, int64_t ldp, double* b_yy, int accumulate, void* workspace, int sms,
+                                     cudaStream_t st);
+
 cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

@@ -315,6 +315,29 @@ def inducing_stats(K, y, m=None, P=None, b_yy=None, accumulate=False):
     return P, b_yy
 
 
+def inducing_stats_i8(K, y, sf2, m=None, P=None, b_yy=None, accumulate=False):
+    """``inducing_stats`` on the INT8 tensor cores (exact products of six 8-bit slices of K / (2 sf2)): K (n, ldk) must
+    hold kernel entries in [0, sf2] as written by ``kuf`` with the same ``sf2``."""
+    lib = _lib.load()
+    _need_cuda(K, y, P, b_yy)
+    n, ldk = K.shape
+    m = ldk if m is None else m
+    fresh = P is None or (y is not None and b_yy is None)
+    if P is None:
+        P = torch.empty(m, m, dtype=F64, device=K.device)
+    if b_yy is None and y is not None:
+        b_yy = torch.empty(m + 1, dtype=F64, device=K.device)
+    nbytes = lib.edrgp_inducing_stats_i8_workspace_bytes(n, m)
+    if nbytes == 0:
+        raise ValueError("the INT8 statistics cover m <= 2048 (got %d)" % m)
+    ws = torch.empty(nbytes // 8, dtype=F64, device=K.device)
+    with _Timed('inducing_stats'):
+        _lib.check(lib.edrgp_inducing_stats_i8(_ptr(K), n, m, ldk, _ptr(y), float(sf2), _ptr(P), m, _ptr(b_yy),
+                                               int(bool(accumulate and not fresh)), _ptr(ws), _stream()),
+                   'edrgp_inducing_stats_i8')
+    return P, b_yy
+
+
 def gemm_tn(A, B, ka=None, kb=None, out=None, accumulate=False):
     """C (+)= A[:, :ka]^T B[:, :kb] for tall row-major A (n, lda), B (n, ldb)."""
     lib = _lib.load()
