@@ -254,6 +254,7 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         tdist.init_process_group('nccl', device_id=dev)
     n, d, m = args.n, args.d, args.m
+    ops.set_stats_mode(args.stats)
     lo, hi = edist.shard_bounds(n, rank, world)
     n_local = hi - lo
 
@@ -393,6 +394,32 @@ def run_ours(args):
             "tolerance": "1e-4 relative on kernel entries (BASELINE north_star, TF32-split mode)"}
         del K64, K32, pk64, pk32
 
+    # ---- the same sweep with the statistics on the INT8 tensor cores (informational unless --stats int8x6 made it
+    # the headline): exact integer products of six 8-bit slices of Kfu, everything else unchanged
+    int8_mode = None
+    if (d + (d & 1) <= 64 and args.precision == 'fp64' and args.stats == 'fp64' and not args.no_int8 and not args.pca
+            and m <= 2048):
+        ops.set_stats_mode('int8x6')
+        try:
+            for _ in range(3):
+                sweep(X, y)
+            ops.start_timing()
+            i_steps = max(1, min(args.steps, 5))
+            i_ms, comps8 = timed(lambda: sweep(X, y), i_steps)
+            i_ops = ops.stop_timing()
+            s_ms, s_n = i_ops.get('inducing_stats', (0.0, 1))
+            from edrgp_b200.utils import principal_angle as _pa8
+            int8_mode = {
+                "ms_per_step": i_ms / i_steps, "value": n / (i_ms / i_steps * 1e-3), "unit": UNIT, "steps": i_steps,
+                "kernels": "slice_u8_kernel + syrk_i8_kernel (tcgen05.mma kind::i8, 21 slice pairs, int32 accumulators "
+                           "in TMEM) + i8_reduce_kernel",
+                "inducing_stats_ms_per_step": s_ms / i_steps,
+                "max_abs_diff_components_vs_fp64": float(np.max(np.abs(np.abs(comps8) - np.abs(comps)))),
+                "leading_direction_angle_vs_fp64_rad": float(_pa8(comps8[:1], comps[:1])),
+                "how": "ops.set_stats_mode('int8x6') / EDRGP_STATS=int8x6 / bench.py --stats int8x6"}
+        finally:
+            ops.set_stats_mode('fp64')
+
     # quality of the directions found (not a timing): principal angle to the true subspace
     from edrgp_b200.utils import principal_angle
     Bt = Bm.cpu().numpy().T
@@ -501,7 +528,7 @@ def run_ours(args):
                    "hyperparameters": "fixed (lengthscales sqrt(d)(1+u/2), variance 1, noise 0.1)",
                    "l2": "inputs (%.2f GB X per rank + %.1f GB Kfu blocks) exceed the 126 MB L2; no flush needed"
                          % (n_local * d * 8 / 1e9, n_local * m * 8 / 1e9),
-                   "chunk_rows": args.chunk_rows, "precision": args.precision, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
+                   "chunk_rows": args.chunk_rows, "precision": args.precision, "stats": args.stats, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                 "api": "SparseGaussianProcessRegressor(method='fixed').fit(X_host, y_host) -> gradient_gram -> "
@@ -555,6 +582,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "edr_fit": edr_fit,
         "tf32x3_mode": tf32_mode,
+        "int8x6_stats_mode": int8_mode,
     }
     print(json.dumps(line), file=real_stdout)
     real_stdout.flush()
@@ -576,6 +604,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-edr', action='store_true')
     ap.add_argument('--no-tf32', action='store_true', help="skip the informational TF32-split arm")
+    ap.add_argument('--no-int8', action='store_true', help="skip the informational INT8-slice statistics arm")
+    ap.add_argument('--stats', default='fp64', choices=['fp64', 'int8x6'],
+                    help="statistics route of the sweep (the headline is fp64: FP64 DMMA)")
     ap.add_argument('--no-pageable', action='store_true', help="skip the pageable-host-memory end-to-end leg")
     ap.add_argument('--config', default=None, choices=sorted(CONFIGS), help="a BASELINE.json configuration (default: C3)")
     ap.add_argument('--pca', action='store_true', help="run the StandardScaler + DevicePCA front of the chain inside the step")

@@ -62,6 +62,8 @@ SIGNATURES = {
     'edrgp_project_dmma': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _c_dp, _i64, _c_dp]),
     'edrgp_project': (_int, [_c_dp, _i64, _int, _c_dp, _int, _c_dp, _c_dp]),
     'edrgp_fixed_layout': (_sz, [_i64, _int, _int, _i64, _int, ctypes.POINTER(ctypes.c_int64)]),
+    'edrgp_set_stats_mode': (_int, [_int]),
+    'edrgp_get_stats_mode': (_int, []),
     'edrgp_fixed_begin': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _c_dp, _i64, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int,
                                  _int, _c_dp, _i64, _c_dp, _c_dp]),
     'edrgp_fixed_stats': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _int, _dbl, _i64, _c_dp, _i64, _int, _int, _c_dp, _i64,

@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 #include "../../include/edrgp_b200.h"
@@ -457,6 +459,19 @@ int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, dou
 // Fixed-hyper-parameter sweep composites (sweep.cu): everything between two collectives in one call
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
+// statistics mode of the composite sweep: 0 = FP64 DMMA, 1 = exact-product INT8 slices.  Process-wide, because the
+// workspace layout depends on it; the default comes from EDRGP_STATS (fp64 | int8x6).
+int g_stats_mode = -1;
+int stats_mode() {
+  if (g_stats_mode < 0) {
+    const char* s = getenv("EDRGP_STATS");
+    g_stats_mode = (s && (!strcmp(s, "int8x6") || !strcmp(s, "int8") || !strcmp(s, "1"))) ? 1 : 0;
+  }
+  return g_stats_mode;
+}
+// the INT8 route covers what its kernel covers; outside that the FP64 reduction runs (same results to 1e-13)
+int stats_mode_for(int m, double sf2) { return (stats_mode() == 1 && m <= 2048 && sf2 < 1e150) ? 1 : 0; }
+
 struct FixedCtx {
   int64_t off[edrgp::FS_NREGIONS];
   int sms;
@@ -472,7 +487,7 @@ int fixed_ctx(const char* who, int64_t n, int d, int m, int64_t chunk_rows, int 
   if (!aligned16(ws)) return fail(EDRGP_ERR_ARG, "%s: the workspace must be 16-byte aligned", who);
   c->sms = sm_count_cached();
   if (c->sms <= 0) return fail(EDRGP_ERR_CUDA, "%s: no CUDA device", who);
-  edrgp::fixed_layout(n, d, m, chunk_rows, world, c->sms, c->off);
+  edrgp::fixed_layout(n, d, m, chunk_rows, world, c->sms, c->off, stats_mode() == 1 && m <= 2048);
   c->ws = (double*)ws;
   return EDRGP_OK;
 }
@@ -482,8 +497,16 @@ size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world
   int sms = sm_count_cached();
   if (sms <= 0) sms = 160;
   if (n <= 0 || d <= 0 || m <= 0 || chunk_rows <= 0 || world <= 0 || !offsets) return 0;
-  return edrgp::fixed_layout(n, d, m, chunk_rows, world, sms, offsets) * sizeof(double);
+  return edrgp::fixed_layout(n, d, m, chunk_rows, world, sms, offsets, stats_mode() == 1 && m <= 2048) * sizeof(double);
 }
+
+int edrgp_set_stats_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(EDRGP_ERR_ARG, "set_stats_mode: 0 (fp64) or 1 (int8x6)");
+  g_stats_mode = mode;
+  return EDRGP_OK;
+}
+
+int edrgp_get_stats_mode(void) { return stats_mode(); }
 
 int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
                       const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
@@ -541,6 +564,7 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
   const double* targets = normalize ? yt : y;
   double* P = c.at(edrgp::FS_STATS);
   double* byy = P + (size_t)m * m;
+  const int i8 = stats_mode_for(m, sf2);
   for (int64_t s = 0; s < n; s += chunk_rows) {
     const int64_t rows = n - s < chunk_rows ? n - s : chunk_rows;
     double* Kc = Kfu + s * ldk;
@@ -552,8 +576,16 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
                                  nullptr, c.sms, st, 0, c.flag())) != cudaSuccess) return cuda_fail(e, "fixed_stats");
     }
     StageScope t(EDRGP_STAGE_STATS, st);
-    if ((e = edrgp::launch_gemm_tn(Kc, ldk, m, nullptr, 0, 0, rows, 1, targets + s, P, m, byy, s > 0,
-                                   c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) return cuda_fail(e, "fixed_stats");
+    if (i8) {
+      if ((e = edrgp::launch_i8_block(Kc, rows, m, ldk, targets + s, sf2, s == 0, c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess)
+        return cuda_fail(e, "fixed_stats");
+      if (s + rows >= n &&
+          (e = edrgp::launch_i8_finish(m, sf2, 1, P, m, byy, 0, c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess)
+        return cuda_fail(e, "fixed_stats");
+    } else if ((e = edrgp::launch_gemm_tn(Kc, ldk, m, nullptr, 0, 0, rows, 1, targets + s, P, m, byy, s > 0,
+                                          c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) {
+      return cuda_fail(e, "fixed_stats");
+    }
   }
   return EDRGP_OK;
 }

@@ -6,9 +6,9 @@
 // Kfu entries lie in [0, sf2], so with t = K / (2 sf2) + 1 in [1, 1.5] the 52 mantissa bits of t are the fixed-point
 // fraction of K / (2 sf2) and its BYTES are unsigned 8-bit slices q_0 .. q_5 (q_s weighs 2^-8(s+1); 48 bits kept,
 // truncation below 2^-48).  Products of slices are exact in the 32-bit integer accumulators of tensor memory, slice
-// pairs (a, b) with the same a + b = g share an accumulator, pairs with a + b > 4 (weight <= 2^-56, below the
-// truncation of the slices themselves) are dropped, and
-//     P = 4 sf2^2 sum_g 2^-8(g+2) A_g,       A_g = sum_{a+b=g} Q_a^T Q_b,   g = 0 .. 4  (15 pairs).
+// pairs (a, b) with the same a + b = g share an accumulator, pairs with a + b >= 6 (below the truncation of the
+// slices themselves) are dropped, and
+//     P = 4 sf2^2 sum_g 2^-8(g+2) A_g,       A_g = sum_{a+b=g} Q_a^T Q_b,   g = 0 .. 5  (21 pairs).
 // Downstream the result is indistinguishable from the FP64 statistics (P within 1e-13, alpha-consumers within the
 // FP64 path's own rounding: tools/int8_slice_syrk_study.py, profiles/r02_int8_slice_syrk_study.txt).
 //
@@ -17,10 +17,10 @@
 //                     (data rows = the contraction index), K-major, 128-byte swizzled -- so the reduction kernel moves
 //                     operands with plain bulk copies.  The same pass accumulates Kfu^T y and y^T y (per-CTA partials).
 //   syrk_i8_kernel    one CTA per (output tile 128 x 128, row split), two passes over its rows (weight groups 0-2, then
-//                     3-4: five groups of 128 tensor-memory columns do not fit at once): warp 0 streams slices (the B
+//                     3-5: six groups of 128 tensor-memory columns do not fit at once): warp 0 streams slices (the B
 //                     tile's per k-block, double buffered; the A tile's one at a time through a ring), warp 1 issues
-//                     tcgen05.mma.kind::i8 (M = N = 128, K = 32: 60 MMAs per k-block), warps 2-9 drain the
-//                     accumulators every 4 096 rows (255 x 255 x 5 pairs x 4 096 rows < 2^31) into FP64 registers.
+//                     tcgen05.mma.kind::i8 (M = N = 128, K = 32: 84 MMAs per k-block), warps 2-9 drain the
+//                     accumulators every 4 096 rows (255 x 255 x 6 pairs x 4 096 rows < 2^31) into FP64 registers.
 //   i8_reduce_kernel  sums the row splits in fixed order, scales, writes P (both triangles), b and y^T y.
 #include <cstdint>
 #include <cstdlib>
@@ -31,20 +31,23 @@ namespace edrgp {
 namespace i8 {
 
 constexpr int S = 6;                       // slices (48 bits)
-constexpr int GMAX = 4;                    // slice pairs (a, b) with a + b <= GMAX are formed: 15 pairs in 5 weight groups
+constexpr int GMAX = 5;                    // slice pairs (a, b) with a + b <= GMAX are formed: 21 pairs in 6 weight groups
 constexpr int TM = 128, TN = 128;          // output tile: A columns x B columns
 constexpr int KBLK = 128;                  // data rows per k-block = bytes per swizzled operand row
 constexpr int ABLK = 128 * 128;            // one slice of a 128-column block for one k-block: 16 KB
 constexpr int BBLK = ABLK;
-constexpr int A_STAGES = 3;
+constexpr int A_STAGES = 2;                // 2 x 16 KB + 2 x 6 x 16 KB of B + barriers = 225 KB of the 227 KB a CTA may have
 constexpr int B_STAGES = 2;
-constexpr int BSL = GMAX + 1;              // slices of the B tile resident per k-block (second pass: 0 .. 4)
+constexpr int BSL = GMAX + 1;              // slices of the B tile resident per k-block (second pass: all six)
 constexpr int DRAIN_KB = 32;               // k-blocks between drains of the int32 accumulators
 constexpr int EPI_W = 8;                   // two warps per tensor-memory lane quarter: 64 output columns per thread
 constexpr int NTHREADS = 32 * (2 + EPI_W);
-// Two passes over the CTA's rows, because five weight groups of 128 columns do not fit the 512 tensor-memory columns:
+// Two passes over the CTA's rows, because six weight groups of 128 columns do not fit the 512 tensor-memory columns:
 //   pass 0  groups 0, 1, 2  (pairs a + b <= 2: 6 pairs, slices 0 .. 2 of both tiles)
-//   pass 1  groups 3, 4     (pairs 3 <= a + b <= 4: 9 pairs, slices 0 .. 4)
+//   pass 1  groups 3, 4, 5  (pairs 3 <= a + b <= 5: 15 pairs, all six slices)
+// (Group g weighs ~2^-8g relative to P: stopping at g = 4 -- 15 pairs, measured 2.15 ms per 524 288-row block instead
+// of this version's time -- leaves P at 1e-11 and alpha at 7e-9, an order worse than the FP64 reduction's own
+// rounding; with g = 5 the result is FP64-equivalent: profiles/r02_int8_slice_syrk_study.txt.)
 // An MMA costs ~100-170 cycles for fetching its 128 x 32-byte slice of A from shared memory whatever N is (SS mode;
 // tools/umma_rate.cu), so wide tiles (N = 128) with few resident groups beat N = 64 with all groups resident (the first
 // version of this kernel: 2.49 ms per 524 288-row block against the FP64 reduction's 3.91 ms incl. everything).
@@ -68,6 +71,7 @@ struct Params {
   int64_t kb_per_split;
   const int* tiles;                        // (ta, tb) per tile
   double* part;                            // [split][tile][TM * TN]
+  int accumulate;                          // add to the partials of earlier row blocks instead of overwriting them
 };
 
 // ---- tcgen05 wrappers (the TF32 kernels' idioms, tf32.cu) -----------------------------------------------------------
@@ -136,7 +140,7 @@ __host__ __device__ inline uint32_t sw128_byte(int r, int k) {
 __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* __restrict__ K, int64_t n, int m, int64_t ldk,
                                                                   const double* __restrict__ y, double inv2sf2,
                                                                   uint8_t* __restrict__ planes, int njb, int64_t nkb,
-                                                                  double* __restrict__ bpart) {
+                                                                  double* __restrict__ bpart, int accumulate) {
   const int tid = threadIdx.x, jl = tid & 127, h = tid >> 7;
   const int mp = njb * 128;
   __shared__ double ys[KBLK];
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
     __syncthreads();
     if (h == 1) bsh[jl] = v;
     __syncthreads();
-    if (h == 0) out[jb * 128 + jl] = v + bsh[jl];
+    if (h == 0) out[jb * 128 + jl] = v + bsh[jl] + (accumulate ? out[jb * 128 + jl] : 0.0);
   }
   __syncthreads();
   ys[tid & 127] = 0.0;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
   if (tid == 0) {
     double s = 0.0;
     for (int i = 0; i < KBLK; ++i) s += ys[i];
-    out[mp] = s;
+    out[mp] = s + (accumulate ? out[mp] : 0.0);
   }
 }
 
@@ -359,7 +363,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) syrk_i8_kernel(const Params p) {
     }
     double* out = p.part + ((size_t)split * p.ntiles + tile) * (TM * TN) + (size_t)r * TN + ch * 64;
 #pragma unroll
-    for (int c = 0; c < 64; c += 2) *reinterpret_cast<double2*>(out + c) = make_double2(sum[c], sum[c + 1]);
+    for (int c = 0; c < 64; c += 2) {
+      double2 o = make_double2(sum[c], sum[c + 1]);
+      if (p.accumulate) { const double2 old = *reinterpret_cast<const double2*>(out + c); o.x += old.x; o.y += old.y; }
+      *reinterpret_cast<double2*>(out + c) = o;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -408,60 +416,87 @@ static int tile_list(int m, int* out) {                 // (ta, tb), tb >= ta: t
 
 }  // namespace i8
 
-// workspace: slice planes of the row block | split partials | slicer partials | tile table
-size_t inducing_stats_i8_workspace_bytes(int64_t n, int m, int sms) {
+// workspace: split partials | slicer partials | tile table | slice planes of one row block (the only part that
+// depends on n, so it comes last: the partials of successive row blocks of different sizes share their place)
+namespace i8 {
+struct Layout {
+  int ntiles, nsplit, njb, mp, sgrid;
+  size_t part, bpart, tiles, planes, total;
+};
+static Layout layout(int64_t n, int m, int sms) {
+  Layout L;
+  L.ntiles = tile_list(m, nullptr);
+  L.nsplit = sms / L.ntiles < 1 ? 1 : sms / L.ntiles;
+  L.njb = mpad(m) / 128;
+  L.mp = L.njb * 128;
+  L.sgrid = 2 * sms;
+  const int64_t nkb = (n + KBLK - 1) / KBLK;
+  size_t o = 0;
+  L.part = o;   o += (size_t)L.nsplit * L.ntiles * TM * TN * 8;
+  L.bpart = o;  o += (size_t)L.sgrid * (L.mp + 1) * 8;
+  L.tiles = o;  o += ((size_t)2 * L.ntiles * 4 + 1023) / 1024 * 1024;
+  L.planes = o; o += (size_t)nkb * L.njb * S * ABLK;
+  L.total = (o + 1023) / 1024 * 1024;
+  return L;
+}
+}  // namespace i8
+
+size_t inducing_stats_i8_workspace_bytes(int64_t n, int m, int sms) { return i8::layout(n, m, sms).total; }
+
+// One row block: slices, then the reduction into the split partials (first = 0: on top of the earlier blocks').
+cudaError_t launch_i8_block(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2, int first,
+                            void* workspace, int sms, cudaStream_t st) {
+  if (m > 2048) return cudaErrorInvalidValue;
+  const i8::Layout L = i8::layout(n, m, sms);
   const int64_t nkb = (n + i8::KBLK - 1) / i8::KBLK;
-  const int njb = i8::mpad(m) / 128;
-  const int ntiles = i8::tile_list(m, nullptr);
-  int nsplit = sms / ntiles;
-  if (nsplit < 1) nsplit = 1;
-  size_t bytes = (size_t)nkb * njb * i8::S * i8::ABLK;
-  bytes += (size_t)nsplit * ntiles * i8::TM * i8::TN * 8;
-  bytes += (size_t)2 * sms * (i8::mpad(m) + 1) * 8;
-  bytes += (size_t)2 * ntiles * 4 + 64;
-  return (bytes + 1023) / 1024 * 1024;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* tiles = reinterpret_cast<int*>(ws + L.tiles);
+  cudaError_t e;
+  if (first) {
+    int host_tiles[2 * 16 * 17 / 2 * 2];
+    i8::tile_list(m, host_tiles);
+    if ((e = cudaMemcpyAsync(tiles, host_tiles, (size_t)2 * L.ntiles * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return e;
+  }
+  i8::slice_u8_kernel<<<L.sgrid, i8::SLICE_THREADS, 0, st>>>(Kfu, n, m, ldk, y, 0.5 / sf2, ws + L.planes, L.njb, nkb,
+                                                             reinterpret_cast<double*>(ws + L.bpart), first ? 0 : 1);
+  count_launch();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  i8::Params p{};
+  p.planes = ws + L.planes; p.njb = L.njb; p.nkb = nkb; p.ntiles = L.ntiles; p.nsplit = L.nsplit;
+  p.kb_per_split = (nkb + L.nsplit - 1) / L.nsplit;
+  p.tiles = tiles; p.part = reinterpret_cast<double*>(ws + L.part); p.accumulate = first ? 0 : 1;
+  const size_t smem = i8::smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    if ((e = cudaFuncSetAttribute(i8::syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    attr_set = true;
+  }
+  i8::syrk_i8_kernel<<<L.ntiles * L.nsplit, i8::NTHREADS, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// P (+)= 4 sf2^2 x the sum of the split partials (fixed order), b_yy (+)= the slicer's partials
+cudaError_t launch_i8_finish(int m, double sf2, int with_y, double* P, int64_t ldp, double* b_yy, int accumulate,
+                             void* workspace, int sms, cudaStream_t st) {
+  const i8::Layout L = i8::layout(0, m, sms);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int64_t total = (int64_t)L.ntiles * i8::TM * i8::TN;
+  i8::i8_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const double*>(ws + L.part), L.nsplit, L.ntiles, reinterpret_cast<const int*>(ws + L.tiles), m,
+      4.0 * sf2 * sf2, P, ldp, accumulate, reinterpret_cast<const double*>(ws + L.bpart), L.sgrid, L.mp,
+      with_y ? b_yy : nullptr);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2,
                                      double* P, int64_t ldp, double* b_yy, int accumulate, void* workspace, int sms,
                                      cudaStream_t st) {
-  if (m > 2048) return cudaErrorInvalidValue;
-  const int64_t nkb = (n + i8::KBLK - 1) / i8::KBLK;
-  const int njb = i8::mpad(m) / 128, mp = njb * 128;
-  int host_tiles[2 * 16 * 33];
-  const int ntiles = i8::tile_list(m, host_tiles);
-  int nsplit = sms / ntiles;
-  if (nsplit < 1) nsplit = 1;
-  if ((int64_t)nsplit > nkb) nsplit = (int)nkb;
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  uint8_t* planes = ws;
-  size_t off = (size_t)nkb * njb * i8::S * i8::ABLK;
-  double* part = reinterpret_cast<double*>(ws + off);
-  off += (size_t)(sms / ntiles < 1 ? 1 : sms / ntiles) * ntiles * i8::TM * i8::TN * 8;
-  double* bpart = reinterpret_cast<double*>(ws + off);
-  off += (size_t)2 * sms * (mp + 1) * 8;
-  int* tiles = reinterpret_cast<int*>(ws + off);
-  cudaError_t e = cudaMemcpyAsync(tiles, host_tiles, (size_t)2 * ntiles * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaError_t e = launch_i8_block(Kfu, n, m, ldk, y, sf2, 1, workspace, sms, st);
   if (e != cudaSuccess) return e;
-  int sgrid = 2 * sms;
-  if ((int64_t)sgrid > nkb) sgrid = (int)nkb;
-  i8::slice_u8_kernel<<<sgrid, i8::SLICE_THREADS, 0, st>>>(Kfu, n, m, ldk, y, 0.5 / sf2, planes, njb, nkb, bpart);
-  count_launch();
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  i8::Params p{};
-  p.planes = planes; p.njb = njb; p.nkb = nkb; p.ntiles = ntiles; p.nsplit = nsplit;
-  p.kb_per_split = (nkb + nsplit - 1) / nsplit;
-  p.tiles = tiles; p.part = part;
-  const size_t smem = i8::smem_bytes();
-  if ((e = cudaFuncSetAttribute(i8::syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-  i8::syrk_i8_kernel<<<ntiles * nsplit, i8::NTHREADS, smem, st>>>(p);
-  count_launch();
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const int64_t total = (int64_t)ntiles * i8::TM * i8::TN;
-  i8::i8_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, nsplit, ntiles, tiles, m, 4.0 * sf2 * sf2, P, ldp,
-                                                                       accumulate, bpart, sgrid, mp, y ? b_yy : nullptr);
-  count_launch();
-  return cudaGetLastError();
+  return launch_i8_finish(m, sf2, y != nullptr, P, ldp, b_yy, accumulate, workspace, sms, st);
 }
 
 }  // namespace edrgp

@@ -76,6 +76,11 @@ cudaError_t launch_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_
                                      double* P, int64_t ldp, double* b_yy, int accumulate, void* workspace, int sms,
                                      cudaStream_t st);
 
+cudaError_t launch_i8_block(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2, int first,
+                            void* workspace, int sms, cudaStream_t st);
+cudaError_t launch_i8_finish(int m, double sf2, int with_y, double* P, int64_t ldp, double* b_yy, int accumulate,
+                             void* workspace, int sms, cudaStream_t st);
+
 cudaError_t launch_dmma_probe(double* scratch, int iters, int sms, double* flops, cudaStream_t st);
 
 }  // namespace edrgp

@@ -153,7 +153,7 @@ cudaError_t launch_form_system(double* S, int m, int64_t lds, double sf2, double
 // ---------------------------------------------------------------------------------------------------------------
 static inline size_t even(size_t x) { return x + (x & 1); }
 
-size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int sms, int64_t* off) {
+size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int sms, int64_t* off, int stats_mode) {
   const size_t pack = ((size_t)padded_dim(d) + (size_t)((m + MT - 1) / MT) * pack_tile_doubles(padded_dim(d)));
   const int64_t rows = chunk_rows < n ? chunk_rows : n;
   size_t scratch = gemm_tn_workspace_bytes(rows, m, m, 1, sms) / 8;
@@ -163,6 +163,10 @@ size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int 
   if (grad > scratch) scratch = grad;
   if (eig > scratch) scratch = eig;
   if (mom > scratch) scratch = mom;
+  if (stats_mode == 1) {
+    const size_t i8 = inducing_stats_i8_workspace_bytes(rows, m, sms) / 8;
+    if (i8 > scratch) scratch = i8;
+  }
   size_t o = 0;
   auto take = [&](int id, size_t count) { off[id] = (int64_t)o; o += even(count); };
   take(FS_PACK_K, pack);

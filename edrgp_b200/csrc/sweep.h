@@ -22,7 +22,8 @@ enum FixedRegion {
   FS_NREGIONS
 };
 
-size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int sms, int64_t* off);
+// stats_mode: 0 = FP64 DMMA statistics, 1 = exact-product INT8 slices (i8syrk.cu; needs room for one block's slices)
+size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int sms, int64_t* off, int stats_mode);
 cudaError_t launch_target_moments(const double* y, int64_t n, double* part, unsigned int* ticket, double* slot, int sms,
                                   cudaStream_t st);
 cudaError_t launch_target_standardize(const double* table, int world, const double* y, int64_t n, double* yt,

@@ -577,6 +577,23 @@ def project(X, V):
     return out
 
 
+STATS_MODES = ('fp64', 'int8x6')
+
+
+def set_stats_mode(mode):
+    """Statistics route of the composite sweep (edrgp_set_stats_mode): 'fp64' -- the FP64 DMMA reduction, the
+    default -- or 'int8x6' -- exact integer products of six 8-bit slices on the INT8 tensor cores, P within 1e-13
+    of the FP64 reduction and ~1.5 x faster.  Process-wide; workspaces are pooled per mode.  The environment
+    variable EDRGP_STATS sets the initial value."""
+    if mode not in STATS_MODES:
+        raise ValueError("stats mode must be one of %s (got %r)" % (STATS_MODES, mode))
+    _lib.check(_lib.load().edrgp_set_stats_mode(STATS_MODES.index(mode)), 'edrgp_set_stats_mode')
+
+
+def get_stats_mode():
+    return STATS_MODES[_lib.load().edrgp_get_stats_mode()]
+
+
 class FixedSweep(object):
     """The composite calls of the fixed-hyper-parameter sweep (``edrgp_fixed_*``) over ONE workspace tensor.
 
@@ -596,7 +613,8 @@ class FixedSweep(object):
     def acquire(cls, n_local, d, m, chunk_rows, rank, world, device):
         """A workspace for one model: a recycled one of the same shape when a previous model has been dropped
         (building the views costs more host time than the kernels of a small shard leave room for)."""
-        key = (torch.device(device).index, int(n_local), int(d), int(m), int(chunk_rows), int(rank), int(world))
+        key = (torch.device(device).index, int(n_local), int(d), int(m), int(chunk_rows), int(rank), int(world),
+               get_stats_mode())
         free = cls._POOL.get(key)
         if free:
             fs = free.pop()

@@ -329,6 +329,13 @@ enum {
   EDRGP_FS_RHS, EDRGP_FS_ALPHA, EDRGP_FS_SCRATCH, EDRGP_FS_TAIL, EDRGP_FS_RESULT, EDRGP_FS_NREGIONS
 };
 size_t edrgp_fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int64_t* offsets);
+
+/* Statistics route of edrgp_fixed_stats: 0 = the FP64 DMMA reduction (edrgp_inducing_stats; default), 1 = the
+ * exact-product INT8 route (edrgp_inducing_stats_i8; m <= 2048, otherwise the FP64 route runs).  Process-wide and
+ * part of the workspace layout: set it BEFORE edrgp_fixed_layout sizes a workspace (route 1 adds room for one row
+ * block's slices, 6 chunk_rows m bytes).  Initial value from the environment: EDRGP_STATS = fp64 | int8x6. */
+int edrgp_set_stats_mode(int mode);
+int edrgp_get_stats_mode(void);
 int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const double* y, const double* Z, int64_t ldz,
                       const double* ell, int m, double sf2, int64_t chunk_rows, double* Kfu, int64_t ldk, int rank,
                       int world, void* h2d, int64_t h2d_ahead, void* workspace, void* stream);
