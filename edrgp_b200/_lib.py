@@ -47,6 +47,8 @@ SIGNATURES = {
     'edrgp_kmm': (_int, [_c_dp, _i64, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _i64, _int, _int, _c_dp]),
     'edrgp_solve_workspace_bytes': (_sz, [_int]),
     'edrgp_solve': (_int, [_c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+    'edrgp_vfe_grad_small_workspace_bytes': (_sz, [_int]),
+    'edrgp_vfe_grad_small': (_int, [_c_dp, _c_dp, _c_dp, _c_dp, _int, _dbl, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_potrf': (_int, [_c_dp, _int, _i64, _c_dp, _c_dp]),
     'edrgp_posv': (_int, [_c_dp, _int, _i64, _c_dp, _i64, _c_dp, _c_dp, _c_dp, _c_dp]),
     'edrgp_trsm': (_int, [_c_dp, _int, _c_dp, _int, _int, _c_dp]),

@@ -370,6 +370,17 @@ int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double bet
   return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "solve");
 }
 
+size_t edrgp_vfe_grad_small_workspace_bytes(int m) { return m > 0 ? (size_t)3 * m * m * sizeof(double) : 0; }
+
+int edrgp_vfe_grad_small(const double* LB, const double* Lm, const double* B, const double* c, int m, double beta,
+                         double* Msym, int64_t ldm, double* Dsym, double* sumAE, void* workspace, void* stream) {
+  if (!LB || !Lm || !B || !c || !Msym || !Dsym || !sumAE || !workspace || m <= 0 || ldm < m)
+    return fail(EDRGP_ERR_ARG, "vfe_grad_small: bad argument");
+  cudaError_t e = edrgp::launch_vfe_grad_small(LB, Lm, B, c, m, beta, Msym, ldm, Dsym, sumAE, (double*)workspace,
+                                               (cudaStream_t)stream);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "vfe_grad_small");
+}
+
 int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream) {
   if (!A || !info || m <= 0 || ld < m) return fail(EDRGP_ERR_ARG, "potrf: bad argument");
   cudaError_t e = edrgp::launch_potrf(A, m, ld, info, (cudaStream_t)stream);

@@ -35,6 +35,9 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, double beta, double* Bmat,
                          double* alpha, double* cvec, double* scalars, int* info, double* workspace,
                          cudaStream_t st);
+cudaError_t launch_vfe_grad_small(const double* LB, const double* Lm, const double* Bmat, const double* c, int m,
+                                  double beta, double* Msym, int64_t ldm, double* Dsym, double* sumAE,
+                                  double* workspace, cudaStream_t st);
 size_t eigh_workspace_doubles(int d);
 cudaError_t launch_eigh(double* A, int d, double* V, double* evals, double* comps, int* sweeps, cudaStream_t st);
 

@@ -805,6 +805,89 @@ cudaError_t launch_solve(double* Kmm, const double* P, const double* b, int m, d
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// The m x m part of the bound's hyper-parameter gradients (GPy VarDTC._compute_dL_dpsi / dL_dKmm,
+// reached from edrgp/gp_model/base.py:69 on every L-BFGS evaluation):
+//   E        = LB^-T (I + c c^T) LB^-1                      (DBi_plus_BiPBi)
+//   dL_dpsi2 = beta/2 Lm^-T (I - E) Lm^-1
+//   dL_dKmm  = Lm^-T (I - E/2 - B/2) Lm^-1,                 B = I + A as kept by the solve chain
+//   sumAE    = sum (B - I) o E
+// Outputs are the symmetrised forms the row pass and the Kuu part consume: Msym = (dL_dpsi2 + dL_dpsi2^T)/2 with
+// leading dimension ldm, Dsym likewise (m x m, dense).  workspace: 3 m^2 doubles.
+// ---------------------------------------------------------------------------------------------
+__global__ void eye_plus_outer_kernel(const double* __restrict__ c, int m, double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)m * m) return;
+  const int r = (int)(idx / m), q = (int)(idx % m);
+  out[idx] = fma(c[r], c[q], r == q ? 1.0 : 0.0);
+}
+
+// Et holds E^T: X2 = I - E, X3 = I - E/2 - B/2, partial sums of (B - I) o E per CTA (summed in order by the last step)
+__global__ void __launch_bounds__(256) grad_small_mid_kernel(const double* __restrict__ Et, const double* __restrict__ B, int m,
+                                                             double* __restrict__ X2, double* __restrict__ X3,
+                                                             double* __restrict__ part) {
+  __shared__ double red[256];
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0.0;
+  if (idx < (int64_t)m * m) {
+    const int r = (int)(idx / m), q = (int)(idx % m);
+    const double e = Et[(int64_t)q * m + r], b = B[idx], id = r == q ? 1.0 : 0.0;
+    X2[idx] = id - e;
+    X3[idx] = id - 0.5 * e - 0.5 * b;
+    a = (b - id) * e;
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+// out (ldo) = scale (T + T^T) / 2;  CTA 0 also folds the partial sums of the previous kernel into *sum
+__global__ void __launch_bounds__(256) sym_scale_kernel(const double* __restrict__ T, int m, double scale, double* __restrict__ out,
+                                                        int64_t ldo, const double* __restrict__ part, int nparts,
+                                                        double* __restrict__ sum) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (int64_t)m * m) {
+    const int r = (int)(idx / m), q = (int)(idx % m);
+    out[(int64_t)r * ldo + q] = scale * 0.5 * (T[(int64_t)r * m + q] + T[(int64_t)q * m + r]);
+  }
+  if (sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < nparts; ++i) a += part[i];
+    *sum = a;
+  }
+}
+
+cudaError_t launch_vfe_grad_small(const double* LB, const double* Lm, const double* Bmat, const double* c, int m,
+                                  double beta, double* Msym, int64_t ldm, double* Dsym, double* sumAE,
+                                  double* workspace, cudaStream_t st) {
+  double* W1 = workspace;
+  double* W2 = workspace + (size_t)m * m;
+  double* W3 = workspace + (size_t)2 * m * m;
+  const unsigned nb2 = (unsigned)(((int64_t)m * m + 255) / 256);
+  dim3 tg((m + 31) / 32, (m + 31) / 32), tb(32, 8);
+  cudaError_t e;
+  // L^-T X L^-1 for symmetric X: solve, transpose, solve (the result is left transposed; symmetric up to rounding)
+  auto both_sides = [&](const double* L, double* X, double* Xt) -> cudaError_t {
+    cudaError_t r = launch_trsm(L, m, m, X, m, m, 1, st);
+    if (r != cudaSuccess) return r;
+    transpose_kernel<<<tg, tb, 0, st>>>(X, m, Xt); count_launch();
+    return launch_trsm(L, m, m, Xt, m, m, 1, st);
+  };
+  eye_plus_outer_kernel<<<nb2, 256, 0, st>>>(c, m, W1); count_launch();
+  if ((e = both_sides(LB, W1, W2)) != cudaSuccess) return e;                       // W2 = E^T
+  // the partial sums live at the head of Dsym until the last kernel has folded them
+  grad_small_mid_kernel<<<nb2, 256, 0, st>>>(W2, Bmat, m, W1, W3, Dsym); count_launch();
+  if ((e = both_sides(Lm, W1, W2)) != cudaSuccess) return e;                       // W2 = (2/beta dL_dpsi2)^T
+  sym_scale_kernel<<<nb2, 256, 0, st>>>(W2, m, 0.5 * beta, Msym, ldm, Dsym, (int)nb2, sumAE); count_launch();
+  if ((e = both_sides(Lm, W3, W1)) != cudaSuccess) return e;                       // W1 = dL_dKmm^T
+  sym_scale_kernel<<<nb2, 256, 0, st>>>(W1, m, 1.0, Dsym, m, nullptr, 0, nullptr); count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitter, cudaStream_t st) {
   kmm_fix_kernel<<<(unsigned)(((int64_t)m * m + 255) / 256), 256, 0, st>>>(K, m, ld, sf2, jitter); count_launch();
   return cudaGetLastError();

@@ -609,16 +609,11 @@ class SparseGPRegression(object):
     def _gradients(self, P, res, beta, sf2, ell, trA, data_fit, yy, ldk):
         dev = self.device
         m, d, n = self.num_inducing, self.input_dim, self.num_data
-        eye = torch.eye(m, dtype=F64, device=dev)
-        c = res.c
-        E = _backsub_both_sides(res.LB, eye + torch.outer(c, c), 'left')        # DBi_plus_BiPBi
-        dL_dpsi2 = (0.5 * beta) * _backsub_both_sides(res.Lm, eye - E, 'left')
-        dL_dKmm = _backsub_both_sides(res.Lm, -0.5 * E - 0.5 * res.B + eye, 'left')
-        sumAE = float(((res.B - eye) * E).sum())
-        self.kernel_launches += 12
+        # the m x m chain (E, dL_dpsi2, dL_dKmm, sum A o E) in one C call: edrgp_vfe_grad_small
+        Mmat, Dsym, sumAE_dev = ops.vfe_grad_small(res, beta)
+        self.kernel_launches += 17
 
         # ---- pass 2 over the rows: T = Kfu o dL/dKfu and its contractions
-        Mmat = ops.even_ld(0.5 * (dL_dpsi2 + dL_dpsi2.t()))
         S = torch.zeros(m, self.d_even, dtype=F64, device=dev)
         cs = torch.zeros(m, dtype=F64, device=dev)
         mom = torch.zeros(2 * self.d_even, dtype=F64, device=dev)
@@ -663,7 +658,7 @@ class SparseGPRegression(object):
 
         # ---- Kuu part: T_mm = K(Z, Z) o dL/dKmm (GPy symmetrises through tmp + tmp.T)
         Kzz = ops.kmm(self._pack, sf2, 0.0)
-        Tm = Kzz * (0.5 * (dL_dKmm + dL_dKmm.t()))
+        Tm = Kzz * Dsym
         rs_m = Tm.sum(1)
         TZ = ops.gemm_tn(ops.even_ld(Tm), self._Z_dev, ka=m)[:, :d]         # Tm symmetric: Tm^T Z = Tm Z
         gZ = gZ + 2.0 * (TZ - rs_m[:, None] * Z) * il2
@@ -674,7 +669,7 @@ class SparseGPRegression(object):
         # ---- Kdiag part and the noise (GPy _compute_dL_dR + Gaussian.exact_inference_gradients)
         gvar = float(gvar) - 0.5 * beta * n
         dL_dR = (-0.5 * n * beta + 0.5 * yy * beta ** 2 + 0.5 * (n * sf2 * beta ** 2 - trA * beta)
-                 + beta * (0.5 * sumAE - data_fit))
+                 + beta * (0.5 * float(sumAE_dev) - data_fit))
         self.grad_variance = gvar
         glen = glen.cpu().numpy()
         self.grad_lengthscale = glen if self.kern.ARD else np.atleast_1d(glen.sum())

@@ -396,6 +396,24 @@ def solve(Kmm, P, b, beta):
     return out
 
 
+def vfe_grad_small(res, beta):
+    """The m x m chain of the bound's gradients from a ``solve`` result: (Msym with an even leading dimension,
+    Dsym, sumAE as a device scalar) -- see edrgp_vfe_grad_small."""
+    lib = _lib.load()
+    m = res.Lm.shape[0]
+    dev = res.Lm.device
+    ldm = m + (m & 1)
+    Msym = torch.zeros(m, ldm, dtype=F64, device=dev) if ldm != m else torch.empty(m, m, dtype=F64, device=dev)
+    Dsym = torch.empty(m, m, dtype=F64, device=dev)
+    sumAE = torch.empty(1, dtype=F64, device=dev)
+    ws = torch.empty(lib.edrgp_vfe_grad_small_workspace_bytes(m) // 8, dtype=F64, device=dev)
+    with _Timed('solve'):
+        _lib.check(lib.edrgp_vfe_grad_small(_ptr(res.LB), _ptr(res.Lm), _ptr(res.B), _ptr(res.c), m, float(beta),
+                                            _ptr(Msym), ldm, _ptr(Dsym), _ptr(sumAE), _ptr(ws), _stream()),
+                   'edrgp_vfe_grad_small')
+    return Msym, Dsym, sumAE
+
+
 def potrf(A):
     """In-place lower Cholesky of a symmetric (m, m) tensor; returns (A, info) with info a device int32
     (0, or 1 + index of the first non-positive pivot)."""

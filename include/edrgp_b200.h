@@ -227,6 +227,16 @@ int edrgp_solve(double* Kmm, const double* P, const double* b, int m, double bet
  * alpha = LS^-T LS^-1 (beta b): the fixed-hyper-parameter sweep needs nothing else of the chain. */
 int edrgp_potrf(double* A, int m, int64_t ld, int* info, void* stream);
 
+/* The m x m part of the hyper-parameter gradients of the bound (GPy VarDTC.inference: _compute_dL_dpsi and
+ * dL_dKmm, reached from edrgp/gp_model/base.py:69 on every optimiser evaluation), from the factors edrgp_solve left:
+ *     E = LB^-T (I + c c^T) LB^-1;   dL_dpsi2 = beta/2 Lm^-T (I - E) Lm^-1;   dL_dKmm = Lm^-T (I - E/2 - B/2) Lm^-1
+ * In:  LB, Lm (m, m) lower factors;  B (m, m) = I + A as kept in the first m^2 doubles of edrgp_solve's workspace;
+ *      c (m).   Out: Msym (m, ldm) = (dL_dpsi2 + dL_dpsi2^T) / 2;  Dsym (m, m) = (dL_dKmm + dL_dKmm^T) / 2;
+ *      sumAE[0] = sum (B - I) o E.   workspace: edrgp_vfe_grad_small_workspace_bytes(m). */
+size_t edrgp_vfe_grad_small_workspace_bytes(int m);
+int edrgp_vfe_grad_small(const double* LB, const double* Lm, const double* B, const double* c, int m, double beta,
+                         double* Msym, int64_t ldm, double* Dsym, double* sumAE, void* workspace, void* stream);
+
 /* A x = rhs by Cholesky with one right-hand side (LAPACK dposv, nrhs = 1): the posterior weights
  * alpha = (Kuu + beta P)^-1 beta b of the fixed-hyper-parameter sweep (GPy Posterior.woodbury_vector,
  * edrgp/gp_model/base.py:69,222) in one call.  One launch per 32-column blocked step (the diagonal
