@@ -3,14 +3,17 @@
 // edrgp/gp_model/base.py:69).
 //
 // The FP64 tensor pipe runs this reduction at 0.91 of its 37 TFLOP/s; the INT8 tensor cores of a B200 offer 4.5 POP/s.
-// Kfu entries lie in [0, sf2], so with t = K / (2 sf2) + 1 in [1, 1.5] the 52 mantissa bits of t are the fixed-point
-// fraction of K / (2 sf2) and its BYTES are unsigned 8-bit slices q_0 .. q_5 (q_s weighs 2^-8(s+1); 48 bits kept,
-// truncation below 2^-48).  Products of slices are exact in the 32-bit integer accumulators of tensor memory, slice
-// pairs (a, b) with the same a + b = g share an accumulator, pairs with a + b >= 6 (below the truncation of the
-// slices themselves) are dropped, and
-//     P = 4 sf2^2 sum_g 2^-8(g+2) A_g,       A_g = sum_{a+b=g} Q_a^T Q_b,   g = 0 .. 5  (21 pairs).
-// Downstream the result is indistinguishable from the FP64 statistics (P within 1e-13, alpha-consumers within the
-// FP64 path's own rounding: tools/int8_slice_syrk_study.py, profiles/r02_int8_slice_syrk_study.txt).
+// Kfu entries lie in [0, sf2], so with t = K / (4 sf2) + 1 in [1, 1.25] the 52 mantissa bits of t are the fixed-point
+// fraction x of K / (4 sf2).  x is ROUNDED to 48 bits and written in balanced radix 256: six SIGNED digits d_0 .. d_5 in
+// [-128, 127] with x = sum_s d_s 2^-8(s+1) (d_0 <= 65).  Products of digits are exact in the 32-bit integer
+// accumulators of tensor memory, digit pairs (a, b) with the same a + b = g share an accumulator, pairs with
+// a + b >= 6 are dropped, and
+//     P = 16 sf2^2 sum_g 2^-8(g+2) A_g,       A_g = sum_{a+b=g} D_a^T D_b,   g = 0 .. 5  (21 pairs).
+// Rounding and balanced digits make both error terms -- the 2^-49 rounding of x and the dropped pairs (weight 2^-64,
+// zero-mean products) -- ZERO-MEAN, so over n rows they grow like sqrt(n) and P comes out at FP64 rounding level
+// (1e-15 relative; measured in tests/test_i8_stats_gpu.py).  The first version of this route truncated x to unsigned
+// bytes: a one-sided error of 2^-48 per entry that adds up linearly (P at 6e-14), enough to lose positive
+// definiteness of Kuu + beta P for optimised low-noise models.
 //
 //   slice_u8_kernel   Kfu (n x m FP64, row-major) -> slice planes in the layout the MMA reads: per 128-row k-block,
 //                     per 128-column block and per slice one 16 KB block of 128 "rows" (inducing columns) x 128 bytes
@@ -20,7 +23,7 @@
 //                     3-5: six groups of 128 tensor-memory columns do not fit at once): warp 0 streams slices (the B
 //                     tile's per k-block, double buffered; the A tile's one at a time through a ring), warp 1 issues
 //                     tcgen05.mma.kind::i8 (M = N = 128, K = 32: 84 MMAs per k-block), warps 2-9 drain the
-//                     accumulators every 4 096 rows (255 x 255 x 6 pairs x 4 096 rows < 2^31) into FP64 registers.
+//                     accumulators every 16 384 rows (128 x 128 x 6 pairs x 16 384 rows < 2^31) into FP64 registers.
 //   i8_reduce_kernel  sums the row splits in fixed order, scales, writes P (both triangles), b and y^T y.
 #include <cstdint>
 #include <cstdlib>
@@ -39,7 +42,7 @@ constexpr int BBLK = ABLK;
 constexpr int A_STAGES = 2;                // 2 x 16 KB + 2 x 6 x 16 KB of B + barriers = 225 KB of the 227 KB a CTA may have
 constexpr int B_STAGES = 2;
 constexpr int BSL = GMAX + 1;              // slices of the B tile resident per k-block (second pass: all six)
-constexpr int DRAIN_KB = 32;               // k-blocks between drains of the int32 accumulators
+constexpr int DRAIN_KB = 128;              // k-blocks between drains of the int32 accumulators: 6 pairs x 128^2 x 16 384 rows < 2^31
 constexpr int EPI_W = 8;                   // two warps per tensor-memory lane quarter: 64 output columns per thread
 constexpr int NTHREADS = 32 * (2 + EPI_W);
 // Two passes over the CTA's rows, because six weight groups of 128 columns do not fit the 512 tensor-memory columns:
@@ -109,10 +112,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: D = S32, A = B = unsigned 8 bit, both K-major, dense (mma_sm100_desc: c_format 2 at bit 4,
-// a_format at bit 7, b_format at bit 10 -- 0 = unsigned --, N >> 3 at bit 17, M >> 4 at bit 24)
+// instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, dense (mma_sm100_desc: c_format 2 at bit 4,
+// a_format at bit 7, b_format at bit 10 -- 0 = unsigned, 1 = signed --, N >> 3 at bit 17, M >> 4 at bit 24)
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -135,22 +138,23 @@ __host__ __device__ inline uint32_t sw128_byte(int r, int k) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Slicing pass.  A CTA walks k-blocks (128 data rows); thread = (inducing column j of the current 128-column block,
-// half h of the rows); per group of 16 rows it forms one 16-byte piece of every slice's swizzled row j.
+// half h of the rows); per group of 32 rows it forms one 32-byte sector of every digit plane's swizzled row j.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* __restrict__ K, int64_t n, int m, int64_t ldk,
-                                                                  const double* __restrict__ y, double inv2sf2,
+                                                                  const double* __restrict__ y, double inv4sf2,
                                                                   uint8_t* __restrict__ planes, int njb, int64_t nkb,
                                                                   double* __restrict__ bpart, int accumulate) {
   const int tid = threadIdx.x, jl = tid & 127, h = tid >> 7;
   const int mp = njb * 128;
   __shared__ double ys[KBLK];
-  __shared__ double bsh[128];
+  // per-thread accumulators in shared memory (a thread owns its (half, column) slots: no races, no barriers):
+  // acc[h][0][j] = sum K_ij y_i, acc[h][1][j] = sum K_ij^2 -- the diagonal of P, which is taken from this FP64 sum:
+  // the dropped digit pair (3, 3) is a sum of squares there, the one place where a dropped term is not zero-mean
+  extern __shared__ double acc_sm[];
+  double* bsum = acc_sm + (size_t)h * 2 * mp;
+  double* dsum = bsum + mp;
+  for (int i = tid; i < 4 * mp; i += SLICE_THREADS) acc_sm[i] = 0.0;
   double yy = 0.0;
-  // b partials of this CTA: column j of block jb lives with thread jl, halves combined at the end
-  // (njb <= 16 covers m <= 2048)
-  double bacc[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) bacc[i] = 0.0;
   for (int64_t kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
     const int64_t row0 = kb * KBLK;
     __syncthreads();
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
       const int j = jb * 128 + jl;
       const bool jok = j < m;
       uint8_t* blk = planes + (((size_t)kb * njb + jb) * S) * ABLK;
-      double bj = 0.0;
+      double bj = 0.0, dj = 0.0;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {                       // 32-row pieces of this thread's half: chunks 2 cp, 2 cp + 1
         const int cp = 2 * h + c;
@@ -185,10 +189,18 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
           double v = 0.0;
           if (jok && r < n) v = __ldg(K + r * ldk + j);
           bj = fma(v, ys[il], bj);
-          const double t = fma(v, inv2sf2, 1.0);
-          const uint32_t hi = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
-          const uint32_t q0 = (hi >> 12) & 0xFFu, q1 = (hi >> 4) & 0xFFu, q2 = ((hi & 0xFu) << 4) | (lo >> 28);
-          const uint32_t q3 = (lo >> 20) & 0xFFu, q4 = (lo >> 12) & 0xFFu, q5 = (lo >> 4) & 0xFFu;
+          dj = fma(v, v, dj);
+          const double t = fma(v, inv4sf2, 1.0);
+          // 52-bit fraction -> rounded to 48 bits -> balanced digits: adding 0x80 to the five low bytes lets the
+          // carries run, after which byte ^ 0x80 (as int8) is the digit; the top byte takes the last carry as it is
+          const unsigned long long F = ((unsigned long long)((uint32_t)__double2hiint(t) & 0xFFFFFu) << 32) |
+                                       (uint32_t)__double2loint(t);
+          // (round half to EVEN: half-up is biased by 2^-53 per entry, which adds up linearly over the rows -- measured
+          // 4e-15 on P at 524 288 rows against 1e-16-level noise otherwise)
+          const unsigned long long R = (((F + 7ull + ((F >> 4) & 1ull)) >> 4) + 0x0000008080808080ull) ^ 0x0000008080808080ull;
+          const uint32_t rl = (uint32_t)R, rh = (uint32_t)(R >> 32);
+          const uint32_t q0 = (rh >> 8) & 0xFFu, q1 = rh & 0xFFu, q2 = rl >> 24;
+          const uint32_t q3 = (rl >> 16) & 0xFFu, q4 = (rl >> 8) & 0xFFu, q5 = rl & 0xFFu;
           const int wi = e >> 2, sh = (e & 3) * 8;
           w[0][wi] |= q0 << sh; w[1][wi] |= q1 << sh; w[2][wi] |= q2 << sh;
           w[3][wi] |= q3 << sh; w[4][wi] |= q4 << sh; w[5][wi] |= q5 << sh;
@@ -200,21 +212,15 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
           *reinterpret_cast<uint4*>(blk + (size_t)s * ABLK + off1) = make_uint4(w[s][4], w[s][5], w[s][6], w[s][7]);
         }
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i == jb) bacc[i] += bj;
+      bsum[j] += bj;
+      dsum[j] += dj;
     }
   }
-  // per-CTA partials: bpart[cta][0 .. mp) = Kfu^T y over this CTA's rows, bpart[cta][mp] = y^T y
-  double* out = bpart + (size_t)blockIdx.x * (mp + 1);
-  for (int jb = 0; jb < njb; ++jb) {
-    double v = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) if (i == jb) v = bacc[i];
-    __syncthreads();
-    if (h == 1) bsh[jl] = v;
-    __syncthreads();
-    if (h == 0) out[jb * 128 + jl] = v + bsh[jl] + (accumulate ? out[jb * 128 + jl] : 0.0);
-  }
+  // per-CTA partials: bpart[cta] = [Kfu^T y (mp) | diag(Kfu^T Kfu) (mp) | y^T y] over this CTA's rows
+  double* out = bpart + (size_t)blockIdx.x * (2 * mp + 1);
+  __syncthreads();
+  for (int i = tid; i < 2 * mp; i += SLICE_THREADS)
+    out[i] = acc_sm[i] + acc_sm[2 * mp + i] + (accumulate ? out[i] : 0.0);
   __syncthreads();
   ys[tid & 127] = 0.0;
   __syncthreads();
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) slice_u8_kernel(const double* _
   if (tid == 0) {
     double s = 0.0;
     for (int i = 0; i < KBLK; ++i) s += ys[i];
-    out[mp] = s + (accumulate ? out[mp] : 0.0);
+    out[2 * mp] = s + (accumulate ? out[2 * mp] : 0.0);
   }
 }
 
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) syrk_i8_kernel(const Params p) {
         for (int64_t k = 0; k < nk; ++k, ++ib) {
           const bool first = (k % DRAIN_KB) == 0;
           if (first && idr > 0) {
-            // the accumulators of the previous 4 096 rows (or of the previous pass) must have been drained
+            // the accumulators of the previous 16 384 rows (or of the previous pass) must have been drained
             mbar_wait(&bars->acc_empty, (uint32_t)((idr - 1) & 1));
             tc_fence_after();
           }
@@ -388,17 +394,21 @@ __global__ void __launch_bounds__(256) i8_reduce_kernel(const double* __restrict
     const int j = ta * TM + e / TN, jp = tb * TN + e % TN;
     if (j < m && jp < m) {
       double s = 0.0;
-      for (int sp = 0; sp < nsplit; ++sp) s += part[((size_t)sp * ntiles + tile) * (TM * TN) + e];
-      s *= scale;
+      if (j == jp) {             // the diagonal: the slicer's FP64 sums of squares
+        for (int c = 0; c < nb; ++c) s += bpart[(size_t)c * (2 * mp + 1) + mp + j];
+      } else {
+        for (int sp = 0; sp < nsplit; ++sp) s += part[((size_t)sp * ntiles + tile) * (TM * TN) + e];
+        s *= scale;
+      }
       P[(int64_t)j * ldp + jp] = accumulate ? P[(int64_t)j * ldp + jp] + s : s;
       // the mirror entry is written here unless the tile is a diagonal one (which computes both triangles itself)
       if (tb > ta) P[(int64_t)jp * ldp + j] = accumulate ? P[(int64_t)jp * ldp + j] + s : s;
     }
   }
   if (b_yy != nullptr && idx <= m) {
-    const int col = idx < m ? (int)idx : mp;
+    const int col = idx < m ? (int)idx : 2 * mp;
     double s = 0.0;
-    for (int c = 0; c < nb; ++c) s += bpart[(size_t)c * (mp + 1) + col];
+    for (int c = 0; c < nb; ++c) s += bpart[(size_t)c * (2 * mp + 1) + col];
     b_yy[idx] = accumulate ? b_yy[idx] + s : s;
   }
 }
@@ -433,7 +443,7 @@ static Layout layout(int64_t n, int m, int sms) {
   const int64_t nkb = (n + KBLK - 1) / KBLK;
   size_t o = 0;
   L.part = o;   o += (size_t)L.nsplit * L.ntiles * TM * TN * 8;
-  L.bpart = o;  o += (size_t)L.sgrid * (L.mp + 1) * 8;
+  L.bpart = o;  o += (size_t)L.sgrid * (2 * L.mp + 1) * 8;
   L.tiles = o;  o += ((size_t)2 * L.ntiles * 4 + 1023) / 1024 * 1024;
   L.planes = o; o += (size_t)nkb * L.njb * S * ABLK;
   L.total = (o + 1023) / 1024 * 1024;
@@ -458,7 +468,13 @@ cudaError_t launch_i8_block(const double* Kfu, int64_t n, int m, int64_t ldk, co
     if ((e = cudaMemcpyAsync(tiles, host_tiles, (size_t)2 * L.ntiles * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess)
       return e;
   }
-  i8::slice_u8_kernel<<<L.sgrid, i8::SLICE_THREADS, 0, st>>>(Kfu, n, m, ldk, y, 0.5 / sf2, ws + L.planes, L.njb, nkb,
+  const size_t slice_smem = (size_t)4 * L.mp * sizeof(double);
+  static bool slice_attr_set = false;
+  if (!slice_attr_set && slice_smem > 40 * 1024) {
+    if ((e = cudaFuncSetAttribute(i8::slice_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 8)) != cudaSuccess) return e;
+    slice_attr_set = true;
+  }
+  i8::slice_u8_kernel<<<L.sgrid, i8::SLICE_THREADS, slice_smem, st>>>(Kfu, n, m, ldk, y, 0.25 / sf2, ws + L.planes, L.njb, nkb,
                                                              reinterpret_cast<double*>(ws + L.bpart), first ? 0 : 1);
   count_launch();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -477,7 +493,7 @@ cudaError_t launch_i8_block(const double* Kfu, int64_t n, int m, int64_t ldk, co
   return cudaGetLastError();
 }
 
-// P (+)= 4 sf2^2 x the sum of the split partials (fixed order), b_yy (+)= the slicer's partials
+// P (+)= 16 sf2^2 x the sum of the split partials (fixed order), b_yy (+)= the slicer's partials
 cudaError_t launch_i8_finish(int m, double sf2, int with_y, double* P, int64_t ldp, double* b_yy, int accumulate,
                              void* workspace, int sms, cudaStream_t st) {
   const i8::Layout L = i8::layout(0, m, sms);
@@ -485,7 +501,7 @@ cudaError_t launch_i8_finish(int m, double sf2, int with_y, double* P, int64_t l
   const int64_t total = (int64_t)L.ntiles * i8::TM * i8::TN;
   i8::i8_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       reinterpret_cast<const double*>(ws + L.part), L.nsplit, L.ntiles, reinterpret_cast<const int*>(ws + L.tiles), m,
-      4.0 * sf2 * sf2, P, ldp, accumulate, reinterpret_cast<const double*>(ws + L.bpart), L.sgrid, L.mp,
+      16.0 * sf2 * sf2, P, ldp, accumulate, reinterpret_cast<const double*>(ws + L.bpart), L.sgrid, L.mp,
       with_y ? b_yy : nullptr);
   count_launch();
   return cudaGetLastError();

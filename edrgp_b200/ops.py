@@ -316,8 +316,8 @@ def inducing_stats(K, y, m=None, P=None, b_yy=None, accumulate=False):
 
 
 def inducing_stats_i8(K, y, sf2, m=None, P=None, b_yy=None, accumulate=False):
-    """``inducing_stats`` on the INT8 tensor cores (exact products of six 8-bit slices of K / (2 sf2)): K (n, ldk) must
-    hold kernel entries in [0, sf2] as written by ``kuf`` with the same ``sf2``."""
+    """``inducing_stats`` on the INT8 tensor cores (exact products of six signed radix-256 digits of K / (4 sf2)):
+    K (n, ldk) must hold kernel entries in [0, sf2] as written by ``kuf`` with the same ``sf2``."""
     lib = _lib.load()
     _need_cuda(K, y, P, b_yy)
     n, ldk = K.shape
@@ -600,8 +600,8 @@ STATS_MODES = ('fp64', 'int8x6')
 
 def set_stats_mode(mode):
     """Statistics route of the composite sweep (edrgp_set_stats_mode): 'fp64' -- the FP64 DMMA reduction, the
-    default -- or 'int8x6' -- exact integer products of six 8-bit slices on the INT8 tensor cores, P within 1e-13
-    of the FP64 reduction and ~1.5 x faster.  Process-wide; workspaces are pooled per mode.  The environment
+    default -- or 'int8x6' -- exact integer products of six signed 8-bit digits on the INT8 tensor cores, P at FP64
+    rounding level and ~1.5 x faster.  Process-wide; workspaces are pooled per mode.  The environment
     variable EDRGP_STATS sets the initial value."""
     if mode not in STATS_MODES:
         raise ValueError("stats mode must be one of %s (got %r)" % (STATS_MODES, mode))

@@ -296,12 +296,13 @@ int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, dou
 /* ---------------------------------------------------------------------------------------------
  * K2 on the INT8 tensor cores (tcgen05.mma.kind::i8): the same statistics as edrgp_inducing_stats --
  * P (+)= Kfu^T Kfu, b_yy[:m] (+)= Kfu^T y, b_yy[m] (+)= y^T y (GPy tdot(psi1) / psi1^T Y in VarDTC.inference,
- * edrgp/gp_model/base.py:69) -- from EXACT integer products: Kfu entries, which lie in [0, sf2], are cut into six
- * unsigned 8-bit slices of K / (2 sf2) (48 bits, truncated), slice products accumulate in 32-bit integers in tensor
- * memory, pairs of equal weight share an accumulator, and P = 4 sf2^2 sum_g 2^-8(g+2) A_g.  P agrees with the FP64
- * reduction to ~1e-13 (max norm, relative) and what consumes it downstream to the FP64 path's own rounding.
+ * edrgp/gp_model/base.py:69) -- from EXACT integer products: Kfu entries, which must lie in [0, sf2], are rounded to
+ * 48 fraction bits of K / (4 sf2) and written as six signed radix-256 digits (balanced, [-128, 127]); digit products
+ * accumulate in 32-bit integers in tensor memory, pairs of equal weight share an accumulator, and
+ * P = 16 sf2^2 sum_g 2^-8(g+2) A_g.  Both error terms (rounding at 2^-49, dropped pairs of weight 2^-64) are
+ * zero-mean, so P agrees with the FP64 reduction to FP64 rounding level (~1e-15 of max |P|).
  * Kfu (n, ldk) row-major as written by edrgp_kuf with THIS sf2; y, b_yy may both be NULL; m <= 2048.
- * workspace: edrgp_inducing_stats_i8_workspace_bytes(n, m) (the slice planes of the block: 6 n m bytes).
+ * workspace: edrgp_inducing_stats_i8_workspace_bytes(n, m) (the digit planes of the block: 6 n m bytes).
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_inducing_stats_i8_workspace_bytes(int64_t n, int m);
 int edrgp_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2, double* P,

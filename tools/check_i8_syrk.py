@@ -62,4 +62,10 @@ t64 = timed(lambda: ops.inducing_stats(K, y, m))
 t8 = timed(lambda: ops.inducing_stats_i8(K, y, 1.0, m))
 P0, _ = ops.inducing_stats(K, y, m)
 P1, _ = ops.inducing_stats_i8(K, y, 1.0, m)
-print(json.dumps({'rows': n, 'fp64_dmma_ms': t64, 'int8_ms': t8, 'rel_P': float((P1 - P0).abs().max() / P0.abs().max())}))
+# extended-precision reference for a 24-column corner (the full product is too slow on the host)
+Kc = K[:, :24].cpu().numpy().astype(np.longdouble)
+Pld = (Kc.T @ Kc).astype(np.float64)
+pmax = float(P0.abs().max())
+print(json.dumps({'rows': n, 'fp64_dmma_ms': t64, 'int8_ms': t8, 'rel_P': float((P1 - P0).abs().max() / pmax),
+                  'corner24_rel_err_fp64_dmma': float(np.max(np.abs(P0[:24, :24].cpu().numpy() - Pld)) / pmax),
+                  'corner24_rel_err_int8x6': float(np.max(np.abs(P1[:24, :24].cpu().numpy() - Pld)) / pmax)}))
