@@ -300,7 +300,7 @@ int edrgp_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, co
   if (m > 2048) return fail(EDRGP_ERR_UNSUPPORTED, "inducing_stats_i8: m=%d > 2048", m);
   if ((y == nullptr) != (b_yy == nullptr)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: y and b_yy go together");
   if (!(sf2 > 0.0) || !(sf2 < 1e150)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: the kernel variance must be positive and finite");
-  if (!aligned16(workspace)) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: the workspace must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(workspace) & 127) return fail(EDRGP_ERR_ARG, "inducing_stats_i8: the workspace must be 128-byte aligned");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "inducing_stats_i8: no CUDA device");
   cudaError_t e = edrgp::launch_inducing_stats_i8(Kfu, n, m, ldk, y, sf2, P, ldp, b_yy, accumulate, workspace, sms,
@@ -576,6 +576,7 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
   double* P = c.at(edrgp::FS_STATS);
   double* byy = P + (size_t)m * m;
   const int i8 = stats_mode_for(m, sf2);
+  void* i8ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(c.at(edrgp::FS_SCRATCH)) + 1023) & ~(uintptr_t)1023);
   for (int64_t s = 0; s < n; s += chunk_rows) {
     const int64_t rows = n - s < chunk_rows ? n - s : chunk_rows;
     double* Kc = Kfu + s * ldk;
@@ -588,10 +589,10 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
     }
     StageScope t(EDRGP_STAGE_STATS, st);
     if (i8) {
-      if ((e = edrgp::launch_i8_block(Kc, rows, m, ldk, targets + s, sf2, s == 0, c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess)
+      if ((e = edrgp::launch_i8_block(Kc, rows, m, ldk, targets + s, sf2, s == 0, i8ws, c.sms, st)) != cudaSuccess)
         return cuda_fail(e, "fixed_stats");
       if (s + rows >= n &&
-          (e = edrgp::launch_i8_finish(m, sf2, 1, P, m, byy, 0, c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess)
+          (e = edrgp::launch_i8_finish(m, sf2, 1, P, m, byy, 0, i8ws, c.sms, st)) != cudaSuccess)
         return cuda_fail(e, "fixed_stats");
     } else if ((e = edrgp::launch_gemm_tn(Kc, ldk, m, nullptr, 0, 0, rows, 1, targets + s, P, m, byy, s > 0,
                                           c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) {

@@ -164,7 +164,9 @@ size_t fixed_layout(int64_t n, int d, int m, int64_t chunk_rows, int world, int 
   if (eig > scratch) scratch = eig;
   if (mom > scratch) scratch = mom;
   if (stats_mode == 1) {
-    const size_t i8 = inducing_stats_i8_workspace_bytes(rows, m, sms) / 8;
+    // + 1 KB: the digit planes are placed on a 1 KB boundary inside the scratch region (32-byte sector stores and
+    // 16 KB bulk copies; measured with a 16-byte aligned base: 1.33 instead of 0.94 ms for the digit pass)
+    const size_t i8 = (inducing_stats_i8_workspace_bytes(rows, m, sms) + 1024) / 8;
     if (i8 > scratch) scratch = i8;
   }
   size_t o = 0;

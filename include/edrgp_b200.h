@@ -302,7 +302,8 @@ int edrgp_project(const double* X, int64_t n, int d, const double* V, int k, dou
  * P = 16 sf2^2 sum_g 2^-8(g+2) A_g.  Both error terms (rounding at 2^-49, dropped pairs of weight 2^-64) are
  * zero-mean, so P agrees with the FP64 reduction to FP64 rounding level (~1e-15 of max |P|).
  * Kfu (n, ldk) row-major as written by edrgp_kuf with THIS sf2; y, b_yy may both be NULL; m <= 2048.
- * workspace: edrgp_inducing_stats_i8_workspace_bytes(n, m) (the digit planes of the block: 6 n m bytes).
+ * workspace: edrgp_inducing_stats_i8_workspace_bytes(n, m) (the digit planes of the block: 6 n m bytes), 128-byte
+ * aligned (the planes are written in 32-byte sectors and read with 16 KB bulk copies).
  * ------------------------------------------------------------------------------------------- */
 size_t edrgp_inducing_stats_i8_workspace_bytes(int64_t n, int m);
 int edrgp_inducing_stats_i8(const double* Kfu, int64_t n, int m, int64_t ldk, const double* y, double sf2, double* P,
