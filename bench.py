@@ -397,8 +397,7 @@ def run_ours(args):
     # ---- the same sweep with the statistics on the INT8 tensor cores (informational unless --stats int8x6 made it
     # the headline): exact integer products of six 8-bit slices of Kfu, everything else unchanged
     int8_mode = None
-    if (d + (d & 1) <= 64 and args.precision == 'fp64' and args.stats == 'fp64' and not args.no_int8 and not args.pca
-            and m <= 2048):
+    if args.precision == 'fp64' and args.stats == 'fp64' and not args.no_int8 and m <= 2048:
         ops.set_stats_mode('int8x6')
         try:
             for _ in range(3):
@@ -584,6 +583,23 @@ def run_ours(args):
         "tf32x3_mode": tf32_mode,
         "int8x6_stats_mode": int8_mode,
     }
+    if args.stats == 'int8x6':
+        # the headline ran with the statistics on the INT8 tensor cores: describe THAT stage (digit pass + reduction +
+        # split sum are bracketed together by the library's stage timer)
+        nt = (m + 127) // 128
+        ops_row = 21 * 2.0 * (nt * (nt + 1) // 2) * 128 * 128           # executed: 21 digit pairs on the upper tiles
+        tops = ops_row * rows_per_launch_syrk / (syrk_avg_ms * 1e-3) / 1e12 if syrk_avg_ms else 0.0
+        line["dtype"] = "f64 (inducing statistics: exact int8 digit products, int32 accumulators)"
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "slice_u8_kernel + syrk_i8_kernel + i8_reduce_kernel (the statistics stage per row block)",
+            "achieved": tops, "peak": 4500.0, "unit": "TOP/s", "frac": tops / 4500.0,
+            "peak_source": "NOMINAL dense INT8 rate of a B200 (4.5 POP/s): MEASURED_PEAKS.json has no INT8 figure",
+            "ops_counted": "EXECUTED by syrk_i8_kernel: 21 digit pairs x 2 x 128 x 128 per row on the %d upper 128 x 128 "
+                           "tiles; the stage time also contains the HBM-bound digit pass (about 40 %% of it)" % (nt * (nt + 1) // 2),
+            "achieved_fp64_equivalent_tflops": syrk_tf, "fp64_dmma_peak_tflops": peak,
+            "fp64_equivalent_note": "the algorithmic 2 m^2 + 2 m FP64 flops per row this stage replaces, over its time",
+            "traffic": None, "traffic_source": "profiles/r02_ncu_top_kernels.txt (per kernel)",
+            "avg_launch_ms": syrk_avg_ms, "launches": syrk_n, "share_of_step": syrk_ms / total_ms}
     print(json.dumps(line), file=real_stdout)
     real_stdout.flush()
     if world > 1:

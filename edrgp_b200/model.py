@@ -450,6 +450,8 @@ class SparseGPRegression(object):
         # the FP64 cross-covariance kernel flags rows holding a NaN / Inf as it forms their norms: the input scan of
         # check_X_y without another pass over X
         self._kuf_flag = torch.zeros(1, dtype=torch.int32, device=dev) if pack32 is None else None
+        # statistics route (ops.set_stats_mode): exact INT8 digit products for FP64 kernel entries in [0, sf2]
+        i8_stats = pack32 is None and m <= 2048 and sf2 < 1e150 and ops.get_stats_mode() == 'int8x6'
         for i, (s, e) in enumerate(self._chunks()):
             if self._row_loader is not None:
                 self._row_loader(s, e)
@@ -459,7 +461,10 @@ class SparseGPRegression(object):
             else:
                 ops.kuf(self.X[s:e], self._pack, sf2, out=Kc, flag=self._kuf_flag)
             y = self._ensure_y()
-            ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
+            if i8_stats:
+                ops.inducing_stats_i8(Kc, y[s:e], sf2, m, P=P, b_yy=byy, accumulate=i > 0)
+            else:
+                ops.inducing_stats(Kc, y[s:e], m, P=P, b_yy=byy, accumulate=i > 0)
             self.kernel_launches += 4
         if self.n_local == 0:
             self._ensure_y()

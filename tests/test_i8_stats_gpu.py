@@ -124,3 +124,31 @@ def test_sweep_with_int8_statistics(n, d, m, chunk, int8_route):
     assert _rel(P8, P64) < 3e-14
     assert _rel(G8, G64) < 1e-8
     assert _rel(C8, C64) < 1e-8
+
+
+def test_generic_pass_with_int8_statistics(int8_route):
+    """d > 64 runs the row passes outside the composite sweep (feature-blocked kernels): the INT8 route there, against
+    the FP64 route and the oracle; also the bound and the hyper-parameter gradients (the optimiser's evaluation)."""
+    from edrgp_b200 import model
+    n, d, m = 3000, 96, 160
+    w = op.make_workload(n, d, m, seed=5, k_true=2)
+
+    def run():
+        mod = model.SparseGPRegression(w['X'], w['y'][:, None], kernel=model.RBF(d, w['sf2'], w['ell'], ARD=True), Z=w['Z'],
+                                       normalizer=True, noise_var=w['noise'], chunk_rows=1024)
+        P = mod._stats[0].cpu().numpy().copy()
+        G, C = mod.gradient_gram(want_G=True, want_C=True)
+        assert mod._fixed is None
+        ll = float(mod.log_likelihood()[0, 0])
+        mod._need_grad = True
+        mod.parameters_changed()
+        mod._need_grad = False
+        return P, G.cpu().numpy(), ll, np.array(mod.grad_lengthscale), mod.grad_variance, mod.grad_noise
+
+    P8, G8, ll8, gl8, gv8, gn8 = run()
+    int8_route.set_stats_mode('fp64')
+    P64, G64, ll64, gl64, gv64, gn64 = run()
+    assert 0 < _rel(P8, P64) < 3e-14            # the route ran (not bit-identical) and agrees
+    assert _rel(G8, G64) < 1e-8
+    assert abs(ll8 - ll64) < 1e-9 * abs(ll64)
+    assert _rel(gl8, gl64) < 1e-7 and abs(gv8 - gv64) < 1e-7 * abs(gv64) and abs(gn8 - gn64) < 1e-7 * abs(gn64)
