@@ -417,7 +417,6 @@ size_t edrgp_col_moments_workspace_bytes(int d) {
 int edrgp_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight, double* out,
                       int accumulate, void* workspace, void* stream) {
   if (!X || !out || !workspace || n <= 0 || d <= 0) return fail(EDRGP_ERR_ARG, "col_moments: bad argument");
-  if (d > 512) return fail(EDRGP_ERR_UNSUPPORTED, "col_moments: d > 512");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(EDRGP_ERR_CUDA, "col_moments: no CUDA device");
   cudaError_t e = edrgp::launch_col_moments(X, n, d, shift, weight, out, accumulate, (double*)workspace, sms,

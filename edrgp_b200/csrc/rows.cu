@@ -14,7 +14,7 @@ constexpr int CM_THREADS = 256;
 
 // part[blk][0][q] = sum_i w_i (x_iq - shift_q),  part[blk][1][q] = sum_i w_i (x_iq - shift_q)^2
 // over the rows of this CTA; deterministic two-stage reduction (no atomics).
-__global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* __restrict__ X, int64_t n, int d,
+__global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* __restrict__ X, int64_t n, int d, int64_t ldx,
                                                                  const double* __restrict__ shift,
                                                                  const double* __restrict__ weight,
                                                                  double* __restrict__ part) {
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* _
   for (int c = 0; c < 16; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
   if (active) {
     for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + tr; r < n; r += (int64_t)gridDim.x * rows_per_pass) {
-      const double* xr = X + r * d;
+      const double* xr = X + r * ldx;
       const double w = weight ? weight[r] : 1.0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(CM_THREADS) col_moments_kernel(const double* _
 // one warp per output (2 d of them): lanes stride over the CTA partials with two accumulators, then a
 // shuffle tree; fixed order, deterministic
 __global__ void __launch_bounds__(256) col_moments_reduce_kernel(const double* __restrict__ part, int nblk, int d,
-                                                                 double* __restrict__ out, int accumulate) {
+                                                                 double* __restrict__ out, int64_t ostride, int accumulate) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= 2 * d) return;
   const int k = i / d, q = i - k * d;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) col_moments_reduce_kernel(const double* _
   double s = s0 + s1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[i] = accumulate ? out[i] + s : s;
+  if (lane == 0) { double* o = out + k * ostride + q; *o = accumulate ? *o + s : s; }
 }
 
 __global__ void standardize_kernel(const double* __restrict__ X, int64_t total, int d, const double* __restrict__ mean,
@@ -169,17 +169,22 @@ size_t col_moments_workspace_bytes(int d, int sms) { return (size_t)sms * 4 * 2 
 
 cudaError_t launch_col_moments(const double* X, int64_t n, int d, const double* shift, const double* weight,
                                double* out, int accumulate, double* workspace, int sms, cudaStream_t st) {
-  if (d > 512) return cudaErrorInvalidValue;
-  int grid = sms * 4;
-  const int lanes = d < 32 ? d : 32;
-  const int rows_per_pass = CM_THREADS / lanes;
-  const int64_t need = (n + rows_per_pass - 1) / rows_per_pass;
-  if (grid > need) grid = (int)need;
-  col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X, n, d, shift, weight, workspace); count_launch();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  col_moments_reduce_kernel<<<(2 * d * 32 + 255) / 256, 256, 0, st>>>(workspace, grid, d, out, accumulate); count_launch();
-  return cudaGetLastError();
+  // a thread keeps 16 column sums: inputs wider than 512 columns are walked in blocks of 512 (out = [2][d])
+  for (int c0 = 0; c0 < d; c0 += 512) {
+    const int dc = d - c0 < 512 ? d - c0 : 512;
+    int grid = sms * 4;
+    const int lanes = dc < 32 ? dc : 32;
+    const int rows_per_pass = CM_THREADS / lanes;
+    const int64_t need = (n + rows_per_pass - 1) / rows_per_pass;
+    if (grid > need) grid = (int)need;
+    col_moments_kernel<<<grid, CM_THREADS, CM_THREADS * sizeof(double), st>>>(X + c0, n, dc, d, shift ? shift + c0 : nullptr,
+                                                                                weight, workspace); count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    col_moments_reduce_kernel<<<(2 * dc * 32 + 255) / 256, 256, 0, st>>>(workspace, grid, dc, out + c0, d, accumulate); count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_standardize(const double* X, int64_t n, int d, const double* mean, const double* scale, double* out,

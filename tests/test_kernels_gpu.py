@@ -155,7 +155,7 @@ def test_projection_matches_numpy(n, d, k):
 
 
 @pytest.mark.parametrize("n,d", [(1, 1), (7, 1), (100000, 1), (500001, 1), (999, 10), (4097, 33), (20000, 64), (3000, 200),
-                                 (513, 512)])
+                                 (513, 512), (300, 513), (257, 1300)])
 def test_col_moments_match_numpy(n, d):
     """Column sums and sums of squares about a shift, optionally weighted (the scaler / normaliser moments
     and the lengthscale-gradient moment): tree reductions, deterministic."""
