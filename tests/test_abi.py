@@ -96,3 +96,38 @@ def test_fixed_sweep_layout_and_tail_decoding():
     tail[1:] = [4e6, 0.25, 1.75]
     assert ops.FixedSweep.decode_tail(tail) == (3, 41, 4e6, 0.25, 1.75)
     assert ops.FixedSweep.supported(64, 10) and not ops.FixedSweep.supported(66, 10) and not ops.FixedSweep.supported(64, 0)
+
+
+def test_stats_mode_switch_and_layout():
+    """The statistics route is process-wide state of the library (no GPU needed to flip it): the sweep workspace
+    grows by one row block's digit planes (6 bytes per Kfu entry) when the INT8 route is on, the offsets of the
+    regions in front of the scratch area do not move, and the Python pool keys workspaces by route."""
+    import ctypes
+    from edrgp_b200 import _lib, ops
+    lib = _lib.load()
+    names = ops.FixedSweep.REGIONS
+    assert ops.get_stats_mode() in ops.STATS_MODES
+    before = ops.get_stats_mode()
+    try:
+        ops.set_stats_mode('fp64')
+        off64 = (ctypes.c_int64 * len(names))()
+        n64 = lib.edrgp_fixed_layout(2000000, 64, 512, 524288, 1, off64)
+        ops.set_stats_mode('int8x6')
+        assert ops.get_stats_mode() == 'int8x6' and lib.edrgp_get_stats_mode() == 1
+        off8 = (ctypes.c_int64 * len(names))()
+        n8 = lib.edrgp_fixed_layout(2000000, 64, 512, 524288, 1, off8)
+        planes = 524288 * 512 * 6
+        assert n8 - n64 >= planes - (n64 - 8 * dict(zip(names, off64))['scratch']) and n8 > n64
+        assert n8 >= lib.edrgp_inducing_stats_i8_workspace_bytes(524288, 512) >= planes
+        i = names.index('scratch')
+        assert list(off8)[:i + 1] == list(off64)[:i + 1]
+        # m beyond the INT8 kernels: the FP64 route's layout
+        big8 = lib.edrgp_fixed_layout(100000, 64, 4096, 65536, 1, off8)
+        ops.set_stats_mode('fp64')
+        assert big8 == lib.edrgp_fixed_layout(100000, 64, 4096, 65536, 1, off64)
+        assert lib.edrgp_inducing_stats_i8_workspace_bytes(1000, 4096) == 0
+        with pytest.raises(ValueError):
+            ops.set_stats_mode('int8x5')
+        assert lib.edrgp_set_stats_mode(7) != 0
+    finally:
+        ops.set_stats_mode(before)
