@@ -496,12 +496,19 @@ __global__ void reduce_gram_kernel(const double* __restrict__ Cpart, int nparts,
 // warps per scheduler, 92 registers) ran at 60.6 % against 62.2 %, and a register-only microbenchmark shows that two
 // warps per scheduler saturate the pipe even with ONE accumulator chain each (tools/dmma_chain.cu), so neither
 // occupancy nor accumulator dependencies are the limiter.  DMMA + FP64 pipe time add up to 74 % of the cycles.
+// Also tried at the end of round 2 and not kept (same time within 1 %): 128-bit fragment loads (lane t owning the
+// features 4t .. 4t+3 of a 16-feature group: half the LDS instructions), and the exponentials' dependent chains woven
+// into the DMMA stream one step per three DMMAs (ptxas -O3 re-clusters them; with -O1 the SASS is woven and the time is
+// the same), a start-up skew of 400 cycles between the two warps of a scheduler (in case they ran their DMMA and
+// exponential bursts in phase).  What did help: not forming the row sums when nobody asks for them (three FP64 instructions per pair).
 // SIMPLE: entries are stored, nothing is multiplied in and no Kfu^T y is accumulated -- the statistics
 // pass.  Its tile loop is software pipelined: the exp + store of inducing tile t is interleaved, at
 // source level and branch-free, with the distance contraction of tile t + 1, so that the DMMA pipe
 // is fed while the FP64 exponentials of the previous tile retire (both warps of a sub-partition
 // otherwise reach their exp phase together behind the shared tile barrier: 57 % pipe use, ncu r01).
-template <int DP, int XS, int NS, bool SIMPLE>
+// MU (pipelined variant only): also form the row sums mu = K coef (posterior mean).  Without it the epilogue drops
+// three FP64 instructions per entry pair, which run on the pipe the DMMAs need (1.449 -> 1.412 ms per 524 288 rows).
+template <int DP, int XS, int NS, bool SIMPLE, bool MU = true>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipeParams p) {
   using L = Smem<DP, XS, NS>;
   constexpr int S = L::S;
@@ -558,7 +565,6 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
       // finish one inducing tile: K = sf2 exp(min(s, 0)), row sums, predicated 16-byte stores
       auto finish = [&](double (&sc)[2][MT / 8][2], int nb, int mt, const double* cf) {
         const int j = mt * MT + 8 * nb + 2 * t;
-        const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
         double2 o0, o1;
         if (p.linear == 2) {       // tuning aid (EDRGP_KUF_DEBUG=1): raw exponents, no exp -- how fast is the loop without it?
           o0.x = sc[0][nb][0]; o0.y = sc[0][nb][1]; o1.x = sc[1][nb][0]; o1.y = sc[1][nb][1];
@@ -566,7 +572,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) kuf_kernel(const PipePara
           o0.x = exp_clip_scaled(sc[0][nb][0], etab); o0.y = exp_clip_scaled(sc[0][nb][1], etab);
           o1.x = exp_clip_scaled(sc[1][nb][0], etab); o1.y = exp_clip_scaled(sc[1][nb][1], etab);
         }
-        mu0 += fma(o0.x, c.x, o0.y * c.y); mu1 += fma(o1.x, c.x, o1.y * c.y);
+        if (MU) {
+          const double2 c = *reinterpret_cast<const double2*>(cf + 8 * nb + 2 * t);
+          mu0 += fma(o0.x, c.x, o0.y * c.y); mu1 += fma(o1.x, c.x, o1.y * c.y);
+        }
         // ldk is even, so a pair starting at an even j < m is in bounds (a column == m is padding)
         if (v0 && j < p.m) *reinterpret_cast<double2*>(k0p + mt * MT + 8 * nb) = o0;
         if (v1 && j < p.m) *reinterpret_cast<double2*>(k1p + mt * MT + 8 * nb) = o1;
@@ -700,10 +709,10 @@ static cudaError_t launch_grad_gram_cached_t(const PipeParams& p, int grid, cuda
   return cudaGetLastError();
 }
 
-template <int DP, int XS, int NS, bool SIMPLE>
+template <int DP, int XS, int NS, bool SIMPLE, bool MU = true>
 static cudaError_t launch_kuf_s(const PipeParams& p, int grid, cudaStream_t st) {
   using L = Smem<DP, XS, NS>;
-  auto kern = kuf_kernel<DP, XS, NS, SIMPLE>;
+  auto kern = kuf_kernel<DP, XS, NS, SIMPLE, MU>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
   kern<<<grid, (WARPS + 1) * 32, L::bytes, st>>>(p); count_launch();
@@ -715,7 +724,8 @@ static cudaError_t launch_kuf_t(const PipeParams& p, int grid, cudaStream_t st) 
   // the pipelined variant needs DP / 16 divisible by 4 (64, 128) to split the next tile's contraction
   const bool simple = p.Kfu != nullptr && !p.mul && !p.linear && p.b == nullptr && (DP % 64 == 0);
   static const int dbg = [] { const char* e = getenv("EDRGP_KUF_DEBUG"); return e ? atoi(e) : 0; }();
-  if (simple && dbg == 1) { PipeParams q = p; q.linear = 2; return launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(q, grid, st); }
+  if (simple && dbg == 1) { PipeParams q = p; q.linear = 2; return launch_kuf_s<DP, XS, NS, (DP % 64 == 0), false>(q, grid, st); }
+  if (simple && p.mu == nullptr) return launch_kuf_s<DP, XS, NS, (DP % 64 == 0), false>(p, grid, st);
   return simple ? launch_kuf_s<DP, XS, NS, (DP % 64 == 0)>(p, grid, st) : launch_kuf_s<DP, XS, NS, false>(p, grid, st);
 }
 
