@@ -373,6 +373,16 @@ def run_ours(args):
         t_steps = max(1, min(args.steps, 5))
         t_ms, comps32 = timed(lambda: sweep(X, y, 'tf32x3'), t_steps)
         t_ops = ops.stop_timing()
+        # ... and with the statistics on the INT8 tensor cores as well (both tcgen05 routes together)
+        both_ms = None
+        if m <= 2048 and not args.no_int8:
+            ops.set_stats_mode('int8x6')
+            try:
+                for _ in range(2):
+                    sweep(X, y, 'tf32x3')
+                both_ms, comps_both = timed(lambda: sweep(X, y, 'tf32x3'), t_steps)
+            finally:
+                ops.set_stats_mode(args.stats)
         k_ms, k_n = t_ops.get('kuf', (0.0, 1))
         rows_chk = min(n_local, 4096)
         pk64 = ops.InducingPack(torch.as_tensor(Z, device=dev), torch.as_tensor(ell, device=dev))
@@ -384,6 +394,9 @@ def run_ours(args):
             "ms_per_step": t_ms / t_steps, "value": n / (t_ms / t_steps * 1e-3), "unit": UNIT, "steps": t_steps,
             "kernel": "kuf_tf32_kernel (tcgen05.mma kind::tf32, 3 products per entry, FP32 accumulators in TMEM)",
             "kuf_ms_per_step": k_ms / t_steps, "kuf_avg_launch_ms": k_ms / max(k_n, 1),
+            "with_int8x6_stats": None if both_ms is None else {
+                "ms_per_step": both_ms / t_steps, "value": n / (both_ms / t_steps * 1e-3), "unit": UNIT,
+                "leading_direction_angle_vs_fp64_rad": float(__import__('edrgp_b200').utils.principal_angle(comps_both[:1], comps[:1]))},
             "roofline": {"bound": "hbm", "unit": "GB/s", "peak": HBM_PEAK_GBS,
                          "achieved": (m + d) * 8.0 * n_local * t_steps / (k_ms * 1e-3) / 1e9 if k_ms else None,
                          "frac": (m + d) * 8.0 * n_local * t_steps / (k_ms * 1e-3) / 1e9 / HBM_PEAK_GBS if k_ms else None,

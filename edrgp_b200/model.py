@@ -450,8 +450,9 @@ class SparseGPRegression(object):
         # the FP64 cross-covariance kernel flags rows holding a NaN / Inf as it forms their norms: the input scan of
         # check_X_y without another pass over X
         self._kuf_flag = torch.zeros(1, dtype=torch.int32, device=dev) if pack32 is None else None
-        # statistics route (ops.set_stats_mode): exact INT8 digit products for FP64 kernel entries in [0, sf2]
-        i8_stats = pack32 is None and m <= 2048 and sf2 < 1e150 and ops.get_stats_mode() == 'int8x6'
+        # statistics route (ops.set_stats_mode): exact INT8 digit products of kernel entries in [0, sf2] (also of the
+        # TF32-split mode's entries: they are clipped at sf2 like the FP64 kernel's)
+        i8_stats = m <= 2048 and sf2 < 1e150 and ops.get_stats_mode() == 'int8x6'
         for i, (s, e) in enumerate(self._chunks()):
             if self._row_loader is not None:
                 self._row_loader(s, e)
