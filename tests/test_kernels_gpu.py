@@ -175,3 +175,51 @@ def test_col_moments_match_numpy(n, d):
     assert np.allclose(s2.cpu().numpy(), ref2, rtol=1e-12)
     t1, t2 = ops.col_moments(Xd, shift=_dev(shift), weight=_dev(w))
     assert torch.equal(s1, t1) and torch.equal(s2, t2)
+
+
+# the plain statistics pass (entries stored, no targets, no row sums): the software-pipelined SIMPLE instantiation of
+# kuf_kernel at d in 49..64 / 113..128, the generic one elsewhere -- the path the composite sweep takes
+PLAIN_SHAPES = [(3000, 64, 512), (1, 50, 64), (255, 64, 64), (257, 64, 128), (5000, 49, 100), (2049, 60, 448),
+                (40000, 64, 512), (300, 64, 96), (513, 32, 128), (1000, 128, 70)]
+
+
+@pytest.mark.parametrize("n,d,m", PLAIN_SHAPES)
+def test_plain_kuf_matches_oracle_with_clip_and_underflow(n, d, m):
+    from edrgp_b200 import ops
+    w = op.make_workload(max(n, m), d, m, seed=n + d + 5)
+    X = w['X'][:n]
+    if n > 100:
+        X[17] = w['Z'][3]                   # a coincident pair: the clip at r^2 = 0 stores exactly sf2
+        X[23] = 1e3 * X[23]                 # a far row: clean underflow to zero
+    pack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']))
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    K, _ = ops.kuf(_dev(X), pack, 1.7, flag=flag)
+    assert int(flag.item()) == 0
+    assert K.shape == (n, m)
+    Kref = op.kuf_faithful(X, w['Z'], w['ell'], 1.7)
+    assert _relerr(K.cpu().numpy(), Kref) < 1e-12
+    if n > 100:
+        assert float(K[17, 3]) == 1.7
+        assert float(K[23].max()) == 0.0
+    # the instantiation with the row sums (posterior mean) stores bit-identical entries
+    alpha = np.random.RandomState(1).standard_normal(m)
+    cpack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']), _dev(alpha), 1.0)
+    K2, _, mu = ops.kuf(_dev(X), cpack, 1.7, want_mu=True)
+    assert torch.equal(K2, K)
+    assert _relerr(mu.cpu().numpy(), Kref.dot(alpha)) < 1e-11
+
+
+def test_plain_kuf_flags_nonfinite_rows_and_leaves_padding_alone():
+    from edrgp_b200 import ops
+    n, d, m = 1000, 64, 126                 # ldk = 126, four tiles: the last pair of columns is cut by j < m
+    w = op.make_workload(n, d, m, seed=3)
+    pack = ops.InducingPack(_dev(w['Z']), _dev(w['ell']))
+    out = torch.full((n + 5, m), -7.0, dtype=torch.float64, device='cuda')
+    K, _ = ops.kuf(_dev(w['X']), pack, 0.9, out=out[:n])
+    assert _relerr(K.cpu().numpy(), op.kuf_faithful(w['X'], w['Z'], w['ell'], 0.9)) < 1e-12
+    assert bool((out[n:] == -7.0).all())    # rows past n are never written
+    X = w['X'].copy()
+    X[777, 5] = np.nan
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ops.kuf(_dev(X), pack, 0.9, flag=flag)
+    assert int(flag.item()) == 1
