@@ -906,7 +906,8 @@ cudaError_t launch_kmm_fix(double* K, int m, int64_t ld, double sf2, double jitt
 //     s = sign(diff) gamma / (h c)            (|t| <= pi / 4, c^2 + s^2 = 1 to rounding)
 // evaluated on operands scaled by a power of two so that the FP32 seeds stay in range.
 // EDRGP_JACOBI_VARIANT (tuning aid, read once): unset = default (the d = 64 specialisation where it applies),
-// 0 = the general kernel everywhere, 1 = fewer lanes per pair, 2 = a warp per pair
+// 0 = the general kernel everywhere, 1 = fewer lanes per pair, 2 = a warp per pair, 3 = the d = 64 solver with the
+// replay as a second kernel
 static int jacobi_variant() {
   static const int v = [] { const char* e = getenv("EDRGP_JACOBI_VARIANT"); return e ? atoi(e) : -1; }();
   return v;
@@ -1144,37 +1145,105 @@ __global__ void __launch_bounds__(1024) jacobi_onesided_kernel(
 // owns exactly four rows and the log is written through a running pointer.  The arithmetic is the general
 // kernel's, operation for operation (0.55 -> 0.51 ms on the bench's spectrum, profiles/r02_jacobi_variants.txt);
 // the default for d = 64, EDRGP_JACOBI_VARIANT=0 selects the general kernel.
-__global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restrict__ C, int max_sweeps,
-                                                         int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
-                                                         int* __restrict__ nlog, const double* __restrict__ V0) {
+//
+// ONE launch holds the solver (CTA 0) and the replay of its rotations on V (CTAs 1 .. 4, a warp per row of V): the
+// replay used to be a second kernel that started when the solver had finished (0.08 ms of a 0.48 ms solve on the
+// rank-replicated tail of the sweep); now it FOLLOWS the solver step by step.  The solver cannot afford a fence per
+// step (a few hundred cycles in a step of ~1 700), so nothing is published: the log is filled with an all-ones
+// pattern before the launch (one memset over log, V and control words), every entry is written with one 16-byte
+// store, and the replay warps poll the entries of their next step past L1 until both words differ from the pattern.
+// When the solver has stored its sweep count (ctrl[0]) and a warp has consumed that many sweeps, it is done; the last
+// replay CTA (ticket) computes eigenvalues, order and signs as before.  Control words, all-ones = initial:
+// [0] sweeps, [1] ticket, [3] time-out (cleared to 0 when a replay warp gave up after ~10 s).
+constexpr int JD_THREADS = 512;
+constexpr int JD_REPLAY_CTAS = 4;                       // 16 rows of V each
+constexpr unsigned long long JD_EMPTY = 0xffffffffffffffffull;
+
+__device__ __forceinline__ int ld_volatile_int(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void jacobi_d64_replay(const double* __restrict__ C, const double2* rotlog, int* ctrl,
+                                                  double* Vt, double* __restrict__ evals, double* __restrict__ comps,
+                                                  double* lam, int* last) {
+  constexpr int D = 64, NP = 32, PER = 63;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = (blockIdx.x - 1) * 16 + warp;
+  unsigned long long flip = 0;                          // bit st: the slot's first column is the larger index at step st
+  for (int st = 0; st < PER; ++st) {
+    int a0 = st + lane, b0 = st + PER - lane;
+    if (a0 >= PER) a0 -= PER;
+    if (b0 >= PER) b0 -= PER;
+    if (lane == 0) a0 = PER;
+    if (a0 > b0) flip |= 1ull << st;
+  }
+  const int a_init = lane == 0 ? PER : lane, b_init = lane == 0 ? 0 : PER - lane;
+  double va = a_init == row ? 1.0 : 0.0, vb = b_init == row ? 1.0 : 0.0;
+  const bool is0 = lane == 0, isl = lane == NP - 1;
+  const double2* lp = rotlog + lane;
+  int st = 0, g = 0, polls = 0;
+  bool timed_out = false;
+  const long long t_start = clock64();
+  for (;;) {
+    double c, sg;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(sg) : "l"(lp) : "memory");
+    const bool ok = (unsigned long long)__double_as_longlong(c) != JD_EMPTY &&
+                    (unsigned long long)__double_as_longlong(sg) != JD_EMPTY;
+    if (!__all_sync(0xffffffffu, ok)) {
+      // not written yet -- or the solver is done: its sweep count says how many steps there are
+      int done = lane == 0 ? ld_volatile_int(ctrl) : 0;
+      done = __shfl_sync(0xffffffffu, done, 0);
+      if (done != -1 && g >= done * PER) break;
+      if ((++polls & 1023) == 0 && clock64() - t_start > 20000000000ll) { timed_out = true; break; }   // ~10 s
+      continue;
+    }
+    lp += NP;
+    ++g;
+    const unsigned fb = (unsigned)((flip >> st) & 1ull) << 31;
+    sg = __hiloint2double(__double2hiint(sg) ^ (int)fb, __double2loint(sg));
+    const double na = c * va - sg * vb, nb = sg * va + c * vb;
+    const double dn = __shfl_down_sync(0xffffffffu, na, 1), up = __shfl_up_sync(0xffffffffu, nb, 1);
+    va = is0 ? na : (isl ? nb : dn);
+    vb = is0 ? dn : up;
+    st = st + 1 == PER ? 0 : st + 1;
+  }
+  // a whole number of sweeps: st == 0, the slots hold their initial columns again
+  Vt[(size_t)a_init * D + row] = va;
+  Vt[(size_t)b_init * D + row] = vb;
+  if (timed_out && lane == 0) ctrl[3] = 0;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *last = atomicAdd(reinterpret_cast<unsigned int*>(ctrl + 1), 1u) == (unsigned)(JD_REPLAY_CTAS - 2);
+  __syncthreads();
+  if (!*last) return;
+  __threadfence();
+  jacobi_finish(C, D, Vt, D, lam, evals, comps, tid, JD_THREADS);
+  if (ld_volatile_int(ctrl + 3) != -1 && tid < D) evals[tid] = __longlong_as_double(0x7ff8000000000000ll);
+}
+
+__global__ void __launch_bounds__(JD_THREADS, 1) jacobi_d64_kernel(const double* __restrict__ C, int max_sweeps,
+                                                                  int* __restrict__ sweeps_out, double2* __restrict__ rotlog,
+                                                                  int* ctrl, double* Vt, double* __restrict__ evals,
+                                                                  double* __restrict__ comps) {
   constexpr int D = 64, DS = 66, NP = 32, PER = 63, L = 16, R = 4;
   extern __shared__ double sh[];
   double* W = sh;                             // [D][DS] column-major
   __shared__ unsigned short sched[PER * NP];  // p | q << 8 of slot k at step s
   __shared__ int rotated;
+  __shared__ int last;
   const int tid = threadIdx.x;
-  const double in_scale = jacobi_input_scale(C, D, tid, 512);
-  if (V0 == nullptr) {
-    for (int i = tid; i < D * D; i += 512) {
-      const int c = i >> 6, r = i & 63;
-      W[c * DS + r] = C[(int64_t)r * D + c] * in_scale;
-    }
-  } else {
-    // warm start from an orthogonal V0 (vector c at V0 + c D: the single-precision pre-solve below): W = C V0.
-    // A thread owns one component r of eight vectors; C is symmetric, so row r is read along the warp.
-    const int r = tid & 63, c0 = (tid >> 6) * 8;
-    double acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-    for (int k = 0; k < D; ++k) {
-      const double crk = C[(int64_t)k * D + r];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fma(crk, V0[(c0 + j) * D + k], acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) W[(c0 + j) * DS + r] = acc[j] * in_scale;
+  if (blockIdx.x > 0) {
+    jacobi_d64_replay(C, rotlog, ctrl, Vt, evals, comps, sh, &last);
+    return;
   }
-  for (int i = tid; i < PER * NP; i += 512) {
+  const double in_scale = jacobi_input_scale(C, D, tid, JD_THREADS);
+  for (int i = tid; i < D * D; i += JD_THREADS) {
+    const int c = i >> 6, r = i & 63;
+    W[c * DS + r] = C[(int64_t)r * D + c] * in_scale;
+  }
+  for (int i = tid; i < PER * NP; i += JD_THREADS) {
     const int step = i >> 5, k = i & 31;
     int a0 = step + k, b0 = step + PER - k;
     if (a0 >= PER) a0 -= PER;
@@ -1231,7 +1300,11 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
           Wq[L * e] = s * wa[e] + c * wb[e];
         }
       }
-      if (l == 0) *rl = make_double2(c, s);
+      if (l == 0) {
+        // (a non-finite input can make the parameters NaN: the log must never hold the replay's "empty" pattern)
+        const bool fin = fabs(c) <= 1.0 && fabs(s) <= 1.0;
+        *rl = make_double2(fin ? c : 1.0, fin ? s : 0.0);
+      }
       rl += NP;
       __syncthreads();
     }
@@ -1240,7 +1313,7 @@ __global__ void __launch_bounds__(512) jacobi_d64_kernel(const double* __restric
   }
   if (tid == 0) {
     if (sweeps_out) *sweeps_out = sweep;
-    nlog[0] = sweep; nlog[1] = 0;
+    asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(ctrl), "r"(sweep) : "memory");
   }
 }
 
@@ -1365,10 +1438,26 @@ static cudaError_t launch_jacobi_small(const double* C, int d, double* ws, doubl
     // FP64 and logged, the FP64 solver warm-started from W = C V1 so that it needs two sweeps instead of eight -- was
     // built and measured in round 2: 0.487 ms against 0.486 ms.  A float step is not shorter: the step is a chain of
     // ~10 dependent stages (load, products, four shuffle levels, parameters, store, barrier), not FP64 issue.)
-    if (jacobi_variant() < 0 && d == 64)
-      jacobi_d64_kernel<<<1, 512, smem, st>>>(C, 60, sweeps, rotlog, ctrl, nullptr);
-    else
-      jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
+    if (jacobi_variant() == 3 && d == 64) {
+      // tuning aid: the same solver, the replay as a second kernel behind it (what the default was before the replay
+      // followed the solver inside one launch)
+      cudaError_t e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
+      if (e != cudaSuccess) return e;
+      jacobi_d64_kernel<<<1, JD_THREADS, smem, st>>>(C, 60, sweeps, rotlog, ctrl, Vt, evals, comps);
+      count_launch();
+      jacobi_vectors_lean_kernel<<<nrep, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps, nullptr, 1);
+      count_launch();
+      return cudaGetLastError();
+    }
+    if (jacobi_variant() < 0 && d == 64) {
+      // solver and replay in one launch; log, V and the control words start as the all-ones "empty" pattern
+      cudaError_t e = cudaMemsetAsync(rotlog, 0xff, (jacobi_log_doubles(d) + (size_t)d * d + 2) * sizeof(double), st);
+      if (e != cudaSuccess) return e;
+      jacobi_d64_kernel<<<1 + JD_REPLAY_CTAS, JD_THREADS, smem, st>>>(C, 60, sweeps, rotlog, ctrl, Vt, evals, comps);
+      count_launch();
+      return cudaGetLastError();
+    }
+    jacobi_onesided_kernel<L, R, true><<<1, threads, smem, st>>>(C, d, evals, comps, 60, sweeps, rotlog, ctrl);
     count_launch();
     jacobi_vectors_lean_kernel<<<nrep, JV_WARPS * 32, 0, st>>>(C, d, rotlog, ctrl, Vt, evals, comps, nullptr, 1);
     count_launch();
