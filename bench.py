@@ -297,8 +297,7 @@ def run_ours(args):
             if not isinstance(yin, torch.Tensor):
                 yin = torch.as_tensor(yin, device=dev)
         est = make_estimator(precision).fit(Xin, yin)
-        _, C = est.estimator_.gradient_gram(want_G=False, check=False)
-        edist.allreduce_sum_(C)
+        _, C = est.estimator_.gradient_gram(want_G=False, check=False, reduce=True)     # summed over the ranks
         tr = eb.GramEighTransformer(n_components=K_TRUE).fit_gram(C, n)
         est.estimator_.finish_checks()
         return tr.components_

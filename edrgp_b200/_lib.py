@@ -74,6 +74,13 @@ SIGNATURES = {
     'edrgp_fixed_grad': (_int, [_c_dp, _i64, _i64, _int, _c_dp, _i64, _c_dp, _i64, _c_dp, _int, _dbl, _dbl, _c_dp, _c_dp,
                                 _i64, _i64, _int, _c_dp, _c_dp]),
     'edrgp_fixed_eigh': (_int, [_i64, _int, _int, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_fixed_reduce_gram': (_int, [_i64, _int, _int, _i64, _int, _c_dp, _c_dp]),
+    'edrgp_peer_layout': (_sz, [_int, _int, _int, ctypes.POINTER(_i64)]),
+    'edrgp_peer_alloc': (_int, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    'edrgp_peer_open': (_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'edrgp_peer_close': (_int, [_c_dp]),
+    'edrgp_peer_free': (_int, [_c_dp]),
+    'edrgp_fixed_bind_peers': (_int, [_c_dp, ctypes.POINTER(ctypes.c_void_p), _int, _int, _int, _int]),
     'edrgp_h2d_open': (ctypes.c_void_p, [_c_dp, _c_dp, _i64, _sz, _sz, _i64, _int, _int, _c_dp, _c_dp, _c_dp, _sz]),
     'edrgp_h2d_wait_side': (_int, [_c_dp, _c_dp]),
     'edrgp_h2d_wait': (_int, [_c_dp, _i64, _i64, _c_dp]),

@@ -11,6 +11,9 @@
 #include "launch.h"
 #include "sweep.h"
 #include "h2d.h"
+#include "peer.h"
+#include <unordered_map>
+#include <iterator>
 
 namespace edrgp {
 static std::atomic<uint64_t> g_launches{0};
@@ -482,6 +485,25 @@ int stats_mode() {
 // the INT8 route covers what its kernel covers; outside that the FP64 reduction runs (same results to 1e-13)
 int stats_mode_for(int m, double sf2) { return (stats_mode() == 1 && m <= 2048 && sf2 < 1e150) ? 1 : 0; }
 
+// NVLink peer exchange (peer.cu): a workspace that has been bound to the ranks' exchange buffers runs its three
+// reductions inside the composite calls; epochs count the uses of each payload (all ranks call in lockstep).
+struct PeerBinding {
+  edrgp::PeerCtx ctx;
+  int m, d;
+  int* epoch;        // [PEER_COLLECTIVES], owned by the BUFFER set (several workspaces may be bound to the same buffers)
+};
+struct PeerEpochs { int v[edrgp::PEER_COLLECTIVES]; };
+std::mutex g_peer_mu;
+std::unordered_map<void*, PeerBinding> g_peer_bindings;
+std::unordered_map<void*, PeerEpochs> g_peer_epochs;       // keyed by the rank's own exchange buffer
+PeerBinding* peer_binding(void* workspace, int m, int d, int world) {
+  std::lock_guard<std::mutex> lk(g_peer_mu);
+  auto it = g_peer_bindings.find(workspace);
+  if (it == g_peer_bindings.end()) return nullptr;
+  PeerBinding* b = &it->second;
+  return (b->m == m && b->d == d && b->ctx.world == world) ? b : nullptr;
+}
+
 struct FixedCtx {
   int64_t off[edrgp::FS_NREGIONS];
   int sms;
@@ -552,6 +574,13 @@ int edrgp_fixed_begin(const double* X, int64_t ldx, int64_t n, int d, const doub
   StageScope t(EDRGP_STAGE_TARGETS, st);
   if ((e = edrgp::launch_target_moments(y, n, scratch, ticket, c.at(edrgp::FS_TABLE) + 4 * rank, c.sms, st)) != cudaSuccess)
     return cuda_fail(e, "fixed_begin");
+  if (PeerBinding* pb = peer_binding(workspace, m, d, world)) {
+    // peer exchange: this rank's row goes into every rank's table, then its flag (no collective call follows)
+    if (pb->ctx.rank != rank) return fail(EDRGP_ERR_ARG, "fixed_begin: the workspace is bound as another rank");
+    const int ep = ++pb->epoch[edrgp::PEER_COLL_TABLE];
+    if ((e = edrgp::launch_peer_push_table(pb->ctx, c.at(edrgp::FS_TABLE) + 4 * rank, ep, st)) != cudaSuccess)
+      return cuda_fail(e, "fixed_begin");
+  }
   return EDRGP_OK;
 }
 
@@ -565,6 +594,12 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   double* yt = c.at(edrgp::FS_YT);
+  PeerBinding* pb = peer_binding(workspace, m, d, world);
+  if (pb) {
+    StageScope t(EDRGP_STAGE_TARGETS, st);
+    if ((e = edrgp::launch_peer_table_wait(pb->ctx, pb->epoch[edrgp::PEER_COLL_TABLE], c.at(edrgp::FS_TABLE), c.flag(), st)) !=
+        cudaSuccess) return cuda_fail(e, "fixed_stats");
+  }
   {
     StageScope t(EDRGP_STAGE_TARGETS, st);
     e = edrgp::launch_target_standardize(c.at(edrgp::FS_TABLE), world, y, n, yt, c.at(edrgp::FS_TAIL) + 1, normalize, c.flag(),
@@ -572,7 +607,10 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
   }
   if (e != cudaSuccess) return cuda_fail(e, "fixed_stats");
   const double* targets = normalize ? yt : y;
-  double* P = c.at(edrgp::FS_STATS);
+  // peer exchange: the rank's partial statistics are written straight into its exchange buffer (the peers read them
+  // from there while they assemble their systems); the workspace region receives the SUM in edrgp_fixed_posterior
+  const int ep_stats = pb ? ++pb->epoch[edrgp::PEER_COLL_STATS] : 0;
+  double* P = pb ? edrgp::peer_partial(pb->ctx, edrgp::PEER_STATS, ep_stats, (size_t)m * m + m + 1) : c.at(edrgp::FS_STATS);
   double* byy = P + (size_t)m * m;
   const int i8 = stats_mode_for(m, sf2);
   void* i8ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(c.at(edrgp::FS_SCRATCH)) + 1023) & ~(uintptr_t)1023);
@@ -598,6 +636,8 @@ int edrgp_fixed_stats(const double* X, int64_t ldx, int64_t n, int d, const doub
       return cuda_fail(e, "fixed_stats");
     }
   }
+  if (pb && (e = edrgp::launch_peer_signal(pb->ctx, edrgp::PEER_COLL_STATS, ep_stats, st)) != cudaSuccess)
+    return cuda_fail(e, "fixed_stats");
   return EDRGP_OK;
 }
 
@@ -615,7 +655,12 @@ int edrgp_fixed_posterior(const double* Z, int64_t ldz, int64_t n, int d, int m,
   const double* P = c.at(edrgp::FS_STATS);
   if ((e = edrgp::launch_kuf(Z, ldz, m, d, c.at(edrgp::FS_PACK_K), m, sf2, S, lds, 0, nullptr, nullptr, nullptr, c.sms, st)) !=
       cudaSuccess) return cuda_fail(e, "fixed_posterior");
-  if ((e = edrgp::launch_form_system(S, m, lds, sf2, jitter, beta, P, m, P + (size_t)m * m, c.at(edrgp::FS_RHS), st)) !=
+  if (PeerBinding* pb = peer_binding(workspace, m, d, world)) {
+    // the reduction over ranks happens while the system is assembled: partials read from the peers over NVLink
+    if ((e = edrgp::launch_form_system_peer(pb->ctx, pb->epoch[edrgp::PEER_COLL_STATS], S, m, lds, sf2, jitter, beta,
+                                            c.at(edrgp::FS_STATS), c.at(edrgp::FS_RHS), c.flag(), st)) != cudaSuccess)
+      return cuda_fail(e, "fixed_posterior");
+  } else if ((e = edrgp::launch_form_system(S, m, lds, sf2, jitter, beta, P, m, P + (size_t)m * m, c.at(edrgp::FS_RHS), st)) !=
       cudaSuccess) return cuda_fail(e, "fixed_posterior");
   if ((e = edrgp::launch_posv(S, m, lds, c.at(edrgp::FS_L), m, c.at(edrgp::FS_RHS), c.at(edrgp::FS_ALPHA), c.info(), st)) !=
       cudaSuccess) return cuda_fail(e, "fixed_posterior");
@@ -642,6 +687,100 @@ int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const doubl
                                           c.at(edrgp::FS_SCRATCH), c.sms, st)) != cudaSuccess) return cuda_fail(e, "fixed_grad");
   if ((e = cudaMemcpyAsync(C + (size_t)d * d, c.at(edrgp::FS_TAIL), 4 * sizeof(double), cudaMemcpyDeviceToDevice, st)) !=
       cudaSuccess) return cuda_fail(e, "fixed_grad");
+  return EDRGP_OK;
+}
+
+int edrgp_fixed_reduce_gram(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream) {
+  FixedCtx c;
+  int rc = fixed_ctx("fixed_reduce_gram", n, d, m, chunk_rows, world, workspace, &c);
+  if (rc) return rc;
+  PeerBinding* pb = peer_binding(workspace, m, d, world);
+  if (!pb) return fail(EDRGP_ERR_UNSUPPORTED, "fixed_reduce_gram: the workspace is not bound to peer exchange buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* res = c.at(edrgp::FS_RESULT);
+  double* C = res + d + (size_t)d * d;
+  const int ep = ++pb->epoch[edrgp::PEER_COLL_GRAM];
+  double* part = edrgp::peer_partial(pb->ctx, edrgp::PEER_GRAM, ep, (size_t)d * d);
+  StageScope t(EDRGP_STAGE_GRAD, st);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(part, C, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+    return cuda_fail(e, "fixed_reduce_gram");
+  if ((e = edrgp::launch_peer_signal(pb->ctx, edrgp::PEER_COLL_GRAM, ep, st)) != cudaSuccess) return cuda_fail(e, "fixed_reduce_gram");
+  if ((e = edrgp::launch_reduce_gram_peer(pb->ctx, ep, d * d, C, c.flag(), st)) != cudaSuccess)
+    return cuda_fail(e, "fixed_reduce_gram");
+  // (the tail copy behind C was made by edrgp_fixed_grad; a time-out raised here reaches the host through the flag word)
+  if ((e = cudaMemcpyAsync(C + (size_t)d * d, c.at(edrgp::FS_TAIL), 4 * sizeof(double), cudaMemcpyDeviceToDevice, st)) !=
+      cudaSuccess) return cuda_fail(e, "fixed_reduce_gram");
+  return EDRGP_OK;
+}
+
+size_t edrgp_peer_layout(int m, int d, int world, int64_t* offsets) {
+  if (m <= 0 || d <= 0 || world <= 0 || world > edrgp::PEER_MAX_WORLD || !offsets) return 0;
+  return edrgp::peer_layout(m, d, world, offsets) * sizeof(double);
+}
+
+int edrgp_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle) {
+  if (!bytes || !dev_ptr || !ipc_handle) return fail(EDRGP_ERR_ARG, "peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == EDRGP_PEER_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_alloc");
+  if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) { cudaFree(p); return cuda_fail(e, "peer_alloc"); }
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) { cudaFree(p); return cuda_fail(e, "peer_alloc"); }
+  memcpy(ipc_handle, &h, sizeof(h));
+  *dev_ptr = p;
+  {
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    g_peer_epochs.erase(p);           // a fresh buffer (flags zeroed) starts at epoch 0 even if the address is an old one
+  }
+  return EDRGP_OK;
+}
+
+int edrgp_peer_open(const void* ipc_handle, void** dev_ptr) {
+  if (!ipc_handle || !dev_ptr) return fail(EDRGP_ERR_ARG, "peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "peer_open");
+  *dev_ptr = p;
+  return EDRGP_OK;
+}
+
+int edrgp_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return EDRGP_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "peer_close");
+}
+
+int edrgp_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return EDRGP_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    for (auto it = g_peer_bindings.begin(); it != g_peer_bindings.end();)
+      it = it->second.ctx.base[it->second.ctx.rank] == dev_ptr ? g_peer_bindings.erase(it) : std::next(it);
+    g_peer_epochs.erase(dev_ptr);
+  }
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? EDRGP_OK : cuda_fail(e, "peer_free");
+}
+
+int edrgp_fixed_bind_peers(void* workspace, void* const* bases, int rank, int world, int m, int d) {
+  if (!workspace) return fail(EDRGP_ERR_ARG, "fixed_bind_peers: bad argument");
+  std::lock_guard<std::mutex> lk(g_peer_mu);
+  if (!bases) { g_peer_bindings.erase(workspace); return EDRGP_OK; }
+  if (world < 1 || world > edrgp::PEER_MAX_WORLD || rank < 0 || rank >= world || m <= 0 || d <= 0)
+    return fail(EDRGP_ERR_ARG, "fixed_bind_peers: 1 <= world <= %d, 0 <= rank < world", edrgp::PEER_MAX_WORLD);
+  PeerBinding b{};
+  for (int r = 0; r < world; ++r) {
+    if (!bases[r]) return fail(EDRGP_ERR_ARG, "fixed_bind_peers: null exchange buffer of rank %d", r);
+    b.ctx.base[r] = (double*)bases[r];
+  }
+  edrgp::peer_layout(m, d, world, b.ctx.off);
+  b.ctx.rank = rank; b.ctx.world = world; b.m = m; b.d = d;
+  b.epoch = g_peer_epochs[bases[rank]].v;                 // (value-initialised to 0 on first use; node addresses are stable)
+  g_peer_bindings[workspace] = b;
   return EDRGP_OK;
 }
 

@@ -2,9 +2,10 @@
 small reductions of the path.  SURVEY.md section 8(e).
 
 The data rows are partitioned across ranks; Z, the hyper-parameters and alpha are replicated.
-Per fixed-hyper-parameter sweep exactly two all-reduces run on the data path:
-{P (m x m), b (m), y^T y, n} after the statistics pass and {C (d x d)} after the gradient pass
-(plus 2d / 2 doubles for the scaler / target normaliser).  Everything else is rank-local.
+Per fixed-hyper-parameter sweep three small reductions run on the data path: the targets' moments table,
+{P (m x m), b (m), y^T y} after the statistics pass and {C (d x d)} after the gradient pass.  On an NVLink box
+they run INSIDE the library's kernels over peer memory (``peer_exchange``, csrc/peer.cu); otherwise, and for
+everything off the composite sweep (scaler, optimisation path), as ``torch.distributed`` all-reduces.
 """
 import contextlib
 import os
@@ -66,6 +67,83 @@ def broadcast_(tensor, src=0):
     if is_distributed():
         torch.distributed.broadcast(tensor, src=src)
     return tensor
+
+
+# --- NVLink peer exchange (csrc/peer.cu): the sweep's three small reductions without a library collective -----------
+_PEER = {}            # (m, d, world) -> PeerExchange, or False when the ranks could not map each other's buffers
+
+
+class PeerExchange(object):
+    """This rank's exchange buffer (cudaMalloc + IPC handle) and the peers' buffers mapped into this process.
+    Built COLLECTIVELY (every rank calls ``peer_exchange`` with the same shape at the same point of the program);
+    ``bases`` is what ``edrgp_fixed_bind_peers`` takes."""
+
+    def __init__(self, m, d):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        self.m, self.d, self.world, self.rank = int(m), int(d), world_size(), rank()
+        self._lib, self._own, self._opened = lib, None, []
+        off = (ctypes.c_int64 * 4)()
+        nbytes = lib.edrgp_peer_layout(self.m, self.d, self.world, off)
+        ok = nbytes > 0
+        handle = ctypes.create_string_buffer(64)
+        own = ctypes.c_void_p()
+        if ok:
+            ok = lib.edrgp_peer_alloc(nbytes, ctypes.byref(own), handle) == 0
+        if ok:
+            self._own = own.value
+        handles = [None] * self.world
+        torch.distributed.all_gather_object(handles, handle.raw if ok else None)
+        ptrs = [None] * self.world
+        ok = ok and all(h is not None for h in handles)
+        if ok:
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs[r] = self._own
+                    continue
+                p = ctypes.c_void_p()
+                if lib.edrgp_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)) != 0:
+                    ok = False
+                    break
+                ptrs[r] = p.value
+                self._opened.append(p.value)
+        # every rank or none: a rank that could not map a peer takes everybody back to the library collectives
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        self.ok = bool(flag.item() > 0.5)
+        self.bases = (ctypes.c_void_p * self.world)(*ptrs) if self.ok else None
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        for p in self._opened:
+            self._lib.edrgp_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self._lib.edrgp_peer_free(self._own)
+            self._own = None
+
+
+def peer_exchange(m, d):
+    """The exchange buffers of this job for an (m, d) sweep, or None: single process, a CPU / gloo job, more than 16
+    ranks, ``EDRGP_COLLECTIVES=nccl`` in the environment, or a rank that could not map a peer's buffer (no NVLink /
+    PCIe peer access).  COLLECTIVE on first use per shape; every rank gets the same answer."""
+    if not is_distributed() or world_size() > 16 or os.environ.get('EDRGP_COLLECTIVES', 'peer') == 'nccl':
+        return None
+    if torch.distributed.get_backend() != 'nccl' or not torch.cuda.is_available():
+        return None
+    key = (int(m), int(d), world_size())
+    ex = _PEER.get(key)
+    if ex is None:
+        ex = PeerExchange(m, d)
+        if not ex.ok:
+            import warnings
+            warnings.warn("edrgp_b200: the ranks could not map each other's exchange buffers; the sweep's reductions "
+                          "run as torch.distributed all-reduces", RuntimeWarning)
+            ex = False
+        _PEER[key] = ex
+    return ex or None
 
 
 def shard_bounds(n, r=None, w=None):

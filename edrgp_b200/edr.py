@@ -241,9 +241,7 @@ class EffectiveDimensionalityReduction(BaseEstimator, TransformerMixin):
     def _gradient_gram(self, want_G):
         """(G on device or None, C reduced over ranks) of the current estimator on its training rows,
         mapped back through the preprocessor on the first iteration (edrgp/edr.py:233-238)."""
-        G, C = self.estimator_.estimator_.gradient_gram(want_G=want_G, want_C=True)
-        C = C.clone()
-        dist.allreduce_sum_(C)
+        G, C = self.estimator_.estimator_.gradient_gram(want_G=want_G, want_C=True, reduce=True)
         C = C.cpu().numpy()
         if self.preprocessor is not None and self.num_iter == 0:
             P = self._preprocessing_

@@ -384,11 +384,18 @@ class SparseGPRegression(object):
             fs = self._fixed = ops.FixedSweep.acquire(self.n_local, self.d_even, m, chunk, dist.rank(),
                                                       dist.world_size(), self.device)
             weakref.finalize(self, ops.FixedSweep.release, fs)
+            if dist.is_distributed():
+                # NVLink peer exchange: the three reductions of the sweep run inside the composite calls (collective
+                # set-up on first use per shape; None -> torch.distributed all-reduces between the calls)
+                ex = dist.peer_exchange(m, self.d_even)
+                if ex is not fs.peer:
+                    fs.bind_peers(ex)
         self._y_loader = None                      # (the calls wait for the targets themselves)
         normalize = self._Y_normalized is None and self.normalizer is not None
         y_in = self._Y_raw if self._Y_normalized is None else self._Y_normalized
         fs.begin(self.X, y_in, self._Z_dev, self._ell_dev, sf2, self._Kcache, h2d, ahead)
-        dist.allreduce_sum_(fs.table)
+        if fs.peer is None:
+            dist.allreduce_sum_(fs.table)
         fs.stats_pass(self.X, y_in, sf2, self._Kcache, normalize, h2d, ahead)
         if self._Y_normalized is None:
             if normalize:
@@ -400,8 +407,9 @@ class SparseGPRegression(object):
             else:
                 self._Y_normalized = self._Y_raw
             self._cnt_dev = fs.tail[1:2]
-        dist.allreduce_sum_(fs.stats)
-        self._stats = (fs.P, fs.byy)
+        if fs.peer is None:
+            dist.allreduce_sum_(fs.stats)
+        self._stats = (fs.P, fs.byy)                # (peer exchange: summed over the ranks by fs.posterior below)
         fs.posterior(self._Z_dev, sf2, CONST_JITTER, beta)
         self.alpha = fs.alpha
         self._fixed_live = True
@@ -578,6 +586,9 @@ class SparseGPRegression(object):
             fs = flat
             tail = fs.host[-4:] if fs.host is not None else fs.tail.cpu().numpy()
             flag, info, count, mean, std = ops.FixedSweep.decode_tail(tail)
+            if flag & 0x100:
+                raise RuntimeError("edrgp_b200: a rank did not reach the peer exchange of the sweep within its time-out "
+                                   "(ranks out of step, or a rank died); results of this sweep are invalid")
             self._num_data = int(round(count))
             norm = self.normalizer
             if self._fixed_norm and isinstance(norm, Standardize) and norm._mean is None:
@@ -837,20 +848,27 @@ class SparseGPRegression(object):
         coef, cs = self._grad_coef(scale, float(self.kern.variance))
         return ops.InducingPack(self._Z_dev, self._ell_dev, coef, cs)
 
-    def gradient_gram(self, X=None, want_G=False, want_C=True, scale_by_normalizer=True, G_out=None, check=True):
+    def gradient_gram(self, X=None, want_G=False, want_C=True, scale_by_normalizer=True, G_out=None, check=True,
+                      reduce=False):
         """Posterior-mean gradients of this rank's rows and their Gram matrix, on the device.
 
-        Returns ``(G or None, C or None)``; C is NOT reduced across ranks (callers all-reduce it
-        together with whatever else they need).  ``X=None`` uses the training rows.  ``check=False``
-        leaves the deferred input / positive-definiteness checks pending (no host synchronisation
-        here): the caller runs ``finish_checks()`` before it trusts what it read back.
+        Returns ``(G or None, C or None)``.  ``reduce=False``: C covers this rank's rows only (callers all-reduce it
+        together with whatever else they need).  ``reduce=True``: C is summed over the ranks -- inside the composite
+        sweep over NVLink peer memory when the job has exchange buffers (``dist.peer_exchange``), by a
+        ``torch.distributed`` all-reduce otherwise; every rank must make the call.  ``X=None`` uses the training
+        rows.  ``check=False`` leaves the deferred input / positive-definiteness checks pending (no host
+        synchronisation here): the caller runs ``finish_checks()`` before it trusts what it read back.
         """
         Xd = self.X if X is None else ops.pad_even(_as_device(X, self.device))
         scale = self._grad_scale(scale_by_normalizer)
         d = self.input_dim
+        reduced = not (reduce and want_C and dist.is_distributed())
         if Xd.shape[0] == 0:
             G = torch.empty(0, d, dtype=F64, device=self.device) if want_G else None
-            return G, (torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None)
+            C = torch.zeros(d, d, dtype=F64, device=self.device) if want_C else None
+            if not reduced:
+                dist.allreduce_sum_(C)
+            return G, C
         use_cache = X is None and getattr(self, '_Kcache', None) is not None
         sf2 = float(self.kern.variance)
         if use_cache and self._fixed_live and self.d_even <= 64 and self.precision == 'fp64':
@@ -865,6 +883,10 @@ class SparseGPRegression(object):
                 C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, 1.0, scale, G)
             else:
                 C = fs.grad(Xd, self._Kcache, self._Z_dev, self._ell_dev, sf2, float(scale), None, G)
+            if not reduced and fs.peer is not None:
+                C = fs.reduce_gram()               # summed over the ranks from the peers' buffers, no collective call
+                reduced = True
+                self.kernel_launches += 2
             # the caller gets its own copy (it may sum it over ranks in place, keep it, call again); the tag lets
             # GramEighTransformer.fit_gram run the eigensolver inside the block and read everything back at once
             C = C.clone()
@@ -921,6 +943,11 @@ class SparseGPRegression(object):
                 G = G[:, :d].contiguous()
             if C is not None:
                 C = C[:d, :d].contiguous()
+        if not reduced:
+            fixed = getattr(C, '_edrgp_fixed', None)
+            dist.allreduce_sum_(C)
+            if fixed is not None:
+                C._edrgp_fixed = fixed
         if check:
             self._check_pd()
         return (G if want_G else None), C

@@ -674,6 +674,30 @@ class FixedSweep(object):
         self.C = self.result[d + d * d:d + 2 * d * d].view(d, d)
         self.host = None                     # the result block once it has been read back (one transfer)
         self.key = None
+        self.peer = None                     # dist.PeerExchange once bound (bind_peers): no collectives between the calls
+
+    def bind_peers(self, exchange):
+        """Bind this workspace to the job's NVLink exchange buffers (``dist.peer_exchange``): begin / stats_pass /
+        posterior then reduce the moments table and the statistics over the ranks themselves and ``reduce_gram``
+        replaces the all-reduce of C.  ``None`` unbinds."""
+        lib = _lib.load()
+        if exchange is None:
+            _lib.check(lib.edrgp_fixed_bind_peers(_ptr(self.ws), None, 0, 0, 0, 0), 'edrgp_fixed_bind_peers')
+        else:
+            _lib.check(lib.edrgp_fixed_bind_peers(_ptr(self.ws), exchange.bases, self.rank, self.world, self.m, self.d),
+                       'edrgp_fixed_bind_peers')
+            if getattr(self, '_unbind', None) is None:
+                # the binding is keyed by the workspace address: it must not outlive the tensor that owns it
+                import weakref
+                self._unbind = weakref.finalize(self, lib.edrgp_fixed_bind_peers, _ptr(self.ws), None, 0, 0, 0, 0)
+        self.peer = exchange
+
+    def reduce_gram(self):
+        """C (result block) <- its sum over the ranks, read from the peers' buffers (bound workspaces only)."""
+        lib = _lib.load()
+        _lib.check(lib.edrgp_fixed_reduce_gram(self.n, self.d, self.m, *self._common()), 'edrgp_fixed_reduce_gram')
+        self.host = None
+        return self.C
 
     def _common(self):
         return self.chunk, self.world, _ptr(self.ws), _stream()

@@ -361,6 +361,36 @@ int edrgp_fixed_grad(const double* X, int64_t ldx, int64_t n, int d, const doubl
                      double* G, int64_t ldg, int64_t chunk_rows, int world, void* workspace, void* stream);
 int edrgp_fixed_eigh(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * NVLink peer exchange for the sweep's three reductions (csrc/peer.cu).  No counterpart in the reference, which is a
+ * single process (edrgp/base.py:435-466 runs one estimator over all rows): this is the n-sharding of the path, and it
+ * replaces the three all-reduce calls a multi-rank caller otherwise issues between the composite calls above.
+ *
+ * Every rank allocates one exchange buffer (edrgp_peer_alloc: cudaMalloc + a 64-byte cudaIpcMemHandle the caller ships
+ * to the other ranks by whatever channel it has), maps the others' (edrgp_peer_open) and binds the set to a sweep
+ * workspace (edrgp_fixed_bind_peers: bases[r] = rank r's buffer as mapped HERE, bases[rank] = its own; bases = NULL
+ * unbinds).  With a bound workspace
+ *   edrgp_fixed_begin      also pushes this rank's moments row into every rank's table and raises its flag,
+ *   edrgp_fixed_stats      waits for all rows first, writes the rank's partial {P, b, y^T y} into its exchange buffer and
+ *                          raises its flag when the last block is done,
+ *   edrgp_fixed_posterior  sums the partials of all ranks, in rank order, WHILE it assembles S = Kuu + beta P and beta b
+ *                          (reads over NVLink; the sums are also left in the EDRGP_FS_STATS region),
+ *   edrgp_fixed_reduce_gram (bound workspaces only) replaces C in the result block by its sum over the ranks,
+ * and the caller issues NO collective of its own.  All ranks must make the same sequence of calls.  Every wait is
+ * bounded (~10 s): a rank that never arrives sets bit 8 (0x100) of the flag word in EDRGP_FS_TAIL instead of hanging.
+ * edrgp_peer_layout returns the buffer size in bytes for (m, d, world <= 16); offsets[4] (doubles): flags, table,
+ * statistics, Gram matrix -- two copies of each payload, used alternately.
+ * ------------------------------------------------------------------------------------------- */
+#define EDRGP_PEER_HANDLE_BYTES 64
+size_t edrgp_peer_layout(int m, int d, int world, int64_t* offsets);
+int edrgp_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle);
+int edrgp_peer_open(const void* ipc_handle, void** dev_ptr);
+int edrgp_peer_close(void* dev_ptr);
+int edrgp_peer_free(void* dev_ptr);
+int edrgp_fixed_bind_peers(void* workspace, void* const* bases, int rank, int world, int m, int d);
+int edrgp_fixed_reduce_gram(int64_t n, int d, int m, int64_t chunk_rows, int world, void* workspace, void* stream);
+
+
 /* ---------------------------------------------------------------------------------------------
  * Host rows -> device in blocks, overlapped with the kernels that consume them.  Replaces the implicit
  * "the arrays are already where the arithmetic runs" of the reference's fit(X, y) (edrgp/gp_model/base.py:46-91:

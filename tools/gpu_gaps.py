@@ -30,8 +30,7 @@ ell = np.sqrt(d) * (1 + 0.5 * np.random.RandomState(1).uniform(size=d))
 def sweep():
     est = eb.SparseGaussianProcessRegressor(kernels=emodel.RBF(d, 1.0, ell, ARD=True), Z=Z, normalizer=True,
                                             method='fixed', noise_var=0.1, chunk_rows=524288, deferred_checks=True).fit(X, y)
-    _, C = est.estimator_.gradient_gram(want_G=False, check=False)
-    edist.allreduce_sum_(C)
+    _, C = est.estimator_.gradient_gram(want_G=False, check=False, reduce=True)
     tr = eb.GramEighTransformer(n_components=3).fit_gram(C, n * world)
     est.estimator_.finish_checks()
     return tr.components_
