@@ -530,6 +530,13 @@ def run_ours(args):
     except (OSError, ValueError, KeyError):
         pass
 
+    if world == 1:
+        collectives = "single rank: none"
+    elif d <= 64 and edist.peer_exchange(m, d + (d & 1)) is not None:
+        collectives = ("NVLink peer exchange inside the library's kernels: moments table pushed, {P, b, yy} summed while the "
+                       "system is assembled, C summed in front of eigh; no library collective on the sweep")
+    else:
+        collectives = "torch.distributed all-reduce over NCCL"
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -539,7 +546,7 @@ def run_ours(args):
                    "hyperparameters": "fixed (lengthscales sqrt(d)(1+u/2), variance 1, noise 0.1)",
                    "l2": "inputs (%.2f GB X per rank + %.1f GB Kfu blocks) exceed the 126 MB L2; no flush needed"
                          % (n_local * d * 8 / 1e9, n_local * m * 8 / 1e9),
-                   "chunk_rows": args.chunk_rows, "precision": args.precision, "stats": args.stats, "parallelism": "n-sharded x%d, 2 all-reduces/step" % world},
+                   "chunk_rows": args.chunk_rows, "precision": args.precision, "stats": args.stats, "parallelism": "n-sharded x%d, 3 small reductions/step (%s)" % (world, collectives)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                 "api": "SparseGaussianProcessRegressor(method='fixed').fit(X_host, y_host) -> gradient_gram -> "
