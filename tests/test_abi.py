@@ -131,3 +131,27 @@ def test_stats_mode_switch_and_layout():
         assert lib.edrgp_set_stats_mode(7) != 0
     finally:
         ops.set_stats_mode(before)
+
+
+def test_peer_exchange_layout_and_argument_checks():
+    """The NVLink exchange's host-side entry points without a GPU: the buffer layout (two copies of every payload behind
+    the flag words), rejected arguments, and that a single process never builds an exchange."""
+    import ctypes
+    from edrgp_b200 import _lib, dist
+    lib = _lib.load()
+    off = (ctypes.c_int64 * 4)()
+    m, d, world = 512, 64, 8
+    nbytes = lib.edrgp_peer_layout(m, d, world, off)
+    flags, table, stats, gram = [int(o) for o in off]
+    assert flags == 0 and table == 4 * 16 // 2                       # 4 rows of 16 int32 flag words
+    assert stats - table == 2 * (4 * world)
+    per_copy = m * m + m + 1
+    assert gram - stats == 2 * (per_copy + (per_copy & 1))
+    assert nbytes == 8 * (gram + 2 * d * d)
+    assert lib.edrgp_peer_layout(m, d, 17, off) == 0                  # at most 16 ranks
+    assert lib.edrgp_peer_layout(0, d, 2, off) == 0
+    assert lib.edrgp_peer_alloc(0, None, None) != 0
+    assert lib.edrgp_peer_open(None, None) != 0
+    assert lib.edrgp_fixed_bind_peers(None, None, 0, 2, m, d) != 0
+    assert lib.edrgp_peer_close(None) == 0 and lib.edrgp_peer_free(None) == 0
+    assert dist.peer_exchange(m, d) is None                          # not a distributed job

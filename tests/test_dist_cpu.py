@@ -48,6 +48,8 @@ def _worker(rank, world, port, out):
         flag = torch.tensor([float(rank == 1)], dtype=torch.float64)
         dist.allreduce_max_(flag)
         assert float(flag[0]) == 1.0
+        # the NVLink peer exchange is a CUDA / NCCL route: a gloo job gets None on every rank and keeps the all-reduces
+        assert dist.peer_exchange(512, 64) is None
         # the targets' moments table of the composite sweep (csrc/sweep.cu): every rank fills its own row
         # [n_r, pivot_r, sum (y - pivot_r), sum (y - pivot_r)^2]; one summed table gives the GLOBAL mean and std
         rng = np.random.RandomState(7)
