@@ -20,6 +20,26 @@ from . import model as _model
 _KERNELS = {'RBF': _model.RBF, 'rbf': _model.RBF}
 
 
+def _from_gpy_kernel(kern, n_features):
+    """A ready ``GPy.kern`` object (edrgp/gp_model/base.py:124-126 hands it to the model as it is): an RBF
+    over all the input columns is read into the B200 path's own hyper-parameter holder, everything else
+    (sums, products, other covariance functions, ``active_dims`` subsets) is outside the path and says so.
+    Duck-typed: GPy itself is never imported."""
+    if getattr(kern, 'parts', None):
+        raise NotImplementedError("sums / products of kernels are outside the B200 path (RBF only)")
+    if getattr(kern, 'name', type(kern).__name__).lower() != 'rbf' and type(kern).__name__ != 'RBF':
+        raise NotImplementedError("kernel %r is outside the B200 path (RBF only)" % (type(kern).__name__,))
+    input_dim = int(kern.input_dim)
+    if input_dim != int(n_features):
+        raise ValueError("kernel has input_dim {}; X has {} features per sample".format(input_dim, n_features))
+    dims = getattr(kern, 'active_dims', None)
+    if dims is not None and not np.array_equal(np.asarray(dims).ravel(), np.arange(input_dim)):
+        raise NotImplementedError("active_dims subsets are outside the B200 path")
+    variance = float(np.asarray(kern.variance, dtype=np.float64).ravel()[0])
+    lengthscale = np.asarray(kern.lengthscale, dtype=np.float64).ravel()
+    return _model.RBF(input_dim, variance, lengthscale, ARD=bool(getattr(kern, 'ARD', lengthscale.size > 1)))
+
+
 def _host_copy_threads():
     """Host threads that stage pageable rows into pinned blocks: the CPUs this process may use, shared fairly
     between the ranks of this node, one left for the thread that drives the GPU; at most 8 (memcpy saturates the
@@ -82,6 +102,8 @@ class _BaseGP(BaseEstimator):
             return None
         if isinstance(self.kernels, _model.RBF):
             return self.kernels.copy()
+        if (getattr(self.kernels, '__module__', None) or '').startswith('GPy.kern'):
+            return _from_gpy_kernel(self.kernels, self.n_features_)
         kernels = [self.kernels] if isinstance(self.kernels, str) else list(self.kernels)
         options = self.kernel_options
         if isinstance(options, dict):
