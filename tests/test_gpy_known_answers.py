@@ -19,7 +19,8 @@ and, ``-m gpu``, for the CUDA estimator under the reference orchestrator.  Three
 prints; the 1e-8 statements of the other tests are oracle-vs-CUDA, this file is oracle-vs-GPy.
 
 Not reproduced, and not asserted: cell [30] (iterative fit, printed 0.056, replayed 0.049: eight chained L-BFGS-B
-runs whose end points depend on the optimiser build -- SciPy's L-BFGS-B was rewritten since) and cell [37]
+runs whose end points depend on the optimiser build -- SciPy's L-BFGS-B was rewritten since; a start moved by 1e-6 or
+another L-BFGS memory scatters the replayed value over 0.046 ... 0.054 while cell [29] stays at 0.13498) and cell [37]
 (``SparsePCA`` refit: scikit-learn changed the algorithm's normalisation; printed -0.648 / -0.444 / -0.619, replayed
 0.653 / 0.432 / 0.622).  ``scipy.sparse.random(..., random_state=11)`` of cell [32] draws differently today, so
 B_sparse is taken from cell [33]'s print (8 decimals).
