@@ -4,6 +4,9 @@ the replayed values beside the notebook's prints -- including the two cells that
 ``tests/test_gpy_known_answers.py`` asserts the reproduced ones.  Run here (needs /root/reference or oracle/_ref):
 
     python tests/golden/replay_notebook.py > profiles/r02_s4_gpy_known_answers.txt
+
+(the sensitivity table and the GPU note at the end of that file were appended by hand: the same replay with
+``fmin_l_bfgs_b``'s options changed, and the log of the ``-m gpu`` tests).
 """
 import os
 import sys

@@ -81,3 +81,16 @@ def test_gpy_objects_outside_the_path_say_so():
         _shell(3, _gpy_like('rbf', 'RBF', active_dims=np.array([0, 2]), **rbf))._make_kernel()
     with pytest.raises(ValueError):
         _shell(4, _gpy_like('rbf', 'RBF', **rbf))._make_kernel()
+
+
+@pytest.mark.gpu
+def test_gpy_rbf_object_fits_like_the_own_kernel():
+    """End to end on the device: the duck-typed GPy object and the package's own holder give the same model."""
+    from oracle import pipeline as op
+    w = op.make_workload(400, 6, 16, seed=2, k_true=1)
+    gk = _gpy_like('rbf', 'RBF', input_dim=6, ARD=True, variance=_Param(w['sf2']), lengthscale=_Param(w['ell']))
+    fits = []
+    for kern in (gk, emodel.RBF(6, w['sf2'], w['ell'], ARD=True)):
+        est = SparseGaussianProcessRegressor(kernels=kern, Z=w['Z'], method='fixed', noise_var=w['noise'])
+        fits.append(est.fit(w['X'], w['y']).predict_gradient(w['X'][:64]))
+    assert np.array_equal(fits[0], fits[1])
