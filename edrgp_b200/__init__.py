@@ -10,4 +10,8 @@ __version__ = '0.1.0'
 from .gp_model import SparseGaussianProcessRegressor          # noqa: F401
 from .transformer import GramEighTransformer, DevicePCA       # noqa: F401
 from .edr import EffectiveDimensionalityReduction, EDR, BlockEDR   # noqa: F401
-from .utils import discrepancy, subspace_variance_ratio_from_gram   # noqa: F401
+from .utils import (discrepancy, ort_space, subspace_variance_ratio,   # noqa: F401
+                    subspace_variance_ratio_from_gram)
+from . import datasets                                        # noqa: F401
+
+SVDTransformer = GramEighTransformer      # the reference's name for the transformer this one replaces (edrgp/utils.py:81)

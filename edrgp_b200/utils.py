@@ -18,6 +18,27 @@ def subspace_variance_ratio_from_gram(C, V):
     return var, ratio
 
 
+def subspace_variance_ratio(X, V):
+    """The row form the reference exposes (``edrgp/utils.py:27-55``): X (n, d) gradients -- a host array or a CUDA
+    tensor holding this rank's rows -- and V (d, k).  The n-scale part, C = X^T X, is reduced on the device
+    (``edrgp_syrk``, summed over ranks); the rest is ``subspace_variance_ratio_from_gram``."""
+    from . import dist, ops
+    from .transformer import _rows_to_device
+    Xd = _rows_to_device(X)
+    d = Xd.shape[1]
+    C = ops.syrk(ops.pad_even(Xd))[:d, :d].contiguous()
+    dist.allreduce_sum_(C)
+    return subspace_variance_ratio_from_gram(C.cpu().numpy(), V)
+
+
+def ort_space(A, tol=1e-10):
+    """Orthonormal basis (n_features, n_features - rank) of the complement of span(A), A (n_features, k):
+    the left singular vectors behind the singular values above ``tol`` (``edrgp/utils.py:8-24``)."""
+    A = np.asarray(A, dtype=np.float64)
+    U, s, _ = np.linalg.svd(A, full_matrices=True)
+    return U[:, int(np.count_nonzero(np.abs(s) > tol)):]
+
+
 def discrepancy(B, V):
     """||B B^T (I - V V^T)||_F / d_true for a true projector basis B (n_features, d_true) and an
     estimated one V (n_features, k), as edrgp/utils.py:58-78."""
